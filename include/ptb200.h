@@ -1,0 +1,187 @@
+/*
+ * ptb200.h — C ABI of libptb200.so, the B200 (sm_100a) CUDA backend for the per-pixel
+ * render loop of MarkJulian19/path_trace_golang.
+ *
+ * This is the boundary the reference's Go code binds through cgo (INTEGRATION.md shows
+ * the binding).  It replaces, for the CPU hot path
+ *     engine.RenderInto(sc, cfg, img, progress)          internal/engine/renderer.go:34-41
+ *       -> renderIntoCPU                                  internal/engine/renderer.go:44-246
+ * exactly what the existing OpenGL plug-in replaces today
+ *     gpu.Render(sc, cfg, img, progress) error            internal/engine/gpu/gpu.go:2534-2546
+ * Plain pointers and sizes only; no C++/torch types.  All functions return PTB_OK (0) or a
+ * negative PTB_ERR_* code; ptb_last_error() gives the message.  There is NO CPU fallback:
+ * if CUDA is unavailable every call fails (the reference's GL path falls back to the CPU at
+ * renderer.go:257-262; this backend deliberately does not).
+ *
+ * Threading: a context renders one frame at a time (calls on one context are serialised by
+ * an internal mutex); any OS thread may call (cudaSetDevice is done per call), which is what
+ * a goroutine-per-render caller such as internal/ui/app.go:135 needs.
+ * Ownership: the library never keeps a host pointer after a call returns.
+ */
+#ifndef PTB200_H
+#define PTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB_ABI_VERSION 1
+
+enum {
+    PTB_OK = 0,
+    PTB_ERR_INVALID = -1,  /* bad argument (NULL, non-positive size, unknown code, ...) */
+    PTB_ERR_CUDA = -2,     /* CUDA runtime/driver error, message has the cudaError string */
+    PTB_ERR_NO_SCENE = -3, /* render called before ptb_scene_upload */
+    PTB_ERR_LIMIT = -4     /* scene exceeds a compiled-in limit (PTB_MAX_OBJECTS, ...) */
+};
+
+/* Object type codes — same values as the GL plug-in's OBJ_* (gpu.go:244-248).
+ * "sphere_light" is a sphere (objects.go:246-252).  Any other code: the object is dropped,
+ * like unknown types in sceneToWorld (objects.go:237-266). */
+enum { PTB_OBJ_SPHERE = 0, PTB_OBJ_PLANE = 1, PTB_OBJ_BOX = 2 };
+
+/* Material type codes — materialType iota (materials.go:11-17) == MAT_* (gpu.go:236-242).
+ * Any scene type string other than metal/dielectric/emissive/mirror maps to LAMBERT
+ * (default branch, materials.go:50-53). */
+enum { PTB_MAT_LAMBERT = 0, PTB_MAT_METAL = 1, PTB_MAT_DIELECTRIC = 2, PTB_MAT_EMISSIVE = 3, PTB_MAT_MIRROR = 4 };
+
+/* Limits of the analytic (constant-memory resident) world; the shipped scenes have <= 44 / 27. */
+#define PTB_MAX_OBJECTS 512
+#define PTB_MAX_MATERIALS 511
+
+/* scene.Camera (internal/scene/scene.go:23-32), raw fields; newCamera (camera.go:19-58)
+ * is evaluated inside the library in binary64 for the frame size of each render. */
+typedef struct {
+    double position[3], target[3], up[3];
+    double fov;          /* degrees, vertical */
+    double aperture;
+    double focus_dist;   /* 0 = |position - target| */
+    double aspect_ratio; /* 0 = width/height */
+} ptb_camera;
+
+/* Sky selection of renderIntoCPU (renderer.go:56-92), resolved by the caller:
+ * kind 1 (gradient) uses horizon/zenith; kind 0 uses color (= sky.color for a "solid" sky,
+ * else scene.background). */
+enum { PTB_SKY_CONST = 0, PTB_SKY_GRADIENT = 1 };
+typedef struct {
+    int32_t kind;
+    double color[3], horizon[3], zenith[3];
+} ptb_sky;
+
+/* Flattened scene, SoA, RAW scene.go fields: the library applies convertMaterial
+ * (materials.go:28-55) and the sceneToWorld geometry (objects.go:225-269: sphere radius =
+ * size.x, plane normal (0,1,0), box min/max = position -/+ size*0.5) itself, in binary64.
+ * obj_mat[i] is the index of the material whose id equals the object's material_id, where
+ * a later duplicate id wins (map semantics, objects.go:226-229); -1 = id not found = the
+ * zero material (black lambert). World index = index among kept objects, in array order. */
+typedef struct {
+    int32_t n_obj;
+    const int32_t* obj_type; /* [n_obj] PTB_OBJ_* (other values: dropped) */
+    const int32_t* obj_mat;  /* [n_obj] index into mat_* or -1 */
+    const double* obj_pos;   /* [n_obj*3] scene.Object.Position */
+    const double* obj_size;  /* [n_obj*3] scene.Object.Size */
+    int32_t n_mat;
+    const int32_t* mat_type;       /* [n_mat] PTB_MAT_* */
+    const double* mat_albedo;      /* [n_mat*3] */
+    const double* mat_rough;       /* [n_mat] */
+    const double* mat_ior;         /* [n_mat] */
+    const double* mat_emit;        /* [n_mat*3] (before * power) */
+    const double* mat_power;       /* [n_mat] */
+    const double* mat_absorption;  /* [n_mat*3] */
+    const double* mat_smoothness;  /* [n_mat] */
+    ptb_camera camera;
+    ptb_sky sky;
+} ptb_scene;
+
+/* engine.RenderConfig (renderer.go:17-22) + the extra knobs a GPU backend needs. */
+typedef struct {
+    int32_t width, height, samples_per_px, max_depth;
+    uint32_t seed;          /* key of the counter RNG; the reference seeds from the clock (random.go:14) */
+    int32_t sample_begin;   /* this context traces samples [sample_begin, sample_begin+sample_count) of    */
+    int32_t sample_count;   /* every pixel; sample_count <= 0 means all of [0, samples_per_px)            */
+    uint32_t flags;         /* PTB_FLAG_* */
+} ptb_cfg;
+
+#define PTB_FLAG_STATS 1u   /* run the counting variant of the integrator (slower); fills ptb_stats */
+
+typedef struct ptb_ctx ptb_ctx;
+
+/* progress callback, same role as `progress func()` of RenderInto (renderer.go:34):
+ * invoked on the calling thread after rgba has been refreshed with the samples so far. */
+typedef void (*ptb_progress_fn)(void* user);
+
+typedef struct {
+    uint64_t samples;     /* camera samples traced */
+    uint64_t segments;    /* closest-hit scans (renderer.go:297) */
+    uint64_t exit_scans;  /* dielectric exit searches (renderer.go:329) */
+    uint64_t accepts[3];  /* winning hits per primitive type */
+    uint64_t scatters;    /* scatter() == ok */
+    uint64_t end_sky, end_emissive, end_rr, end_depth, end_noscatter;
+    uint64_t lane_iters_active; /* integrator loop iterations with the lane alive           */
+    uint64_t lane_iters_total;  /* 32 x warp loop iterations (SIMT utilisation denominator) */
+    double last_render_ms;      /* device time of the last render call (CUDA events) */
+} ptb_stats;
+
+typedef struct {
+    char name[128];
+    int32_t sm_count, cc_major, cc_minor, clock_khz;
+    uint64_t global_mem_bytes;
+} ptb_device_info;
+
+/* Create a context on one CUDA device (one context per GPU; multi-GPU = one context per
+ * process/rank).  Fails with PTB_ERR_CUDA when no usable GPU exists. */
+int ptb_create(int device, ptb_ctx** out);
+void ptb_destroy(ptb_ctx* ctx);
+/* Message of the last failure on ctx (ctx may be NULL: last ptb_create failure of this thread). */
+const char* ptb_last_error(const ptb_ctx* ctx);
+int ptb_abi_version(void);
+int ptb_get_device_info(ptb_ctx* ctx, ptb_device_info* out);
+
+/* Copies and converts the scene (sceneToWorld + convertMaterial).  May be called again to
+ * replace the scene. */
+int ptb_scene_upload(ptb_ctx* ctx, const ptb_scene* scene);
+/* Converted world, for flatten parity tests: number of kept objects, and entry i as 19 doubles
+ * {type, mat_type, a[3], b[3], albedo[3], rough, ior, emit[3], absorption[3]}
+ * (a/b: sphere centre/(radius,0,0); plane point/normal; box min/max). */
+int ptb_world_size(ptb_ctx* ctx);
+int ptb_world_get(ptb_ctx* ctx, int i, double out[19]);
+
+/* The whole of renderIntoCPU (renderer.go:44-246) into a HOST image: rgba is height rows of
+ * `stride` bytes (stride >= 4*width), top row first, R,G,B,A=255 per pixel — the layout of
+ * image.RGBA.Pix/.Stride the caller of RenderInto owns.  progress may be NULL. */
+int ptb_render(ptb_ctx* ctx, const ptb_cfg* cfg, uint8_t* rgba, size_t stride,
+               ptb_progress_fn progress, void* user);
+
+/* Linear fp32 radiance sums (NOT divided by the sample count) of this context's sample range,
+ * width*height*3 floats, top row first — to a host buffer ... */
+int ptb_render_accum(ptb_ctx* ctx, const ptb_cfg* cfg, float* rgb_sum);
+/* ... or asynchronously into DEVICE memory on a caller-supplied CUDA stream (cudaStream_t as
+ * void*; NULL = the context's own stream).  This is what a multi-GPU caller reduces with NCCL. */
+int ptb_render_accum_device(ptb_ctx* ctx, const ptb_cfg* cfg, void* d_rgb_sum, void* stream);
+/* Pixel epilogue (renderer.go:189-221) on device buffers: mean over spp_total, sqrt, *255.999,
+ * clamp, truncate, A=255.  d_rgba: height*width*4 bytes, tightly packed. */
+int ptb_finalize_device(ptb_ctx* ctx, const void* d_rgb_sum, int32_t width, int32_t height,
+                        int32_t spp_total, void* d_rgba, void* stream);
+/* Fused render + epilogue into a DEVICE RGBA8 image (no host copies; stream as above). */
+int ptb_render_device(ptb_ctx* ctx, const ptb_cfg* cfg, void* d_rgba, void* stream);
+
+/* Parity hook: closest hit of the primary ray through (x+xi_u, y+xi_v) of every pixel with the
+ * lens disabled (camera.go:70-73), computed in binary64 with the reference's operation order
+ * and no FMA contraction.  ids: world index or -1; t: ray parameter (0 on miss). Host buffers. */
+int ptb_primary_hits(ptb_ctx* ctx, const ptb_cfg* cfg, double xi_u, double xi_v,
+                     int32_t* ids, double* t);
+
+/* Counters of the last render that ran with PTB_FLAG_STATS (last_render_ms is always valid). */
+int ptb_get_stats(ptb_ctx* ctx, ptb_stats* out);
+
+/* Measurement helper: FP32 FMA throughput of the device (2 flop per FMA), the roofline
+ * denominator MEASURED_PEAKS.json does not carry. */
+int ptb_measure_fp32_peak(ptb_ctx* ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTB200_H */

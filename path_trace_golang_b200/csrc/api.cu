@@ -1,0 +1,560 @@
+// api.cu — the C ABI of include/ptb200.h: context, scene conversion (sceneToWorld + convertMaterial +
+// newCamera, all in binary64 on the host exactly as the reference does them), and the render entry points.
+//
+// No CPU fallback exists anywhere in this file: every path either launches the CUDA kernels or returns an
+// error (the reference's GL plug-in falls back to the CPU, renderer.go:257-262 — this backend must not).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "scene_dev.h"
+
+using namespace ptb;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct World64Entry {   // result of sceneToWorld + convertMaterial, binary64 (objects.go:225-269, materials.go:28-55)
+    int type, mat_type;
+    double a[3], b[3];
+    double albedo[3], rough, ior, emit[3], absorption[3];
+    int mat_slot;       // index into the device material table
+};
+
+}  // namespace
+
+struct ptb_ctx {
+    int device = 0;
+    std::mutex mu;
+    std::string err;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaDeviceProp prop{};
+
+    bool has_scene = false;
+    ptb_camera cam{};
+    std::vector<World64Entry> world;
+    DevScene* h_scene = nullptr;        // pinned
+    uint4* d_blob = nullptr;            // obj[] then mat[] (global copy for the smem fill)
+    size_t blob_words = 0;
+    Obj64* d_world64 = nullptr;
+
+    // scratch device buffers, grown on demand
+    float* d_accum = nullptr; size_t accum_cap = 0;
+    uint8_t* d_rgba = nullptr; size_t rgba_cap = 0;
+    uint8_t* h_rgba = nullptr; size_t h_rgba_cap = 0;   // pinned staging for ptb_render
+    unsigned long long* d_stats = nullptr;
+    ptb_stats stats{};
+};
+
+namespace {
+
+int fail(ptb_ctx* c, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf; else g_create_error = buf;
+    return code;
+}
+#define CK(c, call)                                                                                     \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess) return fail((c), PTB_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }   // materials.go:57-65
+
+// convertMaterial, materials.go:28-55
+void convert_material(const ptb_scene* s, int i, World64Entry& w) {
+    const double al[3] = {s->mat_albedo[3 * i], s->mat_albedo[3 * i + 1], s->mat_albedo[3 * i + 2]};
+    const double power = s->mat_power[i];
+    const double em[3] = {s->mat_emit[3 * i] * power, s->mat_emit[3 * i + 1] * power, s->mat_emit[3 * i + 2] * power};
+    w.rough = 0; w.ior = 0;
+    for (int k = 0; k < 3; k++) { w.albedo[k] = 0; w.emit[k] = 0; w.absorption[k] = 0; }
+    switch (s->mat_type[i]) {
+    case PTB_MAT_METAL: {
+        double rough = s->mat_rough[i];
+        if (s->mat_smoothness[i] > 0) rough = 1.0 - clampd(s->mat_smoothness[i], 0, 1);
+        w.mat_type = PTB_MAT_METAL;
+        for (int k = 0; k < 3; k++) w.albedo[k] = al[k];
+        w.rough = clampd(rough, 0, 1);
+        break;
+    }
+    case PTB_MAT_DIELECTRIC: {
+        double ior = s->mat_ior[i];
+        if (ior == 0) ior = 1.5;
+        w.mat_type = PTB_MAT_DIELECTRIC;
+        for (int k = 0; k < 3; k++) { w.albedo[k] = al[k]; w.absorption[k] = s->mat_absorption[3 * i + k]; }
+        w.ior = ior;
+        break;
+    }
+    case PTB_MAT_EMISSIVE:
+        w.mat_type = PTB_MAT_EMISSIVE;
+        for (int k = 0; k < 3; k++) w.emit[k] = em[k];
+        break;
+    case PTB_MAT_MIRROR:
+        w.mat_type = PTB_MAT_MIRROR;
+        for (int k = 0; k < 3; k++) w.albedo[k] = al[k];
+        break;
+    default:
+        w.mat_type = PTB_MAT_LAMBERT;
+        for (int k = 0; k < 3; k++) w.albedo[k] = al[k];
+        w.rough = clampd(s->mat_rough[i], 0, 1);
+        break;
+    }
+}
+
+struct Cam64 { double origin[3], llc[3], horizontal[3], vertical[3], u[3], v[3], w[3], lens_radius; };
+
+// newCamera, camera.go:19-58 (vec3 helpers of math.go:11-37 written out; div multiplies by the reciprocal)
+Cam64 new_camera(const ptb_camera& c, int width, int height) {
+    auto sub = [](const double* a, const double* b, double* o) { for (int k = 0; k < 3; k++) o[k] = a[k] - b[k]; };
+    auto dot = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    auto cross = [](const double* a, const double* b, double* o) {
+        o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    auto unit = [&](double* a) {
+        double l = std::sqrt(dot(a, a));
+        if (l == 0) return;
+        double inv = 1.0 / l;
+        for (int k = 0; k < 3; k++) a[k] = a[k] * inv;
+    };
+    Cam64 r{};
+    double aspect = (double)width / (double)height;
+    if (c.aspect_ratio != 0) aspect = c.aspect_ratio;
+    double theta = c.fov * M_PI / 180;
+    double h = std::tan(theta / 2);
+    double vh = 2.0 * h, vw = aspect * vh;
+    for (int k = 0; k < 3; k++) r.origin[k] = c.position[k];
+    double ot[3];
+    sub(c.position, c.target, ot);
+    for (int k = 0; k < 3; k++) r.w[k] = ot[k];
+    unit(r.w);
+    cross(c.up, r.w, r.u);
+    unit(r.u);
+    cross(r.w, r.u, r.v);
+    double focus = c.focus_dist;
+    if (focus == 0) focus = std::sqrt(dot(ot, ot));
+    const double inv2 = 1.0 / 2.0;
+    for (int k = 0; k < 3; k++) {
+        r.horizontal[k] = r.u[k] * (vw * focus);
+        r.vertical[k] = r.v[k] * (vh * focus);
+    }
+    for (int k = 0; k < 3; k++)
+        r.llc[k] = r.origin[k] - r.horizontal[k] * inv2 - r.vertical[k] * inv2 - r.w[k] * focus;
+    r.lens_radius = c.aperture / 2;
+    return r;
+}
+
+int ensure(ptb_ctx* c, void** p, size_t* cap, size_t need, bool pinned_host = false) {
+    if (*cap >= need && *p) return PTB_OK;
+    if (*p) { if (pinned_host) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cap = 0; }
+    if (pinned_host) CK(c, cudaMallocHost(p, need)); else CK(c, cudaMalloc(p, need));
+    *cap = need;
+    return PTB_OK;
+}
+
+int check_cfg(ptb_ctx* c, const ptb_cfg* cfg, int& s0, int& s1) {
+    if (!cfg) return fail(c, PTB_ERR_INVALID, "cfg is NULL");
+    if (cfg->width < 2 || cfg->height < 2)   // 1/(W-1), 1/(H-1) (renderer.go:95-96) need W,H >= 2
+        return fail(c, PTB_ERR_INVALID, "width and height must be >= 2 (got %dx%d)", cfg->width, cfg->height);
+    if ((long long)cfg->width * cfg->height > (1ll << 30)) return fail(c, PTB_ERR_LIMIT, "frame too large");
+    if (cfg->samples_per_px < 1) return fail(c, PTB_ERR_INVALID, "samples_per_px must be >= 1");
+    s0 = 0; s1 = cfg->samples_per_px;
+    if (cfg->sample_count > 0) {
+        s0 = cfg->sample_begin; s1 = cfg->sample_begin + cfg->sample_count;
+        if (s0 < 0 || s1 > cfg->samples_per_px)
+            return fail(c, PTB_ERR_INVALID, "sample range [%d,%d) outside [0,%d)", s0, s1, cfg->samples_per_px);
+    }
+    if (!c->has_scene) return fail(c, PTB_ERR_NO_SCENE, "no scene uploaded");
+    return PTB_OK;
+}
+
+uint32_t fmix_host(uint32_t x) { x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15; return x; }
+
+// Launch the integrator for cfg's sample range on `stream`. accum/rgba are device pointers (either may be NULL).
+int render_launch(ptb_ctx* c, const ptb_cfg* cfg, int s0, int s1, float* d_accum, uint8_t* d_rgba, cudaStream_t stream,
+                  bool resume = false) {
+    const int W = cfg->width, H = cfg->height;
+    // camera for this frame size (newCamera is per render in the reference too, renderer.go:168)
+    Cam64 cam = new_camera(c->cam, W, H);
+    DevCamera& dc = c->h_scene->cam;
+    for (int k = 0; k < 3; k++) {
+        dc.origin[k] = (float)cam.origin[k]; dc.llc[k] = (float)cam.llc[k];
+        dc.horizontal[k] = (float)cam.horizontal[k]; dc.vertical[k] = (float)cam.vertical[k];
+        dc.u[k] = (float)cam.u[k]; dc.v[k] = (float)cam.v[k];
+    }
+    dc.lens_radius = (float)cam.lens_radius;
+    int e = upload_scene_constants(*c->h_scene, stream);
+    if (e) return fail(c, PTB_ERR_CUDA, "constant upload: %s", cudaGetErrorString((cudaError_t)e));
+
+    const bool stats = (cfg->flags & PTB_FLAG_STATS) != 0;
+    if (stats) CK(c, cudaMemsetAsync(c->d_stats, 0, sizeof(unsigned long long) * kStatsWords, stream));
+
+    FrameParams fp{};
+    fp.width = W; fp.height = H; fp.s_begin = s0; fp.s_end = s1;
+    fp.spp_total = cfg->samples_per_px; fp.max_depth = cfg->max_depth;
+    fp.seed_key = fmix_host(cfg->seed ^ 0x9E3779B9u);
+    fp.inv_w = 1.0f / (float)(W - 1); fp.inv_h = 1.0f / (float)(H - 1); fp.h_minus_1 = (float)(H - 1);
+    fp.scene_blob = c->d_blob; fp.accum = d_accum; fp.accum_resume = resume ? 1 : 0; fp.rgba = d_rgba; fp.stats = stats ? c->d_stats : nullptr;
+    e = launch_integrator(fp, stats, c->h_scene->n_obj, c->h_scene->n_mat, stream);
+    if (e) return fail(c, PTB_ERR_CUDA, "integrator launch: %s", cudaGetErrorString((cudaError_t)e));
+    return PTB_OK;
+}
+
+int fetch_stats(ptb_ctx* c, bool stats, float ms) {
+    c->stats.last_render_ms = ms;
+    if (!stats) return PTB_OK;
+    unsigned long long w[kStatsWords];
+    CK(c, cudaMemcpy(w, c->d_stats, sizeof w, cudaMemcpyDeviceToHost));
+    ptb_stats& s = c->stats;
+    s.samples = w[ST_SAMPLES]; s.segments = w[ST_SEGMENTS]; s.exit_scans = w[ST_EXIT_SCANS];
+    s.accepts[0] = w[ST_ACC_SPHERE]; s.accepts[1] = w[ST_ACC_PLANE]; s.accepts[2] = w[ST_ACC_BOX];
+    s.scatters = w[ST_SCATTERS]; s.end_sky = w[ST_END_SKY]; s.end_emissive = w[ST_END_EMISSIVE];
+    s.end_rr = w[ST_END_RR]; s.end_depth = w[ST_END_DEPTH]; s.end_noscatter = w[ST_END_NOSCATTER];
+    s.lane_iters_active = w[ST_LANE_ACTIVE]; s.lane_iters_total = w[ST_LANE_TOTAL];
+    return PTB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ptb_abi_version(void) { return PTB_ABI_VERSION; }
+
+int ptb_create(int device, ptb_ctx** out) {
+    if (!out) return fail(nullptr, PTB_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return fail(nullptr, PTB_ERR_CUDA, "cudaGetDeviceCount: %s (no CPU fallback exists)", cudaGetErrorString(e));
+    if (device < 0 || device >= n) return fail(nullptr, PTB_ERR_INVALID, "device %d out of range (%d CUDA devices)", device, n);
+    ptb_ctx* c = new ptb_ctx();
+    c->device = device;
+    auto bail = [&](const char* what, cudaError_t err) {
+        int rc = fail(nullptr, PTB_ERR_CUDA, "%s: %s", what, cudaGetErrorString(err));
+        delete c;
+        return rc;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    if ((e = cudaGetDeviceProperties(&c->prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    if (c->prop.major < 10) {
+        int rc = fail(nullptr, PTB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, c->prop.major, c->prop.minor);
+        delete c;
+        return rc;
+    }
+    if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
+    if ((e = cudaMallocHost((void**)&c->h_scene, sizeof(DevScene))) != cudaSuccess) return bail("cudaMallocHost", e);
+    std::memset(c->h_scene, 0, sizeof(DevScene));
+    if ((e = cudaMalloc((void**)&c->d_stats, sizeof(unsigned long long) * kStatsWords)) != cudaSuccess) return bail("cudaMalloc", e);
+    *out = c;
+    return PTB_OK;
+}
+
+void ptb_destroy(ptb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_blob); cudaFree(c->d_world64); cudaFree(c->d_accum); cudaFree(c->d_rgba); cudaFree(c->d_stats);
+    if (c->h_scene) cudaFreeHost(c->h_scene);
+    if (c->h_rgba) cudaFreeHost(c->h_rgba);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* ptb_last_error(const ptb_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int ptb_get_device_info(ptb_ctx* c, ptb_device_info* out) {
+    if (!c || !out) return fail(c, PTB_ERR_INVALID, "NULL argument");
+    std::memset(out, 0, sizeof *out);
+    std::snprintf(out->name, sizeof out->name, "%.127s", c->prop.name);
+    out->sm_count = c->prop.multiProcessorCount; out->cc_major = c->prop.major; out->cc_minor = c->prop.minor;
+    int khz = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+    out->clock_khz = khz;
+    out->global_mem_bytes = c->prop.totalGlobalMem;
+    return PTB_OK;
+}
+
+int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
+    if (!c) return PTB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!s) return fail(c, PTB_ERR_INVALID, "scene is NULL");
+    if (s->n_obj < 0 || s->n_mat < 0) return fail(c, PTB_ERR_INVALID, "negative counts");
+    if (s->n_obj > 0 && (!s->obj_type || !s->obj_mat || !s->obj_pos || !s->obj_size)) return fail(c, PTB_ERR_INVALID, "object arrays are NULL");
+    if (s->n_mat > 0 && (!s->mat_type || !s->mat_albedo || !s->mat_rough || !s->mat_ior || !s->mat_emit || !s->mat_power ||
+                         !s->mat_absorption || !s->mat_smoothness)) return fail(c, PTB_ERR_INVALID, "material arrays are NULL");
+    if (s->n_mat > PTB_MAX_MATERIALS) return fail(c, PTB_ERR_LIMIT, "%d materials > PTB_MAX_MATERIALS=%d", s->n_mat, PTB_MAX_MATERIALS);
+    CK(c, cudaSetDevice(c->device));
+
+    // materials (convertMaterial) + the zero material in slot n_mat (objects.go:234: missing map key)
+    std::vector<World64Entry> mats(s->n_mat + 1);
+    for (int i = 0; i < s->n_mat; i++) convert_material(s, i, mats[i]);
+    {
+        World64Entry& z = mats[s->n_mat];
+        std::memset(&z, 0, sizeof z);
+        z.mat_type = PTB_MAT_LAMBERT;
+    }
+    // objects (sceneToWorld)
+    std::vector<World64Entry> world;
+    for (int i = 0; i < s->n_obj; i++) {
+        const int t = s->obj_type[i];
+        if (t != PTB_OBJ_SPHERE && t != PTB_OBJ_PLANE && t != PTB_OBJ_BOX) continue;   // dropped (objects.go:237-266)
+        int mi = s->obj_mat[i];
+        if (mi >= s->n_mat) return fail(c, PTB_ERR_INVALID, "obj_mat[%d]=%d out of range", i, mi);
+        if (mi < 0) mi = s->n_mat;
+        World64Entry w = mats[mi];
+        w.mat_slot = mi;
+        w.type = t;
+        const double* pos = s->obj_pos + 3 * i;
+        const double* size = s->obj_size + 3 * i;
+        if (t == PTB_OBJ_SPHERE) { for (int k = 0; k < 3; k++) { w.a[k] = pos[k]; w.b[k] = 0; } w.b[0] = size[0]; }
+        else if (t == PTB_OBJ_PLANE) { for (int k = 0; k < 3; k++) w.a[k] = pos[k]; w.b[0] = 0; w.b[1] = 1; w.b[2] = 0; }
+        else { for (int k = 0; k < 3; k++) { w.a[k] = pos[k] - size[k] * 0.5; w.b[k] = pos[k] + size[k] * 0.5; } }
+        world.push_back(w);
+    }
+    if ((int)world.size() > PTB_MAX_OBJECTS) return fail(c, PTB_ERR_LIMIT, "%zu objects > PTB_MAX_OBJECTS=%d", world.size(), PTB_MAX_OBJECTS);
+
+    // binary32 device tables
+    DevScene& hs = *c->h_scene;
+    hs.n_obj = (int)world.size(); hs.n_mat = s->n_mat + 1; hs.n_diel = 0;
+    for (int i = 0; i < hs.n_mat; i++) {
+        DevMat& m = hs.mat[i];
+        const World64Entry& w = mats[i];
+        m.type = w.mat_type; m.rough = (float)w.rough; m.ior = (float)w.ior;
+        for (int k = 0; k < 3; k++) { m.albedo[k] = (float)w.albedo[k]; m.emit[k] = (float)w.emit[k]; m.absorption[k] = (float)w.absorption[k]; }
+    }
+    std::vector<Obj64> w64(world.size());
+    for (int i = 0; i < hs.n_obj; i++) {
+        const World64Entry& w = world[i];
+        DevObj& o = hs.obj[i];
+        o.ax = (float)w.a[0]; o.ay = (float)w.a[1]; o.az = (float)w.a[2];
+        if (w.type == PTB_OBJ_SPHERE) {
+            float r = (float)w.b[0];
+            o.bx = r; o.by = r * r; o.bz = 1.0f / r;    // radiusSq (objects.go:46), invRadius (objects.go:68)
+        } else { o.bx = (float)w.b[0]; o.by = (float)w.b[1]; o.bz = (float)w.b[2]; }
+        o.type_mat = w.type | (w.mat_slot << 2);
+        o.is_diel = w.mat_type == PTB_MAT_DIELECTRIC;
+        if (o.is_diel) hs.diel_idx[hs.n_diel++] = i;
+        w64[i].type = w.type; w64[i].pad = 0;
+        for (int k = 0; k < 3; k++) { w64[i].a[k] = w.a[k]; w64[i].b[k] = w.b[k]; }
+    }
+    hs.sky.kind = s->sky.kind == PTB_SKY_GRADIENT ? PTB_SKY_GRADIENT : PTB_SKY_CONST;
+    for (int k = 0; k < 3; k++) { hs.sky.color[k] = (float)s->sky.color[k]; hs.sky.horizon[k] = (float)s->sky.horizon[k]; hs.sky.zenith[k] = (float)s->sky.zenith[k]; }
+
+    // global copies
+    const size_t words = (size_t)hs.n_obj * 2 + (size_t)hs.n_mat * 3;
+    cudaFree(c->d_blob); c->d_blob = nullptr;
+    cudaFree(c->d_world64); c->d_world64 = nullptr;
+    CK(c, cudaMalloc((void**)&c->d_blob, words * sizeof(uint4)));
+    CK(c, cudaMemcpy(c->d_blob, hs.obj, (size_t)hs.n_obj * sizeof(DevObj), cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(c->d_blob + (size_t)hs.n_obj * 2, hs.mat, (size_t)hs.n_mat * sizeof(DevMat), cudaMemcpyHostToDevice));
+    c->blob_words = words;
+    CK(c, cudaMalloc((void**)&c->d_world64, sizeof(Obj64) * (w64.size() + 1)));
+    if (!w64.empty()) CK(c, cudaMemcpy(c->d_world64, w64.data(), sizeof(Obj64) * w64.size(), cudaMemcpyHostToDevice));
+
+    c->world = world;
+    c->cam = s->camera;
+    c->has_scene = true;
+    return PTB_OK;
+}
+
+int ptb_world_size(ptb_ctx* c) { return c && c->has_scene ? (int)c->world.size() : PTB_ERR_NO_SCENE; }
+
+int ptb_world_get(ptb_ctx* c, int i, double out[19]) {
+    if (!c || !out) return PTB_ERR_INVALID;
+    if (!c->has_scene) return fail(c, PTB_ERR_NO_SCENE, "no scene uploaded");
+    if (i < 0 || i >= (int)c->world.size()) return fail(c, PTB_ERR_INVALID, "index out of range");
+    const World64Entry& w = c->world[i];
+    int k = 0;
+    out[k++] = w.type; out[k++] = w.mat_type;
+    for (int j = 0; j < 3; j++) out[k++] = w.a[j];
+    for (int j = 0; j < 3; j++) out[k++] = w.b[j];
+    for (int j = 0; j < 3; j++) out[k++] = w.albedo[j];
+    out[k++] = w.rough; out[k++] = w.ior;
+    for (int j = 0; j < 3; j++) out[k++] = w.emit[j];
+    for (int j = 0; j < 3; j++) out[k++] = w.absorption[j];
+    return PTB_OK;
+}
+
+int ptb_render_accum_device(ptb_ctx* c, const ptb_cfg* cfg, void* d_rgb_sum, void* stream) {
+    if (!c) return PTB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    int s0 = 0, s1 = 0, rc;
+    if ((rc = check_cfg(c, cfg, s0, s1))) return rc;
+    if (!d_rgb_sum) return fail(c, PTB_ERR_INVALID, "d_rgb_sum is NULL");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    if ((rc = render_launch(c, cfg, s0, s1, (float*)d_rgb_sum, nullptr, st))) return rc;
+    if (cfg->flags & PTB_FLAG_STATS) { CK(c, cudaStreamSynchronize(st)); return fetch_stats(c, true, 0.f); }
+    return PTB_OK;
+}
+
+int ptb_render_device(ptb_ctx* c, const ptb_cfg* cfg, void* d_rgba, void* stream) {
+    if (!c) return PTB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    int s0 = 0, s1 = 0, rc;
+    if ((rc = check_cfg(c, cfg, s0, s1))) return rc;
+    if (!d_rgba) return fail(c, PTB_ERR_INVALID, "d_rgba is NULL");
+    if (s0 != 0 || s1 != cfg->samples_per_px) return fail(c, PTB_ERR_INVALID, "ptb_render_device needs the full sample range");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    if ((rc = render_launch(c, cfg, s0, s1, nullptr, (uint8_t*)d_rgba, st))) return rc;
+    if (cfg->flags & PTB_FLAG_STATS) { CK(c, cudaStreamSynchronize(st)); return fetch_stats(c, true, 0.f); }
+    return PTB_OK;
+}
+
+int ptb_finalize_device(ptb_ctx* c, const void* d_rgb_sum, int32_t width, int32_t height, int32_t spp_total, void* d_rgba, void* stream) {
+    if (!c) return PTB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!d_rgb_sum || !d_rgba || width < 1 || height < 1 || spp_total < 1) return fail(c, PTB_ERR_INVALID, "bad argument");
+    CK(c, cudaSetDevice(c->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    int e = launch_finalize((const float*)d_rgb_sum, width, height, spp_total, (uint8_t*)d_rgba, st);
+    if (e) return fail(c, PTB_ERR_CUDA, "finalize launch: %s", cudaGetErrorString((cudaError_t)e));
+    return PTB_OK;
+}
+
+int ptb_render_accum(ptb_ctx* c, const ptb_cfg* cfg, float* rgb_sum) {
+    if (!c) return PTB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    int s0 = 0, s1 = 0, rc;
+    if ((rc = check_cfg(c, cfg, s0, s1))) return rc;
+    if (!rgb_sum) return fail(c, PTB_ERR_INVALID, "rgb_sum is NULL");
+    CK(c, cudaSetDevice(c->device));
+    const size_t bytes = (size_t)cfg->width * cfg->height * 3 * sizeof(float);
+    if ((rc = ensure(c, (void**)&c->d_accum, &c->accum_cap, bytes))) return rc;
+    CK(c, cudaEventRecord(c->ev0, c->stream));
+    if ((rc = render_launch(c, cfg, s0, s1, c->d_accum, nullptr, c->stream))) return rc;
+    CK(c, cudaEventRecord(c->ev1, c->stream));
+    CK(c, cudaMemcpyAsync(rgb_sum, c->d_accum, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    return fetch_stats(c, (cfg->flags & PTB_FLAG_STATS) != 0, ms);
+}
+
+int ptb_render(ptb_ctx* c, const ptb_cfg* cfg, uint8_t* rgba, size_t stride, ptb_progress_fn progress, void* user) {
+    if (!c) return PTB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    int s0 = 0, s1 = 0, rc;
+    if ((rc = check_cfg(c, cfg, s0, s1))) return rc;
+    if (!rgba) return fail(c, PTB_ERR_INVALID, "rgba is NULL");
+    const int W = cfg->width, H = cfg->height;
+    if (stride < (size_t)W * 4) return fail(c, PTB_ERR_INVALID, "stride %zu < 4*width", stride);
+    if (s0 != 0 || s1 != cfg->samples_per_px) return fail(c, PTB_ERR_INVALID, "ptb_render needs the full sample range (use ptb_render_accum*)");
+    CK(c, cudaSetDevice(c->device));
+    const size_t img_bytes = (size_t)W * H * 4;
+    if ((rc = ensure(c, (void**)&c->d_rgba, &c->rgba_cap, img_bytes))) return rc;
+    if ((rc = ensure(c, (void**)&c->h_rgba, &c->h_rgba_cap, img_bytes, true))) return rc;
+    auto copy_out = [&]() -> int {
+        CK(c, cudaMemcpyAsync(c->h_rgba, c->d_rgba, img_bytes, cudaMemcpyDeviceToHost, c->stream));
+        CK(c, cudaStreamSynchronize(c->stream));
+        if (stride == (size_t)W * 4) std::memcpy(rgba, c->h_rgba, img_bytes);
+        else for (int y = 0; y < H; y++) std::memcpy(rgba + (size_t)y * stride, c->h_rgba + (size_t)y * W * 4, (size_t)W * 4);
+        return PTB_OK;
+    };
+    CK(c, cudaEventRecord(c->ev0, c->stream));
+    if (!progress || cfg->max_depth <= 0) {
+        // one fused launch: integrate + pixel epilogue, 4 bytes per pixel written once
+        if ((rc = render_launch(c, cfg, s0, s1, nullptr, c->d_rgba, c->stream))) return rc;
+        CK(c, cudaEventRecord(c->ev1, c->stream));
+        if ((rc = copy_out())) return rc;
+    } else {
+        // progressive: ~10 sample batches, image refreshed and progress() called after each — the cadence of
+        // the reference back-ends (every ~5 % of tiles renderer.go:226-235; every spp/10 passes gpu.go:2209-2229).
+        // Partial images show the mean of the samples so far.  The fp32 sums are carried in d_accum.
+        const size_t acc_bytes = (size_t)W * H * 3 * sizeof(float);
+        if ((rc = ensure(c, (void**)&c->d_accum, &c->accum_cap, acc_bytes))) return rc;
+        const int spp = cfg->samples_per_px;
+        const int batch = spp >= 10 ? (spp + 9) / 10 : 1;
+        ptb_cfg sub = *cfg;
+        sub.flags &= ~PTB_FLAG_STATS;
+        for (int b0 = 0; b0 < spp; b0 += batch) {
+            const int b1 = b0 + batch < spp ? b0 + batch : spp;
+            // each launch resumes the per-pixel sums where the previous one stopped (same order as one launch)
+            // and writes the epilogue of the mean over the b1 samples so far
+            sub.samples_per_px = b1;
+            if ((rc = render_launch(c, &sub, b0, b1, c->d_accum, c->d_rgba, c->stream, /*resume=*/b0 > 0))) return rc;
+            if (b1 == spp) CK(c, cudaEventRecord(c->ev1, c->stream));
+            if ((rc = copy_out())) return rc;
+            progress(user);
+        }
+        progress(user);   // final refresh, renderer.go:243-245
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    return fetch_stats(c, (cfg->flags & PTB_FLAG_STATS) != 0 && !progress, ms);
+}
+
+int ptb_primary_hits(ptb_ctx* c, const ptb_cfg* cfg, double xi_u, double xi_v, int32_t* ids, double* t) {
+    if (!c) return PTB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!cfg || cfg->width < 2 || cfg->height < 2) return fail(c, PTB_ERR_INVALID, "width and height must be >= 2");
+    if (!c->has_scene) return fail(c, PTB_ERR_NO_SCENE, "no scene uploaded");
+    if (!ids || !t) return fail(c, PTB_ERR_INVALID, "ids/t is NULL");
+    CK(c, cudaSetDevice(c->device));
+    const int W = cfg->width, H = cfg->height;
+    const size_t n = (size_t)W * H;
+    int32_t* d_ids = nullptr; double* d_t = nullptr;
+    CK(c, cudaMalloc((void**)&d_ids, n * sizeof(int32_t)));
+    if (cudaMalloc((void**)&d_t, n * sizeof(double)) != cudaSuccess) { cudaFree(d_ids); return fail(c, PTB_ERR_CUDA, "cudaMalloc failed"); }
+    Cam64 cam = new_camera(c->cam, W, H);
+    Camera64 dc;
+    for (int k = 0; k < 3; k++) { dc.origin[k] = cam.origin[k]; dc.llc[k] = cam.llc[k]; dc.horizontal[k] = cam.horizontal[k]; dc.vertical[k] = cam.vertical[k]; }
+    int e = launch_primary_hits(c->d_world64, (int)c->world.size(), dc, W, H, xi_u, xi_v, d_ids, d_t, c->stream);
+    cudaError_t ce = (cudaError_t)e;
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(ids, d_ids, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(t, d_t, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+    cudaFree(d_ids); cudaFree(d_t);
+    if (ce != cudaSuccess) return fail(c, PTB_ERR_CUDA, "primary hits: %s", cudaGetErrorString(ce));
+    return PTB_OK;
+}
+
+int ptb_get_stats(ptb_ctx* c, ptb_stats* out) {
+    if (!c || !out) return PTB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    *out = c->stats;
+    return PTB_OK;
+}
+
+int ptb_measure_fp32_peak(ptb_ctx* c, double* tflops) {
+    if (!c || !tflops) return PTB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(c, cudaSetDevice(c->device));
+    const int threads = 256, blocks = c->prop.multiProcessorCount * 8, iters = 4096;
+    float* d = nullptr;
+    CK(c, cudaMalloc((void**)&d, sizeof(float) * threads * blocks));
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        cudaEventRecord(c->ev0, c->stream);
+        int e = launch_fma_peak(d, blocks, threads, iters, c->stream);
+        cudaEventRecord(c->ev1, c->stream);
+        cudaError_t ce = e ? (cudaError_t)e : cudaStreamSynchronize(c->stream);
+        if (ce != cudaSuccess) { cudaFree(d); return fail(c, PTB_ERR_CUDA, "fma probe: %s", cudaGetErrorString(ce)); }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        double flops = 2.0 * 64.0 * (double)iters * threads * blocks;   // 8 chains x 8 unrolled FMAs per iteration
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaFree(d);
+    *tflops = best;
+    return PTB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,481 @@
+// integrator.cu — the per-pixel render loop of internal/engine (renderer.go:163-238 + 286-404) as one
+// persistent-lane sm_100a megakernel.
+//
+// Mapping (DESIGN.md "Integrator kernel"):
+//   * one lane = one pixel; it walks that pixel's samples [s_begin, s_end) in order and keeps the fp32
+//     radiance sum in registers, so the per-pixel sum order is the reference's (renderer.go:181-187) and
+//     no atomics / HBM accumulation traffic exist;
+//   * one warp = an 8x4 pixel tile, one CTA = 16x8 pixels (coherent primary rays per warp);
+//   * rayColorOpt's recursion (renderer.go:286-404) is run iteratively (throughput beta, radiance L);
+//     when a lane's path ends it immediately regenerates the next camera sample of its pixel, so lanes of
+//     a warp are at different bounces of different samples but all of them execute the same closest-hit
+//     scan over the world, which is where the time goes (renderer.go:297-302);
+//   * the warp leaves the loop on a ballot (__any_sync) when every lane has finished its samples;
+//   * the scan indexes the world in __constant__ memory with a warp-uniform index (broadcast); the winning
+//     object and its material are fetched from a shared-memory copy (divergent index).
+//
+// Semantics are the reference's, quirks included: un-normalised primary rays,
+// tMin=0.001 in ray-parameter units, inclusive tMax for spheres/planes (later object wins ties) and
+// exclusive for boxes, box hit from inside returns t=tMin with the nearest-face normal, dielectric exit
+// search without refraction on exit, Russian roulette on the REMAINING depth <= 3.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "scene_dev.h"
+
+namespace ptb {
+
+__constant__ DevScene c_scene;
+
+#ifndef PTB_BLOCK_THREADS
+#define PTB_BLOCK_THREADS 128
+#endif
+#ifndef PTB_MIN_BLOCKS
+#define PTB_MIN_BLOCKS 8
+#endif
+
+constexpr uint32_t kGolden = 0x9E3779B9u;
+
+// ---- counter RNG (DESIGN.md "RNG"); stands in for randSource.Float64 (random.go:27-34)
+__device__ __forceinline__ uint32_t fmix(uint32_t x) {
+    x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
+    return x;
+}
+struct Rng {
+    uint32_t key, ctr;
+    __device__ __forceinline__ float next() {
+        uint32_t x = fmix(key + ctr * kGolden);
+        ++ctr;
+        return (float)(x >> 8) * (1.0f / 16777216.0f);
+    }
+};
+
+struct F3 { float x, y, z; };
+__device__ __forceinline__ F3 f3(float x, float y, float z) { return F3{x, y, z}; }
+__device__ __forceinline__ float dot3(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }   // math.go:19
+__device__ __forceinline__ F3 unit3(F3 a) {                                                       // math.go:31-37, 14-17
+    float l = sqrtf(dot3(a, a));
+    if (l == 0.0f) return a;
+    float inv = 1.0f / l;
+    return f3(a.x * inv, a.y * inv, a.z * inv);
+}
+__device__ __forceinline__ F3 reflect3(F3 v, F3 n) {                                              // math.go:39-46
+    float d = dot3(v, n);
+    return f3(v.x - n.x * 2.0f * d, v.y - n.y * 2.0f * d, v.z - n.z * 2.0f * d);
+}
+__device__ __forceinline__ F3 in_unit_sphere(Rng& rng) {                                          // math.go:66-85
+    for (;;) {
+        float x = rng.next() * 2.0f - 1.0f;
+        float y = rng.next() * 2.0f - 1.0f;
+        float z = rng.next() * 2.0f - 1.0f;
+        if (x * x + y * y + z * z >= 1.0f) continue;
+        return f3(x, y, z);
+    }
+}
+__device__ __forceinline__ F3 cosine_direction(F3 n, Rng& rng) {                                  // math.go:94-131
+    float r1 = rng.next();
+    float r2 = rng.next();
+    float phi = 6.28318530717958647692f * r1;
+    float ct = sqrtf(r2);
+    float st = sqrtf(1.0f - r2);
+    // v = unit(n x helper), u = v x n with helper = (0,1,0) if |n.x| > 0.9 else (1,0,0)
+    F3 v = (fabsf(n.x) > 0.9f) ? f3(-n.z, 0.0f, n.x) : f3(0.0f, n.z, -n.y);
+    v = unit3(v);
+    F3 u = f3(v.y * n.z - v.z * n.y, v.z * n.x - v.x * n.z, v.x * n.y - v.y * n.x);
+    float sp, cp;
+    sincosf(phi, &sp, &cp);
+    float lx = st * cp, ly = st * sp, lz = ct;
+    return f3(lx * u.x + ly * v.x + lz * n.x, lx * u.y + ly * v.y + lz * n.y, lx * u.z + ly * v.z + lz * n.z);
+}
+
+// Candidate ray parameter of one object for interval [tmin, tmax]; returns false on a miss.
+// sphere.hit objects.go:37-59, plane.hit :98-112, box.hit :141-183.  `a` = d.d and inv = 1/d are per ray.
+__device__ __forceinline__ bool hit_t(const DevObj& ob, int type, F3 o, F3 d, float a, F3 inv, float tmin, float tmax,
+                                      float& t_out) {
+    if (type == PTB_OBJ_BOX) {
+        float t0 = tmin, t1 = tmax;
+        float tn = (ob.ax - o.x) * inv.x, tf = (ob.bx - o.x) * inv.x;
+        if (inv.x < 0.0f) { float s = tn; tn = tf; tf = s; }
+        if (tn > t0) t0 = tn;
+        if (tf < t1) t1 = tf;
+        if (t1 <= t0) return false;
+        tn = (ob.ay - o.y) * inv.y; tf = (ob.by - o.y) * inv.y;
+        if (inv.y < 0.0f) { float s = tn; tn = tf; tf = s; }
+        if (tn > t0) t0 = tn;
+        if (tf < t1) t1 = tf;
+        if (t1 <= t0) return false;
+        tn = (ob.az - o.z) * inv.z; tf = (ob.bz - o.z) * inv.z;
+        if (inv.z < 0.0f) { float s = tn; tn = tf; tf = s; }
+        if (tn > t0) t0 = tn;
+        if (tf < t1) t1 = tf;
+        if (t1 <= t0) return false;
+        t_out = t0;
+        return true;
+    } else if (type == PTB_OBJ_SPHERE) {
+        float ocx = o.x - ob.ax, ocy = o.y - ob.ay, ocz = o.z - ob.az;
+        float hb = ocx * d.x + ocy * d.y + ocz * d.z;
+        float c = (ocx * ocx + ocy * ocy + ocz * ocz) - ob.by;     // by = radius*radius
+        float disc = hb * hb - a * c;
+        if (disc < 0.0f) return false;
+        float sq = sqrtf(disc);
+        float root = (-hb - sq) / a;
+        if (root < tmin || root > tmax) {
+            root = (-hb + sq) / a;
+            if (root < tmin || root > tmax) return false;
+        }
+        t_out = root;
+        return true;
+    } else {   // plane with normal (0,1,0): denom = d.y, t = (p.y - o.y)/d.y   (objects.go:100-110, 251-257)
+        float denom = d.y;
+        if (fabsf(denom) < 1e-6f) return false;
+        float t = (ob.ay - o.y) / denom;
+        if (t < tmin || t > tmax) return false;
+        t_out = t;
+        return true;
+    }
+}
+
+// Hit point, face normal and frontFace of object `ob` at parameter t (objects.go:61-88, 114-132, 181-221).
+__device__ __forceinline__ void surface(const DevObj& ob, int type, F3 o, F3 d, float t, F3& p, F3& n, bool& front) {
+    p = f3(o.x + d.x * t, o.y + d.y * t, o.z + d.z * t);
+    F3 on;
+    if (type == PTB_OBJ_SPHERE) {
+        float ir = ob.bz;   // 1/radius
+        on = f3((p.x - ob.ax) * ir, (p.y - ob.ay) * ir, (p.z - ob.az) * ir);
+    } else if (type == PTB_OBJ_PLANE) {
+        on = f3(0.0f, 1.0f, 0.0f);
+    } else {
+        float dxMin = p.x - ob.ax, dxMax = ob.bx - p.x;
+        float dyMin = p.y - ob.ay, dyMax = ob.by - p.y;
+        float dzMin = p.z - ob.az, dzMax = ob.bz - p.z;
+        float md = dxMin;
+        on = f3(-1.0f, 0.0f, 0.0f);
+        if (dxMax < md) { md = dxMax; on = f3(1.0f, 0.0f, 0.0f); }
+        if (dyMin < md) { md = dyMin; on = f3(0.0f, -1.0f, 0.0f); }
+        if (dyMax < md) { md = dyMax; on = f3(0.0f, 1.0f, 0.0f); }
+        if (dzMin < md) { md = dzMin; on = f3(0.0f, 0.0f, -1.0f); }
+        if (dzMax < md) { on = f3(0.0f, 0.0f, 1.0f); }
+    }
+    front = dot3(d, on) < 0.0f;
+    n = front ? on : f3(-on.x, -on.y, -on.z);
+}
+
+__device__ __forceinline__ F3 sky_color(F3 d) {                                                   // renderer.go:56-92
+    if (c_scene.sky.kind == PTB_SKY_GRADIENT) {
+        float len = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+        if (len == 0.0f) return f3(c_scene.sky.horizon[0], c_scene.sky.horizon[1], c_scene.sky.horizon[2]);
+        float t = (d.y / len + 1.0f) * 0.5f;
+        t = t < 0.0f ? 0.0f : t;
+        t = t > 1.0f ? 1.0f : t;
+        return f3(c_scene.sky.horizon[0] * (1.0f - t) + c_scene.sky.zenith[0] * t,
+                  c_scene.sky.horizon[1] * (1.0f - t) + c_scene.sky.zenith[1] * t,
+                  c_scene.sky.horizon[2] * (1.0f - t) + c_scene.sky.zenith[2] * t);
+    }
+    return f3(c_scene.sky.color[0], c_scene.sky.color[1], c_scene.sky.color[2]);
+}
+
+// Pixel epilogue of renderer.go:189-221 in binary64 (one value per channel per pixel; cost is nil).
+__device__ __forceinline__ uint8_t to_u8(float sum, double inv_spp) {
+    double v = sqrt((double)sum * inv_spp) * 255.999;
+    if (v < 0.0) v = 0.0; else if (v > 255.999) v = 255.999;
+    return (v == v) ? (uint8_t)(int)v : (uint8_t)0;
+}
+
+template <bool STATS>
+__global__ void __launch_bounds__(PTB_BLOCK_THREADS, PTB_MIN_BLOCKS)
+integrate_kernel(const __grid_constant__ FrameParams fp) {
+    extern __shared__ uint4 s_blob[];
+    const int n_obj = c_scene.n_obj;
+    {
+        const int n_words = n_obj * 2 + c_scene.n_mat * 3;
+        for (int i = threadIdx.x; i < n_words; i += blockDim.x) s_blob[i] = fp.scene_blob[i];
+        __syncthreads();
+    }
+    const DevObj* __restrict__ s_obj = reinterpret_cast<const DevObj*>(s_blob);
+    const DevMat* __restrict__ s_mat = reinterpret_cast<const DevMat*>(s_blob + 2 * n_obj);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7);
+    const int py = blockIdx.y * 8 + (warp >> 1) * 4 + (lane >> 3);
+    const bool in_frame = px < fp.width && py < fp.height;
+
+    const float xf = (float)px;                               // renderer.go:179
+    const float flip_y = fp.h_minus_1 - (float)py;            // renderer.go:174
+    const uint32_t pixel_key = fmix(fp.seed_key ^ (uint32_t)(py * fp.width + px));
+
+    unsigned long long st[STATS ? kStatsWords : 1] = {0};
+
+    float acc_x = 0.0f, acc_y = 0.0f, acc_z = 0.0f;
+    if (fp.accum_resume && in_frame) {
+        const float* a = fp.accum + ((size_t)py * fp.width + px) * 3;
+        acc_x = a[0]; acc_y = a[1]; acc_z = a[2];
+    }
+    int s = fp.s_begin;
+    bool alive = in_frame && s < fp.s_end && fp.max_depth > 0;   // max_depth <= 0: black frame (renderer.go:287-289)
+
+    // path state
+    Rng rng{0u, 0u};
+    F3 o = f3(0, 0, 0), d = f3(0, 0, 1), beta = f3(1, 1, 1), L = f3(0, 0, 0);
+    int depth = 0;
+
+    auto start_path = [&]() {                                 // renderer.go:182-185 + camera.go:60-74
+        rng.key = fmix(pixel_key + (uint32_t)s * kGolden);
+        rng.ctr = 0u;
+        const float u = (xf + rng.next()) * fp.inv_w;
+        const float v = (flip_y + rng.next()) * fp.inv_h;
+        const DevCamera& cam = c_scene.cam;
+        F3 dir = f3(cam.llc[0] + cam.horizontal[0] * u + cam.vertical[0] * v - cam.origin[0],
+                    cam.llc[1] + cam.horizontal[1] * u + cam.vertical[1] * v - cam.origin[1],
+                    cam.llc[2] + cam.horizontal[2] * u + cam.vertical[2] * v - cam.origin[2]);
+        F3 org = f3(cam.origin[0], cam.origin[1], cam.origin[2]);
+        if (cam.lens_radius > 0.0f) {
+            F3 rd = in_unit_sphere(rng);
+            float rx = rd.x * cam.lens_radius, ry = rd.y * cam.lens_radius;
+            F3 off = f3(cam.u[0] * rx + cam.v[0] * ry, cam.u[1] * rx + cam.v[1] * ry, cam.u[2] * rx + cam.v[2] * ry);
+            org = f3(org.x + off.x, org.y + off.y, org.z + off.z);
+            dir = f3(dir.x - off.x, dir.y - off.y, dir.z - off.z);
+        }
+        o = org; d = dir;
+        beta = f3(1.0f, 1.0f, 1.0f);
+        L = f3(0.0f, 0.0f, 0.0f);
+        depth = fp.max_depth;
+        if (STATS) st[ST_SAMPLES]++;
+    };
+    if (alive) start_path();
+    for (;;) {
+        const unsigned live = __ballot_sync(0xffffffffu, alive);
+        if (live == 0u) break;
+        if (STATS) { st[ST_LANE_TOTAL]++; if (alive) st[ST_LANE_ACTIVE]++; }
+        if (alive) {
+            // ---------------- closest hit over the whole world (renderer.go:292-302)
+            const float a = d.x * d.x + d.y * d.y + d.z * d.z;
+            const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+            float best = FLT_MAX;
+            int bid = -1;
+            for (int i = 0; i < n_obj; ++i) {
+                const DevObj& ob = c_scene.obj[i];
+                float t;
+                if (hit_t(ob, ob.type_mat & 3, o, d, a, inv, 0.001f, best, t)) { best = t; bid = i; }
+            }
+            if (STATS) st[ST_SEGMENTS]++;
+
+            bool done = false;
+            if (bid < 0) {                                    // renderer.go:304-306
+                F3 sk = sky_color(d);
+                L.x += beta.x * sk.x; L.y += beta.y * sk.y; L.z += beta.z * sk.z;
+                done = true;
+                if (STATS) st[ST_END_SKY]++;
+            } else {
+                const DevObj ob = s_obj[bid];
+                const int type = ob.type_mat & 3;
+                if (STATS) st[ST_ACC_SPHERE + type]++;
+                F3 p, n; bool front;
+                surface(ob, type, o, d, best, p, n, front);
+                const DevMat m = s_mat[ob.type_mat >> 2];
+
+                F3 att = f3(0, 0, 0), sd = f3(0, 0, 0), so = p;
+                bool ok = true;
+                if (m.type == PTB_MAT_EMISSIVE) {             // materials.go:67-72, 202-203; renderer.go:308-312
+                    L.x += beta.x * m.emit[0]; L.y += beta.y * m.emit[1]; L.z += beta.z * m.emit[2];
+                    ok = false;
+                    if (STATS) st[ST_END_EMISSIVE]++;
+                } else if (m.type == PTB_MAT_LAMBERT) {       // materials.go:76-97
+                    sd = cosine_direction(n, rng);
+                    if (m.rough > 1e-6f) {
+                        F3 off = in_unit_sphere(rng);
+                        sd.x += off.x * m.rough * 0.1f; sd.y += off.y * m.rough * 0.1f; sd.z += off.z * m.rough * 0.1f;
+                        sd = unit3(sd);
+                    }
+                    att = f3(m.albedo[0], m.albedo[1], m.albedo[2]);
+                } else {
+                    const float len = sqrtf(a);               // |rIn.dir|, materials.go:102,177,207
+                    if (len == 0.0f) {
+                        ok = false;
+                        if (STATS) st[ST_END_NOSCATTER]++;
+                    } else {
+                        const float il = 1.0f / len;
+                        const F3 ud = f3(d.x * il, d.y * il, d.z * il);
+                        if (m.type == PTB_MAT_MIRROR) {       // materials.go:205-221
+                            sd = reflect3(ud, n);
+                            att = f3(m.albedo[0], m.albedo[1], m.albedo[2]);
+                        } else if (m.type == PTB_MAT_METAL) { // materials.go:99-160
+                            const F3 refl = reflect3(ud, n);
+                            sd = refl;
+                            if (m.rough > 1e-6f) {
+                                F3 sc = cosine_direction(refl, rng);
+                                float alpha = m.rough * m.rough;
+                                float sx = refl.x * (1.0f - alpha) + sc.x * alpha;
+                                float sy = refl.y * (1.0f - alpha) + sc.y * alpha;
+                                float sz = refl.z * (1.0f - alpha) + sc.z * alpha;
+                                float l2 = sx * sx + sy * sy + sz * sz;
+                                if (l2 < 1e-8f) { sx = refl.x; sy = refl.y; sz = refl.z; }
+                                else { float i2 = 1.0f / sqrtf(l2); sx *= i2; sy *= i2; sz *= i2; }
+                                if (sx * n.x + sy * n.y + sz * n.z <= 0.0f) { sx = refl.x; sy = refl.y; sz = refl.z; }
+                                sd = f3(sx, sy, sz);
+                            }
+                            att = f3(m.albedo[0], m.albedo[1], m.albedo[2]);
+                        } else {                              // dielectric, materials.go:162-200
+                            att = f3(1.0f, 1.0f, 1.0f);
+                            const float ratio = front ? 1.0f / m.ior : m.ior;
+                            const float cos_t = fminf(-(ud.x * n.x + ud.y * n.y + ud.z * n.z), 1.0f);
+                            const float sin_t = sqrtf(1.0f - cos_t * cos_t);
+                            const bool cannot = ratio * sin_t > 1.0f;
+                            float r0 = (1.0f - ratio) / (1.0f + ratio);
+                            r0 = r0 * r0;
+                            const float om = 1.0f - cos_t;
+                            const float om2 = om * om;
+                            const float refl_prob = r0 + (1.0f - r0) * (om2 * om2 * om);   // Schlick, materials.go:226-231
+                            if (cannot || refl_prob > rng.next()) {
+                                sd = reflect3(ud, n);
+                            } else {                          // refractVec, math.go:48-64
+                                const float c2 = fminf(-ud.x * n.x - ud.y * n.y - ud.z * n.z, 1.0f);
+                                float qx = (ud.x + n.x * c2) * ratio, qy = (ud.y + n.y * c2) * ratio, qz = (ud.z + n.z * c2) * ratio;
+                                const float par = -sqrtf(fabsf(1.0f - (qx * qx + qy * qy + qz * qz)));
+                                sd = f3(qx + n.x * par, qy + n.y * par, qz + n.z * par);
+                            }
+                            if (front) {                      // exit search, renderer.go:316-371
+                                if (STATS) st[ST_EXIT_SCANS]++;
+                                const float a2 = sd.x * sd.x + sd.y * sd.y + sd.z * sd.z;
+                                const F3 inv2 = f3(1.0f / sd.x, 1.0f / sd.y, 1.0f / sd.z);
+                                float exit_t = FLT_MAX;
+                                bool hit_exit = false;
+                                F3 ep = p;
+                                const int n_diel = c_scene.n_diel;
+                                for (int k = 0; k < n_diel; ++k) {   // only dielectric objects can be accepted (:335)
+                                    const DevObj& eo = c_scene.obj[c_scene.diel_idx[k]];
+                                    const int et = eo.type_mat & 3;
+                                    float t;
+                                    if (!hit_t(eo, et, p, sd, a2, inv2, 0.0001f, exit_t, t)) continue;
+                                    F3 q, qn; bool qf;
+                                    surface(eo, et, p, sd, t, q, qn, qf);
+                                    if (!qf && t < exit_t) {
+                                        float ex = q.x - p.x, ey = q.y - p.y, ez = q.z - p.z;
+                                        float d2 = ex * ex + ey * ey + ez * ez;
+                                        if (d2 > 1e-8f && d2 < 1000.0f) { hit_exit = true; exit_t = t; ep = q; }
+                                    }
+                                }
+                                if (hit_exit) {               // renderer.go:352-369
+                                    float ex = ep.x - p.x, ey = ep.y - p.y, ez = ep.z - p.z;
+                                    float dist = sqrtf(ex * ex + ey * ey + ez * ez);
+                                    if (m.absorption[0] > 0.0f || m.absorption[1] > 0.0f || m.absorption[2] > 0.0f) {
+                                        att = f3(expf(-m.absorption[0] * dist), expf(-m.absorption[1] * dist),
+                                                 expf(-m.absorption[2] * dist));
+                                    }
+                                    so = ep;
+                                }
+                            }
+                        }
+                    }
+                }
+
+                if (!ok) {
+                    done = true;
+                } else {
+                    if (STATS) st[ST_SCATTERS]++;
+                    if (depth <= 3) {                         // Russian roulette, renderer.go:374-393
+                        float mx = fmaxf(att.x, fmaxf(att.y, att.z));
+                        if (mx < 1e-6f) {
+                            done = true;
+                        } else {
+                            float pr = fminf(mx, 0.95f);
+                            if (rng.next() > pr) done = true;
+                            else { att.x /= pr; att.y /= pr; att.z /= pr; }
+                        }
+                        if (STATS && done) st[ST_END_RR]++;
+                    }
+                    if (!done) {                              // renderer.go:398-403
+                        beta.x *= att.x; beta.y *= att.y; beta.z *= att.z;
+                        o = so; d = sd;
+                        if (--depth <= 0) {                   // renderer.go:287-289
+                            done = true;
+                            if (STATS) st[ST_END_DEPTH]++;
+                        }
+                    }
+                }
+            }
+
+            if (done) {                                       // renderer.go:186: col = col.add(...)
+                acc_x += L.x; acc_y += L.y; acc_z += L.z;
+                if (++s < fp.s_end) start_path(); else alive = false;
+            }
+        }
+    }
+
+    if (in_frame) {
+        const size_t pix = (size_t)py * fp.width + px;
+        if (fp.accum) {
+            float* a = fp.accum + pix * 3;
+            a[0] = acc_x; a[1] = acc_y; a[2] = acc_z;
+        }
+        if (fp.rgba) {
+            const double inv_spp = 1.0 / (double)fp.spp_total;
+            uchar4 c = make_uchar4(to_u8(acc_x, inv_spp), to_u8(acc_y, inv_spp), to_u8(acc_z, inv_spp), 255);
+            reinterpret_cast<uchar4*>(fp.rgba)[pix] = c;
+        }
+    }
+    if (STATS) {
+        for (int k = 0; k < kStatsWords; ++k) {
+            unsigned long long v = st[k];
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if (lane == 0 && v) atomicAdd(fp.stats + k, v);
+        }
+    }
+}
+
+__global__ void finalize_kernel(const float* __restrict__ accum, int n_pix, double inv_spp, uchar4* __restrict__ rgba) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    const float* a = accum + (size_t)i * 3;
+    rgba[i] = make_uchar4(to_u8(a[0], inv_spp), to_u8(a[1], inv_spp), to_u8(a[2], inv_spp), 255);
+}
+
+// FP32 FMA throughput probe: 8 independent chains per thread, 2 flop per FMA.
+__global__ void fma_peak_kernel(float* out, int iters) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f, c = 1e-3f;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ---------------------------------------------------------------- launchers
+int upload_scene_constants(const DevScene& h, void* stream) {
+    // header + diel_idx + obj: only the used prefix of each array is copied
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_scene, &h, offsetof(DevScene, diel_idx), 0, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && h.n_diel > 0)
+        e = cudaMemcpyToSymbolAsync(c_scene, h.diel_idx, sizeof(int32_t) * h.n_diel, offsetof(DevScene, diel_idx), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && h.n_obj > 0)
+        e = cudaMemcpyToSymbolAsync(c_scene, h.obj, sizeof(DevObj) * h.n_obj, offsetof(DevScene, obj), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && h.n_mat > 0)
+        e = cudaMemcpyToSymbolAsync(c_scene, h.mat, sizeof(DevMat) * h.n_mat, offsetof(DevScene, mat), cudaMemcpyHostToDevice, s);
+    return (int)e;
+}
+
+int launch_integrator(const FrameParams& fp, bool stats, int n_obj, int n_mat, void* stream) {
+    dim3 grid((fp.width + 15) / 16, (fp.height + 7) / 8);
+    size_t smem = (size_t)(n_obj * 2 + n_mat * 3) * sizeof(uint4);
+    if (stats) integrate_kernel<true><<<grid, PTB_BLOCK_THREADS, smem, (cudaStream_t)stream>>>(fp);
+    else integrate_kernel<false><<<grid, PTB_BLOCK_THREADS, smem, (cudaStream_t)stream>>>(fp);
+    return (int)cudaGetLastError();
+}
+
+int launch_finalize(const float* accum, int width, int height, int spp_total, uint8_t* rgba, void* stream) {
+    int n = width * height;
+    finalize_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(accum, n, 1.0 / (double)spp_total,
+                                                                      reinterpret_cast<uchar4*>(rgba));
+    return (int)cudaGetLastError();
+}
+
+int launch_fma_peak(float* d_out, int blocks, int threads, int iters, void* stream) {
+    fma_peak_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(d_out, iters);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace ptb

@@ -1,0 +1,90 @@
+// scene_dev.h — device-side scene layout shared by the host API (api.cu) and the kernels.
+//
+// The analytic world of the reference (objects.go:26-222: spheres, one-normal planes, boxes; at
+// most a few dozen objects) is tiny, so it is not streamed from HBM at all: the fp32 copy lives in
+// __constant__ memory.  The closest-hit scan reads it with a warp-uniform index (every lane tests
+// object i at the same time), which the constant cache serves as a broadcast; the few divergent
+// look-ups (the winning object / its material) go through a shared-memory copy made per CTA.
+#pragma once
+#include <stdint.h>
+#include <vector_types.h>
+
+#include "../../include/ptb200.h"
+
+namespace ptb {
+
+// 32-byte records, two 16-byte vector loads each.
+struct alignas(16) DevObj {
+    float ax, ay, az;   // sphere centre | plane point | box min            (objects.go:31-35, 92-96, 136-139)
+    int32_t type_mat;   // type in bits 0..1, material index in bits 2..
+    float bx, by, bz;   // sphere (radius, radius^2, 1/radius) | plane unused | box max
+    int32_t is_diel;    // material is dielectric (exit search candidate, renderer.go:335)
+};
+
+// 48-byte records. materials.go:19-26.
+struct alignas(16) DevMat {
+    float albedo[3];
+    int32_t type;
+    float emit[3];
+    float rough;
+    float absorption[3];
+    float ior;
+};
+
+struct DevCamera {   // camera.go:9-17, binary32 copy of the binary64 newCamera result
+    float origin[3], llc[3], horizontal[3], vertical[3], u[3], v[3];
+    float lens_radius;
+};
+
+struct DevSky {      // renderer.go:56-92
+    int32_t kind;
+    float color[3], horizon[3], zenith[3];
+};
+
+struct DevScene {                        // ~43 KB of the 64 KB constant bank
+    int32_t n_obj, n_mat, n_diel, pad;   // n_mat counts the appended zero material (index n_mat-1)
+    DevSky sky;
+    DevCamera cam;
+    int32_t diel_idx[PTB_MAX_OBJECTS];   // world indices of objects with a dielectric material, ascending
+    DevObj obj[PTB_MAX_OBJECTS];
+    DevMat mat[PTB_MAX_MATERIALS + 1];   // slot n_mat-1 = the zero material (missing material_id, objects.go:234)
+};
+
+// fp64 world for the primary-hit parity kernel (global memory; N is tiny).
+struct Obj64 {
+    int32_t type, pad;
+    double a[3], b[3];   // sphere: a centre, b.x radius | plane: a point, b normal | box: a min, b max
+};
+struct Camera64 {
+    double origin[3], llc[3], horizontal[3], vertical[3];
+};
+
+struct FrameParams {
+    int32_t width, height;
+    int32_t s_begin, s_end;      // sample range of every pixel traced by this launch
+    int32_t spp_total;           // divisor of the pixel epilogue
+    int32_t max_depth;
+    uint32_t seed_key;           // fmix(seed ^ GOLDEN), hoisted out of the kernel
+    float inv_w, inv_h, h_minus_1;   // renderer.go:95-98
+    const uint4* scene_blob;     // global copy of obj[0..n_obj) then mat[0..n_mat), 16-byte words (for the smem fill)
+    float* accum;                // W*H*3 sums, or nullptr
+    int32_t accum_resume;        // 1: start each pixel's sum from accum[] (progressive batches), 0: from zero
+    uint8_t* rgba;               // W*H*4 finalised pixels, or nullptr
+    unsigned long long* stats;   // kStatsWords counters, or nullptr
+};
+
+enum StatWord {
+    ST_SAMPLES = 0, ST_SEGMENTS, ST_EXIT_SCANS, ST_ACC_SPHERE, ST_ACC_PLANE, ST_ACC_BOX, ST_SCATTERS,
+    ST_END_SKY, ST_END_EMISSIVE, ST_END_RR, ST_END_DEPTH, ST_END_NOSCATTER, ST_LANE_ACTIVE, ST_LANE_TOTAL,
+    kStatsWords
+};
+
+// launchers (integrator.cu / primary_fp64.cu)
+int upload_scene_constants(const DevScene& host_scene, void* stream);
+int launch_integrator(const FrameParams& fp, bool stats, int n_obj, int n_mat, void* stream);
+int launch_finalize(const float* accum, int width, int height, int spp_total, uint8_t* rgba, void* stream);
+int launch_primary_hits(const Obj64* d_world, int n_obj, const Camera64& cam, int width, int height,
+                        double xi_u, double xi_v, int32_t* d_ids, double* d_t, void* stream);
+int launch_fma_peak(float* d_out, int blocks, int threads, int iters, void* stream);
+
+}  // namespace ptb

@@ -1,0 +1,75 @@
+"""Multi-GPU: one process per GPU (torch.distributed), the frame's samples partitioned across ranks.
+
+Every (pixel, sample) path is independent and the counter RNG is keyed by (seed, pixel, sample), so rank r
+simply traces samples [r*spp/N, (r+1)*spp/N) of every pixel into its own fp32 accumulation buffer; the only
+exchange is the additive reduction of those buffers to rank 0 (NCCL over NVLink on GPUs, gloo in CPU tests),
+followed by the pixel epilogue on rank 0.  The image is identical (up to fp32 re-association of the N
+partial sums) for every N.  SURVEY.md §8(e).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def sample_range(spp: int, rank: int, world: int) -> tuple[int, int]:
+    """Samples [begin, end) of every pixel traced by `rank`; ranges tile [0, spp) and differ by <= 1."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world {world}")
+    base, rem = divmod(int(spp), world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def reduce_to_root(accum: torch.Tensor, group=None) -> torch.Tensor:
+    """Sum the per-rank accumulation buffers onto rank 0, in place (ncclReduce / gloo reduce)."""
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.reduce(accum, dst=0, op=dist.ReduceOp.SUM, group=group)
+    return accum
+
+
+def render_partition(ctx, cfg_full, rank: int, world: int, accum: torch.Tensor, stream: int = 0) -> bool:
+    """Launch this rank's share of the frame into `accum` (CUDA fp32 tensor, H*W*3).  Returns False when the
+    rank has no samples (spp < world): its buffer is zero-filled instead."""
+    from ._lib import PtbCfg
+    b, e = sample_range(cfg_full.samples_per_px, rank, world)
+    if e <= b:
+        accum.zero_()
+        return False
+    cfg = PtbCfg(cfg_full.width, cfg_full.height, cfg_full.samples_per_px, cfg_full.max_depth, cfg_full.seed, b, e - b,
+                 cfg_full.flags)
+    ctx.render_accum_device(cfg, accum.data_ptr(), stream)
+    return True
+
+
+def render_distributed(ctx, cfg_full, out_rgba: torch.Tensor | None = None, group=None):
+    """Whole multi-GPU frame: partition -> render -> reduce -> epilogue on rank 0.
+
+    Returns (accum, rgba): rgba is a CUDA uint8 (H, W, 4) tensor on rank 0, None elsewhere.
+    Everything is enqueued on torch's current stream; nothing synchronises with the host.
+    """
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    H, W = cfg_full.height, cfg_full.width
+    dev = torch.device("cuda", ctx.device)
+    accum = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    render_partition(ctx, cfg_full, rank, world, accum, stream)
+    reduce_to_root(accum, group)
+    rgba = None
+    if rank == 0:
+        rgba = out_rgba if out_rgba is not None else torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
+        ctx.finalize_device(accum.data_ptr(), W, H, cfg_full.samples_per_px, rgba.data_ptr(), stream)
+    return accum, rgba
+
+
+def finalize_host(rgb_sum: np.ndarray, spp: int) -> np.ndarray:
+    """Pixel epilogue of renderer.go:189-221 on a host array (used by the CPU/gloo tests of the plumbing)."""
+    v = np.sqrt(rgb_sum.astype(np.float64) * (1.0 / spp)) * 255.999
+    v = np.where(v < 0, 0.0, np.where(v > 255.999, 255.999, v))
+    v = np.where(np.isnan(v), 0.0, v)
+    out = np.empty(rgb_sum.shape[:2] + (4,), dtype=np.uint8)
+    out[..., :3] = v.astype(np.uint8)
+    out[..., 3] = 255
+    return out
