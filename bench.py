@@ -1,0 +1,306 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the B200 path-tracing backend.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C3]
+
+One "step" = one full frame of the workload (default C3 = scenes/metal_glass_room.json at 3840x2160,
+256 spp, depth 16 — the configuration BASELINE.json quotes its metric and target on).
+Prints ONE JSON line on rank 0 (contract in the task statement): metric = Msamples/s (whole job),
+plus Mrays/s, `roofline` (FP32 issue roofline of the integrator kernel), `cpu_baseline` (the oracle = C++
+restatement of the Go CPU renderer, timed on this box's host cores), `e2e` (through engine.RenderInto with host
+buffers), `clocks`, `gpu_launches`.
+
+N > 1 (torchrun, one rank per GPU): the frame's samples are split across ranks (strong scaling: total work
+fixed), the fp32 accumulation buffers are reduced to rank 0 with NCCL, rank 0 runs the pixel epilogue.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    "C1": ("example_simple", 640, 360, 16, 8),
+    "C2": ("test_scene", 1920, 1080, 64, 10),
+    "C3": ("metal_glass_room", 3840, 2160, 256, 16),
+    "C5": ("gpu_showcase", 7680, 4320, 1024, 12),
+}
+# algorithmic flop constants, SURVEY.md §8(d): per primitive test / per accepted hit / per scattered bounce
+F_TEST = {0: 24, 1: 16, 2: 27}     # sphere, plane, box
+F_ACCEPT = {0: 25, 1: 9, 2: 23}
+F_SHADE, F_PIXEL = 80, 12
+
+
+def world_counts(ctx):
+    c = {0: 0, 1: 0, 2: 0}
+    for o in ctx.world():
+        c[o["type"]] += 1
+    return c
+
+
+def flops_per_sample(stats: dict, counts: dict, spp: int) -> float:
+    """tests are credited by the reference's linear-scan definition — every scan (main AND exit
+    search) tests every object — whatever the device actually executes."""
+    n = stats["samples"]
+    scans = (stats["segments"] + stats["exit_scans"]) / n
+    per_scan = sum(counts[t] * F_TEST[t] for t in counts)
+    accepts = sum(stats["accepts"][t] * F_ACCEPT[t] for t in range(3)) / n
+    return scans * per_scan + accepts + stats["scatters"] / n * F_SHADE + F_PIXEL / spp
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md 'clocks' line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons, power = [], None, set(), []
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1]); power.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "power_w_max": max(power) if power else None, "samples": len(sm)}
+
+
+def cpu_reference_run(name, W, H, depth, spp_sample, steps, warmup, threads):
+    """Times the oracle's renderIntoCPU equivalent (fp64, 32x32 tile queue, `threads` workers)."""
+    from oracle import pyoracle
+    ora = pyoracle.OracleScene.load(ROOT / "scenes" / f"{name}.json")
+    for _ in range(warmup):
+        ora.render_rgba(W, max(2, H // 16), spp_sample, depth, seed=1, threads=threads)
+    t0 = time.perf_counter()
+    st = None
+    for i in range(steps):
+        _, st = ora.render_rgba(W, H, spp_sample, depth, seed=1 + i, threads=threads)
+    dt = (time.perf_counter() - t0) / steps
+    n = W * H * spp_sample
+    return n / dt / 1e6, st["segments"] / st["samples"], dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-spp", type=int, default=0, help="spp of the bounded CPU sample (0 = auto, ~15 s)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3                      # timing rule: W >= 3
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    name, W, H, spp, depth = WORKLOADS[args.workload]
+    config = {"workload": f"{args.workload}: scenes/{name}.json {W}x{H}, {spp} spp, max depth {depth}", "scene": name,
+              "width": W, "height": H, "samples_per_px": spp, "max_depth": depth,
+              "partition": "sample ranges per rank + NCCL reduce to rank 0" if world > 1 else "single GPU",
+              "l2": "flushed between steps (256 MiB write); inputs are a few KB of constants"}
+    cores = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cpu_spp = args.cpu_spp or 2
+        msps, rays_per_sample, dt = cpu_reference_run(name, W, H, depth, cpu_spp, args.steps, min(args.warmup, 1), cores)
+        sample = f"{W}x{H}, {cpu_spp} of {spp} spp per step (samples/s is spp-independent), depth {depth}"
+        print(json.dumps({
+            "impl": "reference", "metric": "Msamples/s", "value": msps, "unit": "Msamples/s", "n_gpus": 0,
+            "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "mrays_per_s": msps * rays_per_sample,
+            "cpu_baseline": {"value": msps, "unit": "Msamples/s", "cores": cores, "kind": "port", "sample": sample,
+                             "note": "C++ restatement of the Go CPU path (Go toolchain unavailable); workers = host cores "
+                                     "(runtime.NumCPU analogue), -O2 -ffp-contract=off"},
+            "e2e": {"value": msps, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }))
+        return
+
+    # ------------------------------------------------------------------ our arm (CUDA)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from path_trace_golang_b200 import dist as pdist
+    from path_trace_golang_b200 import engine, scene
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = engine.Context(local_rank)
+    sc = scene.Load(ROOT / "scenes" / f"{name}.json")
+    ctx.upload(sc)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    cfg = ctx.cfg(W, H, spp, depth, seed=1)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    rgba = torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
+    accum = torch.empty((H, W, 3), dtype=torch.float32, device=dev) if world > 1 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def step_resident():
+        flush.zero_()                                            # L2 flush (a torch memset, not one of our kernels)
+        if world == 1:
+            ctx.render_device(cfg, rgba.data_ptr(), stream)      # 1 launch: integrate + epilogue
+        else:
+            pdist.render_partition(ctx, cfg, rank, world, accum, stream)
+            pdist.reduce_to_root(accum)
+            if rank == 0:
+                ctx.finalize_device(accum.data_ptr(), W, H, spp, rgba.data_ptr(), stream)
+
+    host_img = np.zeros((H, W, 4), dtype=np.uint8)
+
+    def step_e2e():
+        flush.zero_()
+        if world == 1:
+            # the reference-facing call: scene flatten + upload (H2D), render, D2H into the caller's image
+            engine.RenderInto(sc, engine.RenderConfig(W, H, spp, depth), host_img, ctx=ctx, seed=1)
+        else:
+            ctx.upload(sc)
+            pdist.render_partition(ctx, cfg, rank, world, accum, stream)
+            pdist.reduce_to_root(accum)
+            if rank == 0:
+                ctx.finalize_device(accum.data_ptr(), W, H, spp, rgba.data_ptr(), stream)
+                host_img[...] = rgba.cpu().numpy()
+
+    # counters for the roofline (one stats pass at reduced spp, outside every timed region)
+    counts = world_counts(ctx)
+    ctx.render_accum(ctx.cfg(W, H, min(spp, 8), depth, seed=1, stats=True))
+    st = ctx.stats()
+    fps = flops_per_sample(st, counts, spp)
+    rays_per_sample = st["segments"] / st["samples"]
+    simt_util = st["lane_iters_active"] / max(1, st["lane_iters_total"])
+    fp32_peak = ctx.fp32_peak_tflops() if rank == 0 else 0.0
+
+    # ---- timed region 1: resident (value)
+    for _ in range(args.warmup):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    kernel_ev = []
+    ev[0].record()
+    for i in range(args.steps):
+        step_resident()
+        ev[i + 1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+
+    # kernel-only duration of the integrator (for the roofline): events tight around the launch, same stream
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kms = []
+    for _ in range(max(3, args.steps)):
+        flush.zero_()
+        k0.record()
+        if world == 1:
+            ctx.render_device(cfg, rgba.data_ptr(), stream)
+        else:
+            pdist.render_partition(ctx, cfg, rank, world, accum, stream)
+        k1.record()
+        torch.cuda.synchronize(dev)
+        kms.append(k0.elapsed_time(k1))
+    kernel_ms = sum(kms) / len(kms)
+
+    # ---- timed region 2: end to end through the public API (host buffers)
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+
+    samples = W * H * spp
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        value = samples / (ms_per_step * 1e-3) / 1e6
+        e2e_value = samples * args.steps / e2e_s / 1e6
+        # the kernel this rank launched covers samples/world of the frame
+        achieved = fps * (samples / world) / (kernel_ms * 1e-3) / 1e12
+        flat = sc.flat()
+        h2d = 8 * (flat.n_obj * 8 + flat.n_mat * 12) + 512          # flattened SoA + camera/sky structs (bytes, approx. exact)
+        out = {
+            "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "mrays_per_s": value * rays_per_sample, "rays_per_sample": rays_per_sample,
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
+                         "kernel": "integrate_kernel<false>", "kernel_ms": kernel_ms,
+                         "flops_per_sample": fps, "simt_lane_utilisation": simt_util,
+                         "peak_source": "measured here: ptb_measure_fp32_peak (FFMA microbenchmark, 2 flop/FMA); "
+                                        "MEASURED_PEAKS.json has no fp32 entry; nominal 148x128x2x1.965 GHz = 74.5",
+                         "note": "algorithmic flops by the reference's linear-scan definition (SURVEY §8d); this path is "
+                                 "FP32-issue bound, not HBM or tensor bound: HBM traffic is ~4 B/pixel/frame"},
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": W * H * 4, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "api": "engine.RenderInto(scene, cfg, host image)" if world == 1 else
+                           "scene upload + dist.render_partition + NCCL reduce + epilogue + D2H on rank 0"},
+            "gpu_launches": args.steps * (1 if world == 1 else 2),
+            "clocks": clocks,
+        }
+        if not args.no_cpu and world == 1:
+            cpu_spp = args.cpu_spp or 4
+            msps, _, dt = cpu_reference_run(name, W, H, depth, cpu_spp, 1, 0, cores)
+            out["cpu_baseline"] = {"value": msps, "unit": "Msamples/s", "cores": cores, "kind": "port",
+                                   "sample": f"{W}x{H}, {cpu_spp} of {spp} spp, depth {depth}, {dt:.1f} s, {cores} worker threads",
+                                   "note": "C++ restatement of the Go CPU path (Go toolchain unavailable)"}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

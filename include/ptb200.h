@@ -158,8 +158,9 @@ int ptb_render(ptb_ctx* ctx, const ptb_cfg* cfg, uint8_t* rgba, size_t stride,
 /* Linear fp32 radiance sums (NOT divided by the sample count) of this context's sample range,
  * width*height*3 floats, top row first — to a host buffer ... */
 int ptb_render_accum(ptb_ctx* ctx, const ptb_cfg* cfg, float* rgb_sum);
-/* ... or asynchronously into DEVICE memory on a caller-supplied CUDA stream (cudaStream_t as
- * void*; NULL = the context's own stream).  This is what a multi-GPU caller reduces with NCCL. */
+/* ... or asynchronously into DEVICE memory on a caller-supplied CUDA stream (cudaStream_t passed as
+ * void*, used exactly as given: NULL is the CUDA default stream, which is also PyTorch's default
+ * stream).  This is what a multi-GPU caller reduces with NCCL. */
 int ptb_render_accum_device(ptb_ctx* ctx, const ptb_cfg* cfg, void* d_rgb_sum, void* stream);
 /* Pixel epilogue (renderer.go:189-221) on device buffers: mean over spp_total, sqrt, *255.999,
  * clamp, truncate, A=255.  d_rgba: height*width*4 bytes, tightly packed. */

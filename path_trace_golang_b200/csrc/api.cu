@@ -338,20 +338,29 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
         for (int k = 0; k < 3; k++) { m.albedo[k] = (float)w.albedo[k]; m.emit[k] = (float)w.emit[k]; m.absorption[k] = (float)w.absorption[k]; }
     }
     std::vector<Obj64> w64(world.size());
-    for (int i = 0; i < hs.n_obj; i++) {
+    // device order: boxes first (world order), then spheres/planes (world order); see integrator.cu for why the
+    // reference's tie rule survives this grouping
+    std::vector<int> order, dev_of(world.size());
+    for (int i = 0; i < (int)world.size(); i++) if (world[i].type == PTB_OBJ_BOX) order.push_back(i);
+    hs.n_box = (int)order.size();
+    for (int i = 0; i < (int)world.size(); i++) if (world[i].type != PTB_OBJ_BOX) order.push_back(i);
+    for (int k = 0; k < hs.n_obj; k++) {
+        const int i = order[k];
+        dev_of[i] = k;
         const World64Entry& w = world[i];
-        DevObj& o = hs.obj[i];
+        DevObj& o = hs.obj[k];
         o.ax = (float)w.a[0]; o.ay = (float)w.a[1]; o.az = (float)w.a[2];
         if (w.type == PTB_OBJ_SPHERE) {
             float r = (float)w.b[0];
             o.bx = r; o.by = r * r; o.bz = 1.0f / r;    // radiusSq (objects.go:46), invRadius (objects.go:68)
         } else { o.bx = (float)w.b[0]; o.by = (float)w.b[1]; o.bz = (float)w.b[2]; }
-        o.type_mat = w.type | (w.mat_slot << 2);
-        o.is_diel = w.mat_type == PTB_MAT_DIELECTRIC;
-        if (o.is_diel) hs.diel_idx[hs.n_diel++] = i;
+        o.meta = w.type | ((w.mat_type == PTB_MAT_DIELECTRIC) << 2) | (w.mat_slot << 3);
+        o.world_idx = i;
         w64[i].type = w.type; w64[i].pad = 0;
-        for (int k = 0; k < 3; k++) { w64[i].a[k] = w.a[k]; w64[i].b[k] = w.b[k]; }
+        for (int j = 0; j < 3; j++) { w64[i].a[j] = w.a[j]; w64[i].b[j] = w.b[j]; }
     }
+    for (int i = 0; i < (int)world.size(); i++)
+        if (world[i].mat_type == PTB_MAT_DIELECTRIC) hs.diel_idx[hs.n_diel++] = dev_of[i];
     hs.sky.kind = s->sky.kind == PTB_SKY_GRADIENT ? PTB_SKY_GRADIENT : PTB_SKY_CONST;
     for (int k = 0; k < 3; k++) { hs.sky.color[k] = (float)s->sky.color[k]; hs.sky.horizon[k] = (float)s->sky.horizon[k]; hs.sky.zenith[k] = (float)s->sky.zenith[k]; }
 
@@ -397,7 +406,7 @@ int ptb_render_accum_device(ptb_ctx* c, const ptb_cfg* cfg, void* d_rgb_sum, voi
     if ((rc = check_cfg(c, cfg, s0, s1))) return rc;
     if (!d_rgb_sum) return fail(c, PTB_ERR_INVALID, "d_rgb_sum is NULL");
     CK(c, cudaSetDevice(c->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;
     if ((rc = render_launch(c, cfg, s0, s1, (float*)d_rgb_sum, nullptr, st))) return rc;
     if (cfg->flags & PTB_FLAG_STATS) { CK(c, cudaStreamSynchronize(st)); return fetch_stats(c, true, 0.f); }
     return PTB_OK;
@@ -411,7 +420,7 @@ int ptb_render_device(ptb_ctx* c, const ptb_cfg* cfg, void* d_rgba, void* stream
     if (!d_rgba) return fail(c, PTB_ERR_INVALID, "d_rgba is NULL");
     if (s0 != 0 || s1 != cfg->samples_per_px) return fail(c, PTB_ERR_INVALID, "ptb_render_device needs the full sample range");
     CK(c, cudaSetDevice(c->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;
     if ((rc = render_launch(c, cfg, s0, s1, nullptr, (uint8_t*)d_rgba, st))) return rc;
     if (cfg->flags & PTB_FLAG_STATS) { CK(c, cudaStreamSynchronize(st)); return fetch_stats(c, true, 0.f); }
     return PTB_OK;
@@ -422,7 +431,7 @@ int ptb_finalize_device(ptb_ctx* c, const void* d_rgb_sum, int32_t width, int32_
     std::lock_guard<std::mutex> lk(c->mu);
     if (!d_rgb_sum || !d_rgba || width < 1 || height < 1 || spp_total < 1) return fail(c, PTB_ERR_INVALID, "bad argument");
     CK(c, cudaSetDevice(c->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    cudaStream_t st = (cudaStream_t)stream;
     int e = launch_finalize((const float*)d_rgb_sum, width, height, spp_total, (uint8_t*)d_rgba, st);
     if (e) return fail(c, PTB_ERR_CUDA, "finalize launch: %s", cudaGetErrorString((cudaError_t)e));
     return PTB_OK;

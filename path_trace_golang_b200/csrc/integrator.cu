@@ -37,103 +37,145 @@ __constant__ DevScene c_scene;
 
 constexpr uint32_t kGolden = 0x9E3779B9u;
 
-// ---- counter RNG (DESIGN.md "RNG"); stands in for randSource.Float64 (random.go:27-34)
+// ---- arithmetic policy.  PTB_FAST_MATH=1 (default): reciprocal / square root / sin / cos use the SFU
+// approximations (rcp.approx, sqrt.approx, sin/cos.approx: <= 2 ulp, resp. ~1e-6 absolute) and every
+// division of the reference becomes a multiplication by such a reciprocal.  The radiance estimate is
+// statistical and the parity tests (tests/test_gpu_parity.py) run against this build.  PTB_FAST_MATH=0 keeps
+// IEEE division / sqrt and libdevice sincosf/expf.
+#ifndef PTB_FAST_MATH
+#define PTB_FAST_MATH 1
+#endif
+__device__ __forceinline__ float rcp_(float x) {
+#if PTB_FAST_MATH
+    float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+    return 1.0f / x;
+#endif
+}
+__device__ __forceinline__ float sqrt_(float x) {
+#if PTB_FAST_MATH
+    float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+    return sqrtf(x);
+#endif
+}
+__device__ __forceinline__ void sincos_(float x, float* s, float* c) {
+#if PTB_FAST_MATH
+    __sincosf(x, s, c);
+#else
+    sincosf(x, s, c);
+#endif
+}
+__device__ __forceinline__ float exp_(float x) {
+#if PTB_FAST_MATH
+    return __expf(x);
+#else
+    return expf(x);
+#endif
+}
+
+// ---- counter RNG (DESIGN.md "RNG"); stands in for randSource.Float64 (random.go:27-34).
+// Draw i of a path is a pure function of (key, i), so the draws a bounce MIGHT need are evaluated up front
+// at full warp width (peek) and the counter is advanced afterwards by the number actually consumed — the
+// consumed sequence is exactly the sequential one the oracle uses.
 __device__ __forceinline__ uint32_t fmix(uint32_t x) {
     x ^= x >> 16; x *= 0x21f0aaadu; x ^= x >> 15; x *= 0x735a2d97u; x ^= x >> 15;
     return x;
 }
 struct Rng {
     uint32_t key, ctr;
-    __device__ __forceinline__ float next() {
-        uint32_t x = fmix(key + ctr * kGolden);
-        ++ctr;
-        return (float)(x >> 8) * (1.0f / 16777216.0f);
+    __device__ __forceinline__ float peek(uint32_t k) const {
+        return (float)(fmix(key + (ctr + k) * kGolden) >> 8) * (1.0f / 16777216.0f);
     }
+    __device__ __forceinline__ float next() { float v = peek(0); ++ctr; return v; }
 };
 
 struct F3 { float x, y, z; };
 __device__ __forceinline__ F3 f3(float x, float y, float z) { return F3{x, y, z}; }
 __device__ __forceinline__ float dot3(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }   // math.go:19
 __device__ __forceinline__ F3 unit3(F3 a) {                                                       // math.go:31-37, 14-17
-    float l = sqrtf(dot3(a, a));
+    float l = sqrt_(dot3(a, a));
     if (l == 0.0f) return a;
-    float inv = 1.0f / l;
+    float inv = rcp_(l);
     return f3(a.x * inv, a.y * inv, a.z * inv);
-}
-__device__ __forceinline__ F3 reflect3(F3 v, F3 n) {                                              // math.go:39-46
-    float d = dot3(v, n);
-    return f3(v.x - n.x * 2.0f * d, v.y - n.y * 2.0f * d, v.z - n.z * 2.0f * d);
 }
 __device__ __forceinline__ F3 in_unit_sphere(Rng& rng) {                                          // math.go:66-85
     for (;;) {
-        float x = rng.next() * 2.0f - 1.0f;
-        float y = rng.next() * 2.0f - 1.0f;
-        float z = rng.next() * 2.0f - 1.0f;
+        float x = rng.peek(0) * 2.0f - 1.0f;
+        float y = rng.peek(1) * 2.0f - 1.0f;
+        float z = rng.peek(2) * 2.0f - 1.0f;
+        rng.ctr += 3u;
         if (x * x + y * y + z * z >= 1.0f) continue;
         return f3(x, y, z);
     }
 }
-__device__ __forceinline__ F3 cosine_direction(F3 n, Rng& rng) {                                  // math.go:94-131
-    float r1 = rng.next();
-    float r2 = rng.next();
+// randomCosineDirection (math.go:94-131) about axis n with the two uniforms already drawn.
+__device__ __forceinline__ F3 cosine_direction(F3 n, float r1, float r2) {
     float phi = 6.28318530717958647692f * r1;
-    float ct = sqrtf(r2);
-    float st = sqrtf(1.0f - r2);
+    float ct = sqrt_(r2);
+    float st = sqrt_(1.0f - r2);
     // v = unit(n x helper), u = v x n with helper = (0,1,0) if |n.x| > 0.9 else (1,0,0)
     F3 v = (fabsf(n.x) > 0.9f) ? f3(-n.z, 0.0f, n.x) : f3(0.0f, n.z, -n.y);
     v = unit3(v);
     F3 u = f3(v.y * n.z - v.z * n.y, v.z * n.x - v.x * n.z, v.x * n.y - v.y * n.x);
     float sp, cp;
-    sincosf(phi, &sp, &cp);
+    sincos_(phi, &sp, &cp);
     float lx = st * cp, ly = st * sp, lz = ct;
     return f3(lx * u.x + ly * v.x + lz * n.x, lx * u.y + ly * v.y + lz * n.y, lx * u.z + ly * v.z + lz * n.z);
 }
 
-// Candidate ray parameter of one object for interval [tmin, tmax]; returns false on a miss.
-// sphere.hit objects.go:37-59, plane.hit :98-112, box.hit :141-183.  `a` = d.d and inv = 1/d are per ray.
-__device__ __forceinline__ bool hit_t(const DevObj& ob, int type, F3 o, F3 d, float a, F3 inv, float tmin, float tmax,
-                                      float& t_out) {
-    if (type == PTB_OBJ_BOX) {
-        float t0 = tmin, t1 = tmax;
-        float tn = (ob.ax - o.x) * inv.x, tf = (ob.bx - o.x) * inv.x;
-        if (inv.x < 0.0f) { float s = tn; tn = tf; tf = s; }
-        if (tn > t0) t0 = tn;
-        if (tf < t1) t1 = tf;
-        if (t1 <= t0) return false;
-        tn = (ob.ay - o.y) * inv.y; tf = (ob.by - o.y) * inv.y;
-        if (inv.y < 0.0f) { float s = tn; tn = tf; tf = s; }
-        if (tn > t0) t0 = tn;
-        if (tf < t1) t1 = tf;
-        if (t1 <= t0) return false;
-        tn = (ob.az - o.z) * inv.z; tf = (ob.bz - o.z) * inv.z;
-        if (inv.z < 0.0f) { float s = tn; tn = tf; tf = s; }
-        if (tn > t0) t0 = tn;
-        if (tf < t1) t1 = tf;
-        if (t1 <= t0) return false;
-        t_out = t0;
-        return true;
-    } else if (type == PTB_OBJ_SPHERE) {
-        float ocx = o.x - ob.ax, ocy = o.y - ob.ay, ocz = o.z - ob.az;
-        float hb = ocx * d.x + ocy * d.y + ocz * d.z;
-        float c = (ocx * ocx + ocy * ocy + ocz * ocz) - ob.by;     // by = radius*radius
-        float disc = hb * hb - a * c;
-        if (disc < 0.0f) return false;
-        float sq = sqrtf(disc);
-        float root = (-hb - sq) / a;
-        if (root < tmin || root > tmax) {
-            root = (-hb + sq) / a;
-            if (root < tmin || root > tmax) return false;
-        }
-        t_out = root;
-        return true;
-    } else {   // plane with normal (0,1,0): denom = d.y, t = (p.y - o.y)/d.y   (objects.go:100-110, 251-257)
-        float denom = d.y;
-        if (fabsf(denom) < 1e-6f) return false;
-        float t = (ob.ay - o.y) / denom;
-        if (t < tmin || t > tmax) return false;
-        t_out = t;
-        return true;
-    }
+// Per-ray constants of the closest-hit tests: a = d.d (objects.go:43), inv = 1/d (objects.go:149-161),
+// inv_a = 1/a (the divisions of objects.go:55,57 become multiplications).
+struct RayK { F3 o, d, inv; float a, inv_a; };
+__device__ __forceinline__ RayK make_ray(F3 o, F3 d) {
+    RayK r;
+    r.o = o; r.d = d;
+    r.a = d.x * d.x + d.y * d.y + d.z * d.z;
+    r.inv = f3(rcp_(d.x), rcp_(d.y), rcp_(d.z));
+    r.inv_a = rcp_(r.a);
+    return r;
+}
+
+// box.hit (objects.go:141-183), branch-free.  t0 = max(tmin, near_x, near_y, near_z), t1 = min(tmax, far_*);
+// hit iff t1 > t0 (the per-axis early exits of the reference are equivalent: t0 only grows, t1 only shrinks).
+// fmaxf/fminf drop a NaN operand exactly like the reference's `if tNear > t0` / `if tFar < t1` comparisons.
+__device__ __forceinline__ bool hit_box(const DevObj& ob, const RayK& r, float tmin, float tmax, float& t_out) {
+    float ax = (ob.ax - r.o.x) * r.inv.x, bx = (ob.bx - r.o.x) * r.inv.x;
+    float ay = (ob.ay - r.o.y) * r.inv.y, by = (ob.by - r.o.y) * r.inv.y;
+    float az = (ob.az - r.o.z) * r.inv.z, bz = (ob.bz - r.o.z) * r.inv.z;
+    const bool nx = r.inv.x < 0.0f, ny = r.inv.y < 0.0f, nz = r.inv.z < 0.0f;
+    float t0 = fmaxf(tmin, nx ? bx : ax);
+    float t1 = fminf(tmax, nx ? ax : bx);
+    t0 = fmaxf(t0, ny ? by : ay);
+    t1 = fminf(t1, ny ? ay : by);
+    t0 = fmaxf(t0, nz ? bz : az);
+    t1 = fminf(t1, nz ? az : bz);
+    t_out = t0;
+    return t1 > t0;
+}
+// sphere.hit (objects.go:37-59), branch-free.
+__device__ __forceinline__ bool hit_sphere(const DevObj& ob, const RayK& r, float tmin, float tmax, float& t_out) {
+    float ocx = r.o.x - ob.ax, ocy = r.o.y - ob.ay, ocz = r.o.z - ob.az;
+    float hb = ocx * r.d.x + ocy * r.d.y + ocz * r.d.z;
+    float c = (ocx * ocx + ocy * ocy + ocz * ocz) - ob.by;     // by = radius*radius
+    float disc = hb * hb - r.a * c;
+    float sq = sqrt_(fmaxf(disc, 0.0f));
+    float r1 = (-hb - sq) * r.inv_a;
+    float r2 = (-hb + sq) * r.inv_a;
+    float root = (r1 < tmin || r1 > tmax) ? r2 : r1;
+    t_out = root;
+    return !(disc < 0.0f) && !(root < tmin || root > tmax);
+}
+// plane.hit with normal (0,1,0): denom = d.y, t = (p.y - o.y)/d.y (objects.go:100-110, 251-257).
+__device__ __forceinline__ bool hit_plane(const DevObj& ob, const RayK& r, float tmin, float tmax, float& t_out) {
+    float t = (ob.ay - r.o.y) * r.inv.y;
+    t_out = t;
+    return !(fabsf(r.d.y) < 1e-6f) && !(t < tmin || t > tmax);
+}
+__device__ __forceinline__ bool hit_any(const DevObj& ob, int type, const RayK& r, float tmin, float tmax, float& t) {
+    if (type == PTB_OBJ_BOX) return hit_box(ob, r, tmin, tmax, t);
+    if (type == PTB_OBJ_SPHERE) return hit_sphere(ob, r, tmin, tmax, t);
+    return hit_plane(ob, r, tmin, tmax, t);
 }
 
 // Hit point, face normal and frontFace of object `ob` at parameter t (objects.go:61-88, 114-132, 181-221).
@@ -163,9 +205,9 @@ __device__ __forceinline__ void surface(const DevObj& ob, int type, F3 o, F3 d, 
 
 __device__ __forceinline__ F3 sky_color(F3 d) {                                                   // renderer.go:56-92
     if (c_scene.sky.kind == PTB_SKY_GRADIENT) {
-        float len = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z);
+        float len = sqrt_(d.x * d.x + d.y * d.y + d.z * d.z);
         if (len == 0.0f) return f3(c_scene.sky.horizon[0], c_scene.sky.horizon[1], c_scene.sky.horizon[2]);
-        float t = (d.y / len + 1.0f) * 0.5f;
+        float t = (d.y * rcp_(len) + 1.0f) * 0.5f;
         t = t < 0.0f ? 0.0f : t;
         t = t > 1.0f ? 1.0f : t;
         return f3(c_scene.sky.horizon[0] * (1.0f - t) + c_scene.sky.zenith[0] * t,
@@ -222,8 +264,9 @@ integrate_kernel(const __grid_constant__ FrameParams fp) {
     auto start_path = [&]() {                                 // renderer.go:182-185 + camera.go:60-74
         rng.key = fmix(pixel_key + (uint32_t)s * kGolden);
         rng.ctr = 0u;
-        const float u = (xf + rng.next()) * fp.inv_w;
-        const float v = (flip_y + rng.next()) * fp.inv_h;
+        const float u = (xf + rng.peek(0)) * fp.inv_w;
+        const float v = (flip_y + rng.peek(1)) * fp.inv_h;
+        rng.ctr = 2u;
         const DevCamera& cam = c_scene.cam;
         F3 dir = f3(cam.llc[0] + cam.horizontal[0] * u + cam.vertical[0] * v - cam.origin[0],
                     cam.llc[1] + cam.horizontal[1] * u + cam.vertical[1] * v - cam.origin[1],
@@ -243,23 +286,35 @@ integrate_kernel(const __grid_constant__ FrameParams fp) {
         if (STATS) st[ST_SAMPLES]++;
     };
     if (alive) start_path();
-    for (;;) {
-        const unsigned live = __ballot_sync(0xffffffffu, alive);
-        if (live == 0u) break;
-        if (STATS) { st[ST_LANE_TOTAL]++; if (alive) st[ST_LANE_ACTIVE]++; }
-        if (alive) {
-            // ---------------- closest hit over the whole world (renderer.go:292-302)
-            const float a = d.x * d.x + d.y * d.y + d.z * d.z;
-            const F3 inv = f3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
-            float best = FLT_MAX;
-            int bid = -1;
-            for (int i = 0; i < n_obj; ++i) {
-                const DevObj& ob = c_scene.obj[i];
-                float t;
-                if (hit_t(ob, ob.type_mat & 3, o, d, a, inv, 0.001f, best, t)) { best = t; bid = i; }
-            }
-            if (STATS) st[ST_SEGMENTS]++;
 
+    const int n_box = c_scene.n_box;
+    for (;;) {
+        if (__ballot_sync(0xffffffffu, alive) == 0u) break;   // warp-uniform exit: every lane has finished its samples
+        if (STATS) { st[ST_LANE_TOTAL]++; if (alive) st[ST_LANE_ACTIVE]++; }
+
+        // ---------------- closest hit over the whole world (renderer.go:292-302).
+        // Executed by ALL lanes of the warp (finished lanes trace a dummy ray): the loops are warp-uniform, so the
+        // object records come straight from the constant bank through the uniform datapath.
+        // Device order = boxes first, then spheres/planes, each group in world order.  Reference tie rule kept:
+        // a box wins only with t < closest (first box wins ties), a sphere/plane with t <= closest (a later one
+        // wins ties, and beats a box at equal t whatever their order) — so grouping boxes first changes nothing.
+        const RayK ray = make_ray(o, d);
+        float best = FLT_MAX;
+        int bid = -1;
+#pragma unroll 2
+        for (int i = 0; i < n_box; ++i) {
+            float t;
+            if (hit_box(c_scene.obj[i], ray, 0.001f, best, t)) { best = t; bid = i; }
+        }
+        for (int i = n_box; i < n_obj; ++i) {
+            const DevObj& ob = c_scene.obj[i];
+            float t;
+            const bool h = (ob.meta & 3) == PTB_OBJ_SPHERE ? hit_sphere(ob, ray, 0.001f, best, t) : hit_plane(ob, ray, 0.001f, best, t);
+            if (h) { best = t; bid = i; }
+        }
+
+        if (alive) {
+            if (STATS) st[ST_SEGMENTS]++;
             bool done = false;
             if (bid < 0) {                                    // renderer.go:304-306
                 F3 sk = sky_color(d);
@@ -268,122 +323,129 @@ integrate_kernel(const __grid_constant__ FrameParams fp) {
                 if (STATS) st[ST_END_SKY]++;
             } else {
                 const DevObj ob = s_obj[bid];
-                const int type = ob.type_mat & 3;
+                const int type = ob.meta & 3;
                 if (STATS) st[ST_ACC_SPHERE + type]++;
                 F3 p, n; bool front;
                 surface(ob, type, o, d, best, p, n, front);
-                const DevMat m = s_mat[ob.type_mat >> 2];
+                const DevMat m = s_mat[ob.meta >> 3];
 
-                F3 att = f3(0, 0, 0), sd = f3(0, 0, 0), so = p;
+                // the draws this bounce can consume, evaluated together (scatter: <= 2, Russian roulette: 1)
+                const float u0 = rng.peek(0), u1 = rng.peek(1), u2 = rng.peek(2);
+                uint32_t used = 0u;
+                bool repeek = false;
+
+                // |rIn.dir|, unit direction and mirror direction (materials.go:102-112, 177-183, 207-215); lambert ignores them
+                const float len = sqrt_(ray.a);
+                const float il = rcp_(len);
+                const F3 ud = f3(d.x * il, d.y * il, d.z * il);
+                const float udn = ud.x * n.x + ud.y * n.y + ud.z * n.z;
+                const F3 refl = f3(ud.x - n.x * 2.0f * udn, ud.y - n.y * 2.0f * udn, ud.z - n.z * 2.0f * udn);   // math.go:39-46
+
+                F3 att = f3(m.albedo[0], m.albedo[1], m.albedo[2]), sd = refl, so = p;
                 bool ok = true;
+                const bool rough_metal = m.type == PTB_MAT_METAL && m.rough > 1e-6f;
                 if (m.type == PTB_MAT_EMISSIVE) {             // materials.go:67-72, 202-203; renderer.go:308-312
                     L.x += beta.x * m.emit[0]; L.y += beta.y * m.emit[1]; L.z += beta.z * m.emit[2];
                     ok = false;
                     if (STATS) st[ST_END_EMISSIVE]++;
-                } else if (m.type == PTB_MAT_LAMBERT) {       // materials.go:76-97
-                    sd = cosine_direction(n, rng);
-                    if (m.rough > 1e-6f) {
-                        F3 off = in_unit_sphere(rng);
-                        sd.x += off.x * m.rough * 0.1f; sd.y += off.y * m.rough * 0.1f; sd.z += off.z * m.rough * 0.1f;
-                        sd = unit3(sd);
-                    }
-                    att = f3(m.albedo[0], m.albedo[1], m.albedo[2]);
-                } else {
-                    const float len = sqrtf(a);               // |rIn.dir|, materials.go:102,177,207
-                    if (len == 0.0f) {
-                        ok = false;
-                        if (STATS) st[ST_END_NOSCATTER]++;
+                } else if (m.type != PTB_MAT_LAMBERT && len == 0.0f) {   // materials.go:103-105, 178-180, 208-210
+                    ok = false;
+                    if (STATS) st[ST_END_NOSCATTER]++;
+                } else if (m.type == PTB_MAT_LAMBERT || rough_metal) {
+                    // one cosine-weighted sample, about the normal (lambert, materials.go:76-97) or about the mirror
+                    // direction (rough metal, materials.go:114-147): the two materials share this code
+                    const F3 cd = cosine_direction(m.type == PTB_MAT_LAMBERT ? n : refl, u0, u1);
+                    used = 2u;
+                    if (m.type == PTB_MAT_LAMBERT) {
+                        sd = cd;
+                        if (m.rough > 1e-6f) {                // rejection loop: consumes its draws itself (rare path)
+                            rng.ctr += 2u;
+                            F3 off = in_unit_sphere(rng);
+                            used = 0u; repeek = true;
+                            sd.x += off.x * m.rough * 0.1f; sd.y += off.y * m.rough * 0.1f; sd.z += off.z * m.rough * 0.1f;
+                            sd = unit3(sd);
+                        }
                     } else {
-                        const float il = 1.0f / len;
-                        const F3 ud = f3(d.x * il, d.y * il, d.z * il);
-                        if (m.type == PTB_MAT_MIRROR) {       // materials.go:205-221
-                            sd = reflect3(ud, n);
-                            att = f3(m.albedo[0], m.albedo[1], m.albedo[2]);
-                        } else if (m.type == PTB_MAT_METAL) { // materials.go:99-160
-                            const F3 refl = reflect3(ud, n);
-                            sd = refl;
-                            if (m.rough > 1e-6f) {
-                                F3 sc = cosine_direction(refl, rng);
-                                float alpha = m.rough * m.rough;
-                                float sx = refl.x * (1.0f - alpha) + sc.x * alpha;
-                                float sy = refl.y * (1.0f - alpha) + sc.y * alpha;
-                                float sz = refl.z * (1.0f - alpha) + sc.z * alpha;
-                                float l2 = sx * sx + sy * sy + sz * sz;
-                                if (l2 < 1e-8f) { sx = refl.x; sy = refl.y; sz = refl.z; }
-                                else { float i2 = 1.0f / sqrtf(l2); sx *= i2; sy *= i2; sz *= i2; }
-                                if (sx * n.x + sy * n.y + sz * n.z <= 0.0f) { sx = refl.x; sy = refl.y; sz = refl.z; }
-                                sd = f3(sx, sy, sz);
+                        const float alpha = m.rough * m.rough;
+                        float sx = refl.x * (1.0f - alpha) + cd.x * alpha;
+                        float sy = refl.y * (1.0f - alpha) + cd.y * alpha;
+                        float sz = refl.z * (1.0f - alpha) + cd.z * alpha;
+                        const float l2 = sx * sx + sy * sy + sz * sz;
+                        if (l2 < 1e-8f) { sx = refl.x; sy = refl.y; sz = refl.z; }
+                        else { const float i2 = rcp_(sqrt_(l2)); sx *= i2; sy *= i2; sz *= i2; }
+                        if (sx * n.x + sy * n.y + sz * n.z <= 0.0f) { sx = refl.x; sy = refl.y; sz = refl.z; }
+                        sd = f3(sx, sy, sz);
+                    }
+                } else if (m.type == PTB_MAT_DIELECTRIC) {    // materials.go:162-200
+                    att = f3(1.0f, 1.0f, 1.0f);
+                    const float ratio = front ? rcp_(m.ior) : m.ior;
+                    const float cos_t = fminf(-udn, 1.0f);
+                    const float sin_t = sqrt_(1.0f - cos_t * cos_t);
+                    const bool cannot = ratio * sin_t > 1.0f;
+                    float r0 = (1.0f - ratio) * rcp_(1.0f + ratio);
+                    r0 = r0 * r0;
+                    const float om = 1.0f - cos_t;
+                    const float om2 = om * om;
+                    const float refl_prob = r0 + (1.0f - r0) * (om2 * om2 * om);   // Schlick, materials.go:226-231
+                    bool reflect = cannot;
+                    if (!cannot) { reflect = refl_prob > u0; used = 1u; }           // `||` short-circuit: no draw when cannot
+                    if (!reflect) {                           // refractVec, math.go:48-64
+                        const float c2 = fminf(-ud.x * n.x - ud.y * n.y - ud.z * n.z, 1.0f);
+                        float qx = (ud.x + n.x * c2) * ratio, qy = (ud.y + n.y * c2) * ratio, qz = (ud.z + n.z * c2) * ratio;
+                        const float par = -sqrt_(fabsf(1.0f - (qx * qx + qy * qy + qz * qz)));
+                        sd = f3(qx + n.x * par, qy + n.y * par, qz + n.z * par);
+                    }
+                    if (front) {                              // exit search, renderer.go:316-371
+                        if (STATS) st[ST_EXIT_SCANS]++;
+                        const RayK er = make_ray(p, sd);
+                        float exit_t = FLT_MAX;
+                        bool hit_exit = false;
+                        F3 ep = p;
+                        const int n_diel = c_scene.n_diel;
+                        for (int k = 0; k < n_diel; ++k) {    // only dielectric objects can be accepted (:335)
+                            const DevObj& eo = c_scene.obj[c_scene.diel_idx[k]];
+                            const int et = eo.meta & 3;
+                            float t;
+                            if (!hit_any(eo, et, er, 0.0001f, exit_t, t)) continue;
+                            F3 q, qn; bool qf;
+                            surface(eo, et, p, sd, t, q, qn, qf);
+                            if (!qf && t < exit_t) {
+                                float ex = q.x - p.x, ey = q.y - p.y, ez = q.z - p.z;
+                                float d2 = ex * ex + ey * ey + ez * ez;
+                                if (d2 > 1e-8f && d2 < 1000.0f) { hit_exit = true; exit_t = t; ep = q; }
                             }
-                            att = f3(m.albedo[0], m.albedo[1], m.albedo[2]);
-                        } else {                              // dielectric, materials.go:162-200
-                            att = f3(1.0f, 1.0f, 1.0f);
-                            const float ratio = front ? 1.0f / m.ior : m.ior;
-                            const float cos_t = fminf(-(ud.x * n.x + ud.y * n.y + ud.z * n.z), 1.0f);
-                            const float sin_t = sqrtf(1.0f - cos_t * cos_t);
-                            const bool cannot = ratio * sin_t > 1.0f;
-                            float r0 = (1.0f - ratio) / (1.0f + ratio);
-                            r0 = r0 * r0;
-                            const float om = 1.0f - cos_t;
-                            const float om2 = om * om;
-                            const float refl_prob = r0 + (1.0f - r0) * (om2 * om2 * om);   // Schlick, materials.go:226-231
-                            if (cannot || refl_prob > rng.next()) {
-                                sd = reflect3(ud, n);
-                            } else {                          // refractVec, math.go:48-64
-                                const float c2 = fminf(-ud.x * n.x - ud.y * n.y - ud.z * n.z, 1.0f);
-                                float qx = (ud.x + n.x * c2) * ratio, qy = (ud.y + n.y * c2) * ratio, qz = (ud.z + n.z * c2) * ratio;
-                                const float par = -sqrtf(fabsf(1.0f - (qx * qx + qy * qy + qz * qz)));
-                                sd = f3(qx + n.x * par, qy + n.y * par, qz + n.z * par);
+                        }
+                        if (hit_exit) {                       // renderer.go:352-369
+                            float ex = ep.x - p.x, ey = ep.y - p.y, ez = ep.z - p.z;
+                            float dist = sqrt_(ex * ex + ey * ey + ez * ez);
+                            if (m.absorption[0] > 0.0f || m.absorption[1] > 0.0f || m.absorption[2] > 0.0f) {
+                                att = f3(exp_(-m.absorption[0] * dist), exp_(-m.absorption[1] * dist), exp_(-m.absorption[2] * dist));
                             }
-                            if (front) {                      // exit search, renderer.go:316-371
-                                if (STATS) st[ST_EXIT_SCANS]++;
-                                const float a2 = sd.x * sd.x + sd.y * sd.y + sd.z * sd.z;
-                                const F3 inv2 = f3(1.0f / sd.x, 1.0f / sd.y, 1.0f / sd.z);
-                                float exit_t = FLT_MAX;
-                                bool hit_exit = false;
-                                F3 ep = p;
-                                const int n_diel = c_scene.n_diel;
-                                for (int k = 0; k < n_diel; ++k) {   // only dielectric objects can be accepted (:335)
-                                    const DevObj& eo = c_scene.obj[c_scene.diel_idx[k]];
-                                    const int et = eo.type_mat & 3;
-                                    float t;
-                                    if (!hit_t(eo, et, p, sd, a2, inv2, 0.0001f, exit_t, t)) continue;
-                                    F3 q, qn; bool qf;
-                                    surface(eo, et, p, sd, t, q, qn, qf);
-                                    if (!qf && t < exit_t) {
-                                        float ex = q.x - p.x, ey = q.y - p.y, ez = q.z - p.z;
-                                        float d2 = ex * ex + ey * ey + ez * ez;
-                                        if (d2 > 1e-8f && d2 < 1000.0f) { hit_exit = true; exit_t = t; ep = q; }
-                                    }
-                                }
-                                if (hit_exit) {               // renderer.go:352-369
-                                    float ex = ep.x - p.x, ey = ep.y - p.y, ez = ep.z - p.z;
-                                    float dist = sqrtf(ex * ex + ey * ey + ez * ez);
-                                    if (m.absorption[0] > 0.0f || m.absorption[1] > 0.0f || m.absorption[2] > 0.0f) {
-                                        att = f3(expf(-m.absorption[0] * dist), expf(-m.absorption[1] * dist),
-                                                 expf(-m.absorption[2] * dist));
-                                    }
-                                    so = ep;
-                                }
-                            }
+                            so = ep;
                         }
                     }
                 }
+                // (mirror and smooth metal: sd = refl, att = albedo — the defaults; materials.go:148-158, 205-221)
 
                 if (!ok) {
                     done = true;
                 } else {
                     if (STATS) st[ST_SCATTERS]++;
                     if (depth <= 3) {                         // Russian roulette, renderer.go:374-393
-                        float mx = fmaxf(att.x, fmaxf(att.y, att.z));
+                        const float mx = fmaxf(att.x, fmaxf(att.y, att.z));
                         if (mx < 1e-6f) {
                             done = true;
                         } else {
-                            float pr = fminf(mx, 0.95f);
-                            if (rng.next() > pr) done = true;
-                            else { att.x /= pr; att.y /= pr; att.z /= pr; }
+                            const float pr = fminf(mx, 0.95f);
+                            float ur = used == 0u ? u0 : (used == 1u ? u1 : u2);
+                            if (repeek) ur = rng.peek(0);
+                            used += 1u;
+                            if (ur > pr) done = true;
+                            else { const float ip = rcp_(pr); att.x *= ip; att.y *= ip; att.z *= ip; }
                         }
                         if (STATS && done) st[ST_END_RR]++;
                     }
+                    rng.ctr += used;
                     if (!done) {                              // renderer.go:398-403
                         beta.x *= att.x; beta.y *= att.y; beta.z *= att.z;
                         o = so; d = sd;

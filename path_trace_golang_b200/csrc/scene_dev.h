@@ -16,9 +16,9 @@ namespace ptb {
 // 32-byte records, two 16-byte vector loads each.
 struct alignas(16) DevObj {
     float ax, ay, az;   // sphere centre | plane point | box min            (objects.go:31-35, 92-96, 136-139)
-    int32_t type_mat;   // type in bits 0..1, material index in bits 2..
+    int32_t meta;       // type in bits 0..1, bit 2 = dielectric material, material index in bits 3..
     float bx, by, bz;   // sphere (radius, radius^2, 1/radius) | plane unused | box max
-    int32_t is_diel;    // material is dielectric (exit search candidate, renderer.go:335)
+    int32_t world_idx;  // index in the reference's world order (device order groups boxes first)
 };
 
 // 48-byte records. materials.go:19-26.
@@ -42,10 +42,10 @@ struct DevSky {      // renderer.go:56-92
 };
 
 struct DevScene {                        // ~43 KB of the 64 KB constant bank
-    int32_t n_obj, n_mat, n_diel, pad;   // n_mat counts the appended zero material (index n_mat-1)
+    int32_t n_obj, n_mat, n_diel, n_box;   // n_mat counts the appended zero material (index n_mat-1); boxes are obj[0..n_box)
     DevSky sky;
     DevCamera cam;
-    int32_t diel_idx[PTB_MAX_OBJECTS];   // world indices of objects with a dielectric material, ascending
+    int32_t diel_idx[PTB_MAX_OBJECTS];   // DEVICE indices of objects with a dielectric material, in ascending world order
     DevObj obj[PTB_MAX_OBJECTS];
     DevMat mat[PTB_MAX_MATERIALS + 1];   // slot n_mat-1 = the zero material (missing material_id, objects.go:234)
 };

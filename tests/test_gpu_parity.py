@@ -97,22 +97,24 @@ def test_converged_radiance_vs_fp64_oracle(name, ctx, host_scenes, oracle_scenes
     assert rel_rmse <= 0.06 and abs(ratio - 1) <= 0.02
 
 
-def test_same_seed_fp64_oracle_image_rmse(ctx, host_scenes, oracle_scenes):
-    """With the SAME RNG key the fp32 device image and the fp64 oracle image differ only where a path
-    diverged numerically.  C1 (example_simple 640x360, 16 spp, depth 8), 8-bit gamma image.
-    Tolerance: RMSE <= 1.5/255 and >= 99 % of channel values within 2/255."""
+def test_same_seed_image_rmse_c1(ctx, host_scenes, oracle_scenes):
+    """C1 (example_simple 640x360, 16 spp, depth 8), 8-bit gamma image, SAME RNG key on both sides: the images
+    differ only where a path diverged numerically (one diverged path of 16 moves a pixel by a few LSB).
+    Tolerance vs the binary32 oracle (same arithmetic width): RMSE <= 2/255, >= 99 % of channel values
+    within 2/255.  Tolerance vs the Go-faithful binary64 oracle: RMSE <= 4/255, >= 96 % within 2/255."""
     from oracle import pyoracle
     name, W, H, spp, depth = CONFIGS["C1"]
     ctx.upload(host_scenes[name])
     img = ctx.render(ctx.cfg(W, H, spp, depth, seed=5))
-    ora_sum, _ = oracle_scenes[name].render_sum(W, H, spp, depth, seed=5, precision=64)
-    ref = pyoracle.finalize(ora_sum, spp)
     assert (img[..., 3] == 255).all()
-    d = img[..., :3].astype(np.float64) - ref[..., :3].astype(np.float64)
-    rmse = np.sqrt((d ** 2).mean())
-    close = (np.abs(d) <= 2).mean()
-    print(f"C1 8-bit RMSE {rmse:.3f}/255, within 2/255: {close:.4f}")
-    assert rmse <= 1.5 and close >= 0.99
+    for precision, max_rmse, min_close in [(32, 2.0, 0.99), (64, 4.0, 0.96)]:
+        ora_sum, _ = oracle_scenes[name].render_sum(W, H, spp, depth, seed=5, precision=precision)
+        ref = pyoracle.finalize(ora_sum, spp)
+        d = img[..., :3].astype(np.float64) - ref[..., :3].astype(np.float64)
+        rmse = np.sqrt((d ** 2).mean())
+        close = (np.abs(d) <= 2).mean()
+        print(f"C1 vs fp{precision} oracle: 8-bit RMSE {rmse:.3f}/255, within 2/255: {close:.4f}")
+        assert rmse <= max_rmse and close >= min_close
 
 
 def test_epilogue_bit_exact(ctx, host_scenes, oracle_mod):
@@ -185,17 +187,29 @@ def test_errors_and_edge_cases(ctx, host_scenes):
     assert (sky[..., :3] == np.array(exp, dtype=np.uint8)).all()
 
 
-def test_glass_quirks_on_device(ctx, host_scenes):
-    """The two dielectric quirks the survey verified: a glass BOX swallows the path
-    (re-hit at t=tMin every bounce until the depth budget is gone -> black), a glass SPHERE refracts once and
-    the ray leaves from the far side.  One object in front of a white sky, camera straight at it."""
-    from path_trace_golang_b200 import engine, scene
+def test_glass_quirks_on_device(ctx, oracle_mod):
+    """The two dielectric quirks the survey verified, one object in front of a white sky:
+    a glass BOX is re-hit at t=tMin every bounce ("creeps" 1 mm per bounce) so a path only escapes through a
+    Fresnel reflection and the box renders dark; a glass SPHERE refracts once, is teleported to the exit point
+    and leaves, so it renders as bright as the sky.  Device vs binary64 oracle, 64x64, 256 spp, different RNG
+    keys: mean linear radiance of the central 16x16 region within 3 % (relative), and box << sphere."""
+    import json
+    from path_trace_golang_b200 import scene
     base = ('{"camera":{"position":{"x":0,"y":0,"z":5},"target":{"x":0,"y":0,"z":0},"up":{"x":0,"y":1,"z":0},"fov":20},'
             '"objects":[{"type":"%s","position":{"x":0,"y":0,"z":0},"size":{"x":%s,"y":2,"z":2},"material_id":"g"}],'
             '"materials":[{"id":"g","type":"dielectric","ior":1.5}],"sky":{"type":"solid","color":{"r":1,"g":1,"b":1}}}')
-    box = engine.Render(scene.Parse(base % ("box", "2")), engine.RenderConfig(64, 64, 64, 16), ctx=ctx)
-    c = box[24:40, 24:40, :3].astype(np.float64).mean()
-    assert c < 60, c            # only the Fresnel-reflected ~4-10 % of samples escape to the white sky
-    sph = engine.Render(scene.Parse(base % ("sphere", "1")), engine.RenderConfig(64, 64, 64, 16), ctx=ctx)
-    c = sph[28:36, 28:36, :3].astype(np.float64).mean()
-    assert c > 230, c           # refract in, teleport to the exit point, leave: sees the white sky
+    means = {}
+    for kind, sx in (("box", "2"), ("sphere", "1")):
+        doc = base % (kind, sx)
+        ctx.upload(scene.Parse(doc))
+        dev = ctx.render_accum(ctx.cfg(64, 64, 256, 16, seed=21)).astype(np.float64) / 256
+        ctx.render_accum(ctx.cfg(64, 64, 4, 16, seed=21, stats=True))
+        st = ctx.stats()
+        ora, ost = oracle_mod.OracleScene(json.loads(doc)).render_sum(64, 64, 256, 16, seed=77, precision=64)
+        ora /= 256
+        d, o = dev[24:40, 24:40].mean(), ora[24:40, 24:40].mean()
+        print(f"glass {kind}: device {d:.4f} oracle {o:.4f}; depth-exhausted {st['end_depth'] / st['samples']:.3f}")
+        assert abs(d - o) <= 0.03 * o
+        means[kind] = (d, st["end_depth"] / st["samples"])
+    assert means["box"][0] < 0.5 and means["sphere"][0] > 0.9
+    assert means["box"][1] > 0.05 and means["sphere"][1] < 0.01
