@@ -105,7 +105,9 @@ typedef struct {
     uint32_t flags;         /* PTB_FLAG_* */
 } ptb_cfg;
 
-#define PTB_FLAG_STATS 1u   /* run the counting variant of the integrator (slower); fills ptb_stats */
+#define PTB_FLAG_STATS 1u       /* run the counting variant of the integrator (slower); fills ptb_stats */
+#define PTB_FLAG_MEGAKERNEL 2u  /* use the pixel-per-lane megakernel instead of the default wavefront-in-shared-memory
+                                   kernel (same results up to fp32 rounding; kept for A/B profiling) */
 
 typedef struct ptb_ctx ptb_ctx;
 

@@ -16,6 +16,7 @@ PTB_OBJ_SPHERE, PTB_OBJ_PLANE, PTB_OBJ_BOX = 0, 1, 2
 PTB_MAT_LAMBERT, PTB_MAT_METAL, PTB_MAT_DIELECTRIC, PTB_MAT_EMISSIVE, PTB_MAT_MIRROR = 0, 1, 2, 3, 4
 PTB_SKY_CONST, PTB_SKY_GRADIENT = 0, 1
 PTB_FLAG_STATS = 1
+PTB_FLAG_MEGAKERNEL = 2
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

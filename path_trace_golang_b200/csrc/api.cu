@@ -51,6 +51,7 @@ struct ptb_ctx {
     uint8_t* d_rgba = nullptr; size_t rgba_cap = 0;
     uint8_t* h_rgba = nullptr; size_t h_rgba_cap = 0;   // pinned staging for ptb_render
     unsigned long long* d_stats = nullptr;
+    unsigned int* d_work = nullptr;
     ptb_stats stats{};
 };
 
@@ -206,7 +207,14 @@ int render_launch(ptb_ctx* c, const ptb_cfg* cfg, int s0, int s1, float* d_accum
     fp.seed_key = fmix_host(cfg->seed ^ 0x9E3779B9u);
     fp.inv_w = 1.0f / (float)(W - 1); fp.inv_h = 1.0f / (float)(H - 1); fp.h_minus_1 = (float)(H - 1);
     fp.scene_blob = c->d_blob; fp.accum = d_accum; fp.accum_resume = resume ? 1 : 0; fp.rgba = d_rgba; fp.stats = stats ? c->d_stats : nullptr;
-    e = launch_integrator(fp, stats, c->h_scene->n_obj, c->h_scene->n_mat, stream);
+    const bool mega = (cfg->flags & PTB_FLAG_MEGAKERNEL) != 0 || cfg->max_depth <= 0;
+    if (mega) {
+        e = launch_integrator(fp, stats, c->h_scene->n_obj, c->h_scene->n_mat, stream);
+    } else {
+        fp.work_counter = c->d_work;
+        CK(c, cudaMemsetAsync(c->d_work, 0, sizeof(unsigned int), stream));
+        e = launch_integrator_wf(fp, stats, c->h_scene->n_obj, c->h_scene->n_mat, c->prop.multiProcessorCount, stream);
+    }
     if (e) return fail(c, PTB_ERR_CUDA, "integrator launch: %s", cudaGetErrorString((cudaError_t)e));
     return PTB_OK;
 }
@@ -258,6 +266,7 @@ int ptb_create(int device, ptb_ctx** out) {
     if ((e = cudaMallocHost((void**)&c->h_scene, sizeof(DevScene))) != cudaSuccess) return bail("cudaMallocHost", e);
     std::memset(c->h_scene, 0, sizeof(DevScene));
     if ((e = cudaMalloc((void**)&c->d_stats, sizeof(unsigned long long) * kStatsWords)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&c->d_work, sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc", e);
     *out = c;
     return PTB_OK;
 }
@@ -266,7 +275,7 @@ void ptb_destroy(ptb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_blob); cudaFree(c->d_world64); cudaFree(c->d_accum); cudaFree(c->d_rgba); cudaFree(c->d_stats);
+    cudaFree(c->d_blob); cudaFree(c->d_world64); cudaFree(c->d_accum); cudaFree(c->d_rgba); cudaFree(c->d_stats); cudaFree(c->d_work);
     if (c->h_scene) cudaFreeHost(c->h_scene);
     if (c->h_rgba) cudaFreeHost(c->h_rgba);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -354,7 +363,14 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
             float r = (float)w.b[0];
             o.bx = r; o.by = r * r; o.bz = 1.0f / r;    // radiusSq (objects.go:46), invRadius (objects.go:68)
         } else { o.bx = (float)w.b[0]; o.by = (float)w.b[1]; o.bz = (float)w.b[2]; }
-        o.meta = w.type | ((w.mat_type == PTB_MAT_DIELECTRIC) << 2) | (w.mat_slot << 3);
+        // shading class of the wavefront kernel: 0 diffuse (lambert, rough metal), 1 specular (mirror, smooth metal),
+        // 2 dielectric, 3 terminate (emissive)
+        int cls = 0;
+        if (w.mat_type == PTB_MAT_METAL) cls = ((float)w.rough > 1e-6f) ? 0 : 1;
+        else if (w.mat_type == PTB_MAT_MIRROR) cls = 1;
+        else if (w.mat_type == PTB_MAT_DIELECTRIC) cls = 2;
+        else if (w.mat_type == PTB_MAT_EMISSIVE) cls = 3;
+        o.meta = w.type | ((w.mat_type == PTB_MAT_DIELECTRIC) << 2) | (cls << 3) | (w.mat_slot << 6);
         o.world_idx = i;
         w64[i].type = w.type; w64[i].pad = 0;
         for (int j = 0; j < 3; j++) { w64[i].a[j] = w.a[j]; w64[i].b[j] = w.b[j]; }

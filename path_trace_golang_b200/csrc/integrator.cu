@@ -34,6 +34,9 @@ __constant__ DevScene c_scene;
 #ifndef PTB_MIN_BLOCKS
 #define PTB_MIN_BLOCKS 8
 #endif
+#ifndef PTB_WF_MIN_BLOCKS
+#define PTB_WF_MIN_BLOCKS 4
+#endif
 
 constexpr uint32_t kGolden = 0x9E3779B9u;
 
@@ -125,57 +128,66 @@ __device__ __forceinline__ F3 cosine_direction(F3 n, float r1, float r2) {
 }
 
 // Per-ray constants of the closest-hit tests: a = d.d (objects.go:43), inv = 1/d (objects.go:149-161),
-// inv_a = 1/a (the divisions of objects.go:55,57 become multiplications).
-struct RayK { F3 o, d, inv; float a, inv_a; };
+// oi = o*inv (so a slab distance (b - o)*inv is one FFMA: b*inv - oi), inv_a = 1/a (the divisions of
+// objects.go:55,57 become multiplications).
+struct RayK { F3 o, d, inv, oi; float a, inv_a; };
 __device__ __forceinline__ RayK make_ray(F3 o, F3 d) {
     RayK r;
     r.o = o; r.d = d;
     r.a = d.x * d.x + d.y * d.y + d.z * d.z;
     r.inv = f3(rcp_(d.x), rcp_(d.y), rcp_(d.z));
+    r.oi = f3(o.x * r.inv.x, o.y * r.inv.y, o.z * r.inv.z);
     r.inv_a = rcp_(r.a);
     return r;
 }
 
-// box.hit (objects.go:141-183), branch-free.  t0 = max(tmin, near_x, near_y, near_z), t1 = min(tmax, far_*);
-// hit iff t1 > t0 (the per-axis early exits of the reference are equivalent: t0 only grows, t1 only shrinks).
-// fmaxf/fminf drop a NaN operand exactly like the reference's `if tNear > t0` / `if tFar < t1` comparisons.
-__device__ __forceinline__ bool hit_box(const DevObj& ob, const RayK& r, float tmin, float tmax, float& t_out) {
-    float ax = (ob.ax - r.o.x) * r.inv.x, bx = (ob.bx - r.o.x) * r.inv.x;
-    float ay = (ob.ay - r.o.y) * r.inv.y, by = (ob.by - r.o.y) * r.inv.y;
-    float az = (ob.az - r.o.z) * r.inv.z, bz = (ob.bz - r.o.z) * r.inv.z;
-    const bool nx = r.inv.x < 0.0f, ny = r.inv.y < 0.0f, nz = r.inv.z < 0.0f;
-    float t0 = fmaxf(tmin, nx ? bx : ax);
-    float t1 = fminf(tmax, nx ? ax : bx);
-    t0 = fmaxf(t0, ny ? by : ay);
-    t1 = fminf(t1, ny ? ay : by);
-    t0 = fmaxf(t0, nz ? bz : az);
-    t1 = fminf(t1, nz ? az : bz);
+// box.hit (objects.go:141-183), branch-free: t0 = max(tmin, near_x, near_y, near_z), t1 = min(tmax, far_x, far_y,
+// far_z), hit iff t1 > t0 (the per-axis early exits of the reference are equivalent: t0 only grows, t1 only
+// shrinks).  near/far of an axis are min/max of the two slab distances, which is what the reference's swap on
+// invD < 0 produces.  [Only difference: a 0*inf = NaN slab distance (origin exactly on a slab plane AND that
+// direction component exactly 0) is dropped by min/max instead of poisoning the comparison; the binary64
+// parity kernel keeps the reference's exact form.]
+__device__ __forceinline__ bool hit_box(float4 lo, float4 hi, const RayK& r, float tmin, float tmax, float& t_out) {
+#if PTB_FAST_MATH
+    const float ax = fmaf(lo.x, r.inv.x, -r.oi.x), bx = fmaf(hi.x, r.inv.x, -r.oi.x);
+    const float ay = fmaf(lo.y, r.inv.y, -r.oi.y), by = fmaf(hi.y, r.inv.y, -r.oi.y);
+    const float az = fmaf(lo.z, r.inv.z, -r.oi.z), bz = fmaf(hi.z, r.inv.z, -r.oi.z);
+#else
+    const float ax = (lo.x - r.o.x) * r.inv.x, bx = (hi.x - r.o.x) * r.inv.x;
+    const float ay = (lo.y - r.o.y) * r.inv.y, by = (hi.y - r.o.y) * r.inv.y;
+    const float az = (lo.z - r.o.z) * r.inv.z, bz = (hi.z - r.o.z) * r.inv.z;
+#endif
+    const float t0 = fmaxf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)), tmin);
+    const float t1 = fminf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), tmax);
     t_out = t0;
     return t1 > t0;
 }
-// sphere.hit (objects.go:37-59), branch-free.
-__device__ __forceinline__ bool hit_sphere(const DevObj& ob, const RayK& r, float tmin, float tmax, float& t_out) {
-    float ocx = r.o.x - ob.ax, ocy = r.o.y - ob.ay, ocz = r.o.z - ob.az;
-    float hb = ocx * r.d.x + ocy * r.d.y + ocz * r.d.z;
-    float c = (ocx * ocx + ocy * ocy + ocz * ocz) - ob.by;     // by = radius*radius
-    float disc = hb * hb - r.a * c;
-    float sq = sqrt_(fmaxf(disc, 0.0f));
-    float r1 = (-hb - sq) * r.inv_a;
-    float r2 = (-hb + sq) * r.inv_a;
-    float root = (r1 < tmin || r1 > tmax) ? r2 : r1;
+// sphere.hit (objects.go:37-59), branch-free.  lo = (centre, -), hi = (radius, radius^2, 1/radius, -).
+__device__ __forceinline__ bool hit_sphere(float4 lo, float4 hi, const RayK& r, float tmin, float tmax, float& t_out) {
+    const float ocx = r.o.x - lo.x, ocy = r.o.y - lo.y, ocz = r.o.z - lo.z;
+    const float hb = ocx * r.d.x + ocy * r.d.y + ocz * r.d.z;
+    const float c = (ocx * ocx + ocy * ocy + ocz * ocz) - hi.y;
+    const float disc = hb * hb - r.a * c;
+    const float sq = sqrt_(fmaxf(disc, 0.0f));
+    const float r1 = (-hb - sq) * r.inv_a;
+    const float r2 = (-hb + sq) * r.inv_a;
+    const float root = (r1 < tmin || r1 > tmax) ? r2 : r1;
     t_out = root;
     return !(disc < 0.0f) && !(root < tmin || root > tmax);
 }
 // plane.hit with normal (0,1,0): denom = d.y, t = (p.y - o.y)/d.y (objects.go:100-110, 251-257).
-__device__ __forceinline__ bool hit_plane(const DevObj& ob, const RayK& r, float tmin, float tmax, float& t_out) {
-    float t = (ob.ay - r.o.y) * r.inv.y;
+__device__ __forceinline__ bool hit_plane(float4 lo, const RayK& r, float tmin, float tmax, float& t_out) {
+    float t = (lo.y - r.o.y) * r.inv.y;
     t_out = t;
     return !(fabsf(r.d.y) < 1e-6f) && !(t < tmin || t > tmax);
 }
-__device__ __forceinline__ bool hit_any(const DevObj& ob, int type, const RayK& r, float tmin, float tmax, float& t) {
-    if (type == PTB_OBJ_BOX) return hit_box(ob, r, tmin, tmax, t);
-    if (type == PTB_OBJ_SPHERE) return hit_sphere(ob, r, tmin, tmax, t);
-    return hit_plane(ob, r, tmin, tmax, t);
+// Constant-bank object record as two 16-byte vectors: lo = (a.xyz, meta), hi = (b.xyz, world_idx).
+__device__ __forceinline__ float4 obj_lo(int i) { return reinterpret_cast<const float4*>(&c_scene.obj[i])[0]; }
+__device__ __forceinline__ float4 obj_hi(int i) { return reinterpret_cast<const float4*>(&c_scene.obj[i])[1]; }
+__device__ __forceinline__ bool hit_any(float4 lo, float4 hi, int type, const RayK& r, float tmin, float tmax, float& t) {
+    if (type == PTB_OBJ_BOX) return hit_box(lo, hi, r, tmin, tmax, t);
+    if (type == PTB_OBJ_SPHERE) return hit_sphere(lo, hi, r, tmin, tmax, t);
+    return hit_plane(lo, r, tmin, tmax, t);
 }
 
 // Hit point, face normal and frontFace of object `ob` at parameter t (objects.go:61-88, 114-132, 181-221).
@@ -304,12 +316,12 @@ integrate_kernel(const __grid_constant__ FrameParams fp) {
 #pragma unroll 2
         for (int i = 0; i < n_box; ++i) {
             float t;
-            if (hit_box(c_scene.obj[i], ray, 0.001f, best, t)) { best = t; bid = i; }
+            if (hit_box(obj_lo(i), obj_hi(i), ray, 0.001f, best, t)) { best = t; bid = i; }
         }
         for (int i = n_box; i < n_obj; ++i) {
-            const DevObj& ob = c_scene.obj[i];
+            const float4 lo = obj_lo(i), hi = obj_hi(i);
             float t;
-            const bool h = (ob.meta & 3) == PTB_OBJ_SPHERE ? hit_sphere(ob, ray, 0.001f, best, t) : hit_plane(ob, ray, 0.001f, best, t);
+            const bool h = (__float_as_int(lo.w) & 3) == PTB_OBJ_SPHERE ? hit_sphere(lo, hi, ray, 0.001f, best, t) : hit_plane(lo, ray, 0.001f, best, t);
             if (h) { best = t; bid = i; }
         }
 
@@ -327,7 +339,7 @@ integrate_kernel(const __grid_constant__ FrameParams fp) {
                 if (STATS) st[ST_ACC_SPHERE + type]++;
                 F3 p, n; bool front;
                 surface(ob, type, o, d, best, p, n, front);
-                const DevMat m = s_mat[ob.meta >> 3];
+                const DevMat m = s_mat[ob.meta >> 6];
 
                 // the draws this bounce can consume, evaluated together (scatter: <= 2, Russian roulette: 1)
                 const float u0 = rng.peek(0), u1 = rng.peek(1), u2 = rng.peek(2);
@@ -403,10 +415,11 @@ integrate_kernel(const __grid_constant__ FrameParams fp) {
                         F3 ep = p;
                         const int n_diel = c_scene.n_diel;
                         for (int k = 0; k < n_diel; ++k) {    // only dielectric objects can be accepted (:335)
-                            const DevObj& eo = c_scene.obj[c_scene.diel_idx[k]];
+                            const int ei = c_scene.diel_idx[k];
+                            const DevObj& eo = c_scene.obj[ei];
                             const int et = eo.meta & 3;
                             float t;
-                            if (!hit_any(eo, et, er, 0.0001f, exit_t, t)) continue;
+                            if (!hit_any(obj_lo(ei), obj_hi(ei), et, er, 0.0001f, exit_t, t)) continue;
                             F3 q, qn; bool qf;
                             surface(eo, et, p, sd, t, q, qn, qf);
                             if (!qf && t < exit_t) {
@@ -485,6 +498,10 @@ integrate_kernel(const __grid_constant__ FrameParams fp) {
     }
 }
 
+}  // namespace ptb
+#include "wavefront.cuh"
+namespace ptb {
+
 __global__ void finalize_kernel(const float* __restrict__ accum, int n_pix, double inv_spp, uchar4* __restrict__ rgba) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_pix) return;
@@ -525,6 +542,31 @@ int launch_integrator(const FrameParams& fp, bool stats, int n_obj, int n_mat, v
     size_t smem = (size_t)(n_obj * 2 + n_mat * 3) * sizeof(uint4);
     if (stats) integrate_kernel<true><<<grid, PTB_BLOCK_THREADS, smem, (cudaStream_t)stream>>>(fp);
     else integrate_kernel<false><<<grid, PTB_BLOCK_THREADS, smem, (cudaStream_t)stream>>>(fp);
+    return (int)cudaGetLastError();
+}
+
+int launch_integrator_wf(const FrameParams& fp, bool stats, int n_obj, int n_mat, int sm_count, void* stream) {
+    static int blocks_per_sm[2] = {0, 0};
+    const size_t smem = ((sizeof(WfState) + 15) / 16 + (size_t)(n_obj * 2 + n_mat * 3)) * sizeof(uint4);
+    if (!blocks_per_sm[stats]) {
+        int nb = 0;
+        cudaError_t e;
+        if (stats) {
+            if (smem > 48 * 1024) cudaFuncSetAttribute(integrate_wf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, integrate_wf_kernel<true>, WF_THREADS, smem);
+        } else {
+            if (smem > 48 * 1024) cudaFuncSetAttribute(integrate_wf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, integrate_wf_kernel<false>, WF_THREADS, smem);
+        }
+        if (e != cudaSuccess) return (int)e;
+        blocks_per_sm[stats] = nb > 0 ? nb : 1;
+    }
+    const long long n_pix = (long long)fp.width * fp.height;
+    long long grid = (long long)sm_count * blocks_per_sm[stats];
+    const long long need = (n_pix + WF_THREADS - 1) / WF_THREADS;
+    if (grid > need) grid = need;
+    if (stats) integrate_wf_kernel<true><<<(unsigned)grid, WF_THREADS, smem, (cudaStream_t)stream>>>(fp);
+    else integrate_wf_kernel<false><<<(unsigned)grid, WF_THREADS, smem, (cudaStream_t)stream>>>(fp);
     return (int)cudaGetLastError();
 }
 

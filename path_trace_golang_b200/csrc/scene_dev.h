@@ -16,7 +16,7 @@ namespace ptb {
 // 32-byte records, two 16-byte vector loads each.
 struct alignas(16) DevObj {
     float ax, ay, az;   // sphere centre | plane point | box min            (objects.go:31-35, 92-96, 136-139)
-    int32_t meta;       // type in bits 0..1, bit 2 = dielectric material, material index in bits 3..
+    int32_t meta;       // bits 0..1 type, bit 2 dielectric material, bits 3..5 shading class (wavefront.cuh), bits 6.. material index
     float bx, by, bz;   // sphere (radius, radius^2, 1/radius) | plane unused | box max
     int32_t world_idx;  // index in the reference's world order (device order groups boxes first)
 };
@@ -71,6 +71,7 @@ struct FrameParams {
     int32_t accum_resume;        // 1: start each pixel's sum from accum[] (progressive batches), 0: from zero
     uint8_t* rgba;               // W*H*4 finalised pixels, or nullptr
     unsigned long long* stats;   // kStatsWords counters, or nullptr
+    unsigned int* work_counter;  // wavefront kernel: next unassigned pixel index (zeroed before the launch)
 };
 
 enum StatWord {
@@ -82,6 +83,7 @@ enum StatWord {
 // launchers (integrator.cu / primary_fp64.cu)
 int upload_scene_constants(const DevScene& host_scene, void* stream);
 int launch_integrator(const FrameParams& fp, bool stats, int n_obj, int n_mat, void* stream);
+int launch_integrator_wf(const FrameParams& fp, bool stats, int n_obj, int n_mat, int sm_count, void* stream);
 int launch_finalize(const float* accum, int width, int height, int spp_total, uint8_t* rgba, void* stream);
 int launch_primary_hits(const Obj64* d_world, int n_obj, const Camera64& cam, int width, int height,
                         double xi_u, double xi_v, int32_t* d_ids, double* d_t, void* stream);

@@ -1,0 +1,339 @@
+// wavefront.cuh — the render loop as a persistent "wavefront in shared memory" kernel (included by integrator.cu).
+//
+// Why: in the pixel-per-lane megakernel (integrate_kernel) every lane of a warp executes the same closest-hit scan,
+// but after it the lanes want different code (sky / emissive / lambert / mirror / glass + exit search / new
+// camera ray), and ncu shows that part running with ~8 of 32 lanes active (profiles/r01_*).  Here the path state
+// lives in shared memory and, after every scan, the CTA's 256 path slots are counting-sorted by the class of
+// work they need, so that a warp shades 32 slots of the SAME class:
+//
+//   loop:  SCAN   thread i <-> slot i      closest hit over the world (warp-uniform, constant-bank operands)
+//          SORT   ballot/popc per class -> per-warp counts -> exclusive scan -> stable permutation (2 barriers)
+//          SHADE  thread i <-> slot perm[i]  scatter / terminate / regenerate, one class per warp (mostly)
+//
+// A slot is bound to one pixel at a time and walks that pixel's samples in order with its fp32 sum in shared
+// memory (deterministic per-pixel sum order, no atomics on radiance); when the pixel is done the slot writes it
+// out and takes the next pixel index from a global atomic counter — dynamic scheduling at pixel granularity, so
+// cheap sky pixels and expensive glass pixels balance across the whole chip.
+//
+// Semantics are those of integrate_kernel (same helpers, same counter-RNG draw order), hence of the reference.
+#pragma once
+
+namespace ptb {
+
+constexpr int WF_THREADS = 256;
+constexpr int WF_WARPS = WF_THREADS / 32;
+enum : int { CL_DIFFUSE = 0, CL_SPEC = 1, CL_DIEL = 2, CL_TERM = 3, CL_REGEN = 4, CL_DEAD = 5, CL_COUNT = 6 };
+
+struct WfState {                       // SoA, one entry per slot
+    float ox[WF_THREADS], oy[WF_THREADS], oz[WF_THREADS];
+    float dx[WF_THREADS], dy[WF_THREADS], dz[WF_THREADS];
+    float bx[WF_THREADS], by[WF_THREADS], bz[WF_THREADS];     // throughput beta
+    float ax[WF_THREADS], ay[WF_THREADS], az[WF_THREADS];     // pixel sum
+    float best[WF_THREADS];
+    int bid[WF_THREADS];
+    uint32_t key[WF_THREADS], ctr[WF_THREADS];
+    int depth[WF_THREADS];             // remaining depth of the live path; 0 = no live path (needs regeneration)
+    int smp[WF_THREADS];               // sample index being traced
+    int pix[WF_THREADS];               // pixel index, -1 = slot retired
+    unsigned short perm[WF_THREADS];   // slot | class << 12
+    int cnt[CL_COUNT * WF_WARPS];
+};
+
+template <bool STATS>
+__global__ void __launch_bounds__(WF_THREADS, PTB_WF_MIN_BLOCKS)
+integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
+    extern __shared__ uint4 s_raw[];
+    WfState& S = *reinterpret_cast<WfState*>(s_raw);
+    uint4* s_blob = s_raw + (sizeof(WfState) + 15) / 16;
+    const int n_obj = c_scene.n_obj;
+    {
+        const int n_words = n_obj * 2 + c_scene.n_mat * 3;
+        for (int i = threadIdx.x; i < n_words; i += blockDim.x) s_blob[i] = fp.scene_blob[i];
+    }
+    const DevObj* __restrict__ s_obj = reinterpret_cast<const DevObj*>(s_blob);
+    const DevMat* __restrict__ s_mat = reinterpret_cast<const DevMat*>(s_blob + 2 * n_obj);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_pix = fp.width * fp.height;
+    const int n_box = c_scene.n_box;
+    unsigned long long st[STATS ? kStatsWords : 1] = {0};
+
+    // Finish the slot's current sample and give it its next camera ray: next sample of the same pixel, or — when the
+    // pixel is complete — write the pixel out and take the next pixel from the global counter (renderer.go:171-221).
+    auto regen = [&](int j, bool sample_done) {
+        int pix = S.pix[j];
+        int s = S.smp[j] + (sample_done ? 1 : 0);
+        if (pix < 0 || s >= fp.s_end) {
+            if (pix >= 0) {                                   // pixel complete: epilogue / accumulation buffer
+                const float sx = S.ax[j], sy = S.ay[j], sz = S.az[j];
+                if (fp.accum) { float* a = fp.accum + (size_t)pix * 3; a[0] = sx; a[1] = sy; a[2] = sz; }
+                if (fp.rgba) {
+                    const double inv_spp = 1.0 / (double)fp.spp_total;
+                    reinterpret_cast<uchar4*>(fp.rgba)[pix] = make_uchar4(to_u8(sx, inv_spp), to_u8(sy, inv_spp), to_u8(sz, inv_spp), 255);
+                }
+            }
+            pix = (int)atomicAdd(fp.work_counter, 1u);
+            if (pix >= n_pix) { S.pix[j] = -1; S.depth[j] = 0; return; }
+            S.pix[j] = pix;
+            s = fp.s_begin;
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+            if (fp.accum_resume) { const float* a = fp.accum + (size_t)pix * 3; a0 = a[0]; a1 = a[1]; a2 = a[2]; }
+            S.ax[j] = a0; S.ay[j] = a1; S.az[j] = a2;
+        }
+        S.smp[j] = s;
+        const int px = pix % fp.width, py = pix / fp.width;
+        Rng rng;
+        rng.key = fmix(fmix(fp.seed_key ^ (uint32_t)pix) + (uint32_t)s * kGolden);
+        rng.ctr = 0u;
+        const float u = ((float)px + rng.peek(0)) * fp.inv_w;                       // renderer.go:182
+        const float v = ((fp.h_minus_1 - (float)py) + rng.peek(1)) * fp.inv_h;      // renderer.go:174,183
+        rng.ctr = 2u;
+        const DevCamera& cam = c_scene.cam;                                         // camera.go:60-74
+        F3 dir = f3(cam.llc[0] + cam.horizontal[0] * u + cam.vertical[0] * v - cam.origin[0],
+                    cam.llc[1] + cam.horizontal[1] * u + cam.vertical[1] * v - cam.origin[1],
+                    cam.llc[2] + cam.horizontal[2] * u + cam.vertical[2] * v - cam.origin[2]);
+        F3 org = f3(cam.origin[0], cam.origin[1], cam.origin[2]);
+        if (cam.lens_radius > 0.0f) {
+            F3 rd = in_unit_sphere(rng);
+            float rx = rd.x * cam.lens_radius, ry = rd.y * cam.lens_radius;
+            F3 off = f3(cam.u[0] * rx + cam.v[0] * ry, cam.u[1] * rx + cam.v[1] * ry, cam.u[2] * rx + cam.v[2] * ry);
+            org = f3(org.x + off.x, org.y + off.y, org.z + off.z);
+            dir = f3(dir.x - off.x, dir.y - off.y, dir.z - off.z);
+        }
+        S.ox[j] = org.x; S.oy[j] = org.y; S.oz[j] = org.z;
+        S.dx[j] = dir.x; S.dy[j] = dir.y; S.dz[j] = dir.z;
+        S.bx[j] = 1.0f; S.by[j] = 1.0f; S.bz[j] = 1.0f;
+        S.key[j] = rng.key; S.ctr[j] = rng.ctr;
+        S.depth[j] = fp.max_depth;
+        if (STATS) st[ST_SAMPLES]++;
+    };
+
+    S.pix[tid] = -1; S.smp[tid] = 0; S.depth[tid] = 0;
+    S.ox[tid] = 0.f; S.oy[tid] = 0.f; S.oz[tid] = 0.f; S.dx[tid] = 0.f; S.dy[tid] = 0.f; S.dz[tid] = 1.f;
+    if (fp.max_depth > 0) regen(tid, false);
+    __syncthreads();
+
+    for (;;) {
+        // ------------------------------------------------------------ SCAN (thread <-> its own slot)
+        const F3 o = f3(S.ox[tid], S.oy[tid], S.oz[tid]);
+        const F3 d = f3(S.dx[tid], S.dy[tid], S.dz[tid]);
+        const int my_depth = S.depth[tid], my_pix = S.pix[tid];
+        const RayK ray = make_ray(o, d);
+        float best = FLT_MAX;
+        int bid = -1;
+#pragma unroll 2
+        for (int i = 0; i < n_box; ++i) {
+            float t;
+            if (hit_box(obj_lo(i), obj_hi(i), ray, 0.001f, best, t)) { best = t; bid = i; }
+        }
+        for (int i = n_box; i < n_obj; ++i) {
+            const float4 lo = obj_lo(i), hi = obj_hi(i);
+            float t;
+            const bool h = (__float_as_int(lo.w) & 3) == PTB_OBJ_SPHERE ? hit_sphere(lo, hi, ray, 0.001f, best, t) : hit_plane(lo, ray, 0.001f, best, t);
+            if (h) { best = t; bid = i; }
+        }
+        int cls;
+        if (my_pix < 0) cls = CL_DEAD;
+        else if (my_depth <= 0) cls = CL_REGEN;
+        else if (bid < 0) cls = CL_TERM;
+        else cls = (s_obj[bid].meta >> 3) & 7;
+        S.best[tid] = best; S.bid[tid] = bid;
+        if (STATS) { st[ST_LANE_TOTAL]++; if (cls <= CL_TERM) { st[ST_LANE_ACTIVE]++; st[ST_SEGMENTS]++; } }
+
+        // ------------------------------------------------------------ SORT (stable counting sort of the 256 slots by class)
+        unsigned mine = 0u, below = 0u;
+#pragma unroll
+        for (int c = 0; c < CL_COUNT; ++c) {
+            const unsigned m = __ballot_sync(0xffffffffu, cls == c);
+            if (lane == c) mine = m;
+            if (cls == c) below = m;
+        }
+        if (lane < CL_COUNT) S.cnt[lane * WF_WARPS + warp] = __popc(mine);
+        __syncthreads();
+        // exclusive prefix over the 48 (class-major, warp-minor) counts, redundantly in every warp
+        int e0 = S.cnt[lane];
+        int e1 = lane < CL_COUNT * WF_WARPS - 32 ? S.cnt[32 + lane] : 0;
+        int i0 = e0, i1 = e1;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, i0, off), b = __shfl_up_sync(0xffffffffu, i1, off);
+            if (lane >= off) { i0 += a; i1 += b; }
+        }
+        const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
+        const int x0 = i0 - e0, x1 = i1 - e1 + tot0;                                  // exclusive
+        const int n_dead = __shfl_sync(0xffffffffu, i1, CL_COUNT * WF_WARPS - 33) - __shfl_sync(0xffffffffu, i1, CL_DEAD * WF_WARPS - 33);   // sum of the CL_DEAD row
+        const int idx = cls * WF_WARPS + warp;
+        const int b0 = __shfl_sync(0xffffffffu, x0, idx & 31), b1 = __shfl_sync(0xffffffffu, x1, idx & 31);
+        const int dest = (idx < 32 ? b0 : b1) + __popc(below & ((1u << lane) - 1u));
+        S.perm[dest] = (unsigned short)(tid | (cls << 12));
+        __syncthreads();
+        if (n_dead == WF_THREADS) break;                                              // every slot retired (CTA-uniform)
+
+        // ------------------------------------------------------------ SHADE (thread <-> slot perm[tid], one class per warp)
+        const unsigned pv = S.perm[tid];
+        const int j = pv & 0xFFF, c = pv >> 12;
+        if (c <= CL_DIEL) {
+            const F3 ro = f3(S.ox[j], S.oy[j], S.oz[j]);
+            const F3 rd = f3(S.dx[j], S.dy[j], S.dz[j]);
+            const float t_hit = S.best[j];
+            const DevObj ob = s_obj[S.bid[j]];
+            const int type = ob.meta & 3;
+            if (STATS) st[ST_ACC_SPHERE + type]++;
+            F3 p, n; bool front;
+            surface(ob, type, ro, rd, t_hit, p, n, front);
+            const DevMat m = s_mat[ob.meta >> 6];
+            Rng rng{S.key[j], S.ctr[j]};
+            int depth = S.depth[j];
+
+            const float u0 = rng.peek(0), u1 = rng.peek(1), u2 = rng.peek(2);
+            uint32_t used = 0u;
+            bool repeek = false;
+            const float a = rd.x * rd.x + rd.y * rd.y + rd.z * rd.z;
+            const float len = sqrt_(a);
+            const float il = rcp_(len);
+            const F3 ud = f3(rd.x * il, rd.y * il, rd.z * il);
+            const float udn = ud.x * n.x + ud.y * n.y + ud.z * n.z;
+            const F3 refl = f3(ud.x - n.x * 2.0f * udn, ud.y - n.y * 2.0f * udn, ud.z - n.z * 2.0f * udn);   // math.go:39-46
+
+            F3 att = f3(m.albedo[0], m.albedo[1], m.albedo[2]), sd = refl, so = p;
+            bool ok = true;
+            if (m.type != PTB_MAT_LAMBERT && len == 0.0f) {   // materials.go:103-105, 178-180, 208-210
+                ok = false;
+                if (STATS) st[ST_END_NOSCATTER]++;
+            } else if (c == CL_DIFFUSE) {                     // lambert (materials.go:76-97) / rough metal (:114-147)
+                const F3 cd = cosine_direction(m.type == PTB_MAT_LAMBERT ? n : refl, u0, u1);
+                used = 2u;
+                if (m.type == PTB_MAT_LAMBERT) {
+                    sd = cd;
+                    if (m.rough > 1e-6f) {                    // rejection loop: consumes its draws itself (rare path)
+                        rng.ctr += 2u;
+                        F3 off = in_unit_sphere(rng);
+                        used = 0u; repeek = true;
+                        sd.x += off.x * m.rough * 0.1f; sd.y += off.y * m.rough * 0.1f; sd.z += off.z * m.rough * 0.1f;
+                        sd = unit3(sd);
+                    }
+                } else {
+                    const float alpha = m.rough * m.rough;
+                    float sx = refl.x * (1.0f - alpha) + cd.x * alpha;
+                    float sy = refl.y * (1.0f - alpha) + cd.y * alpha;
+                    float sz = refl.z * (1.0f - alpha) + cd.z * alpha;
+                    const float l2 = sx * sx + sy * sy + sz * sz;
+                    if (l2 < 1e-8f) { sx = refl.x; sy = refl.y; sz = refl.z; }
+                    else { const float i2 = rcp_(sqrt_(l2)); sx *= i2; sy *= i2; sz *= i2; }
+                    if (sx * n.x + sy * n.y + sz * n.z <= 0.0f) { sx = refl.x; sy = refl.y; sz = refl.z; }
+                    sd = f3(sx, sy, sz);
+                }
+            } else if (c == CL_DIEL) {                        // materials.go:162-200
+                att = f3(1.0f, 1.0f, 1.0f);
+                const float ratio = front ? rcp_(m.ior) : m.ior;
+                const float cos_t = fminf(-udn, 1.0f);
+                const float sin_t = sqrt_(1.0f - cos_t * cos_t);
+                const bool cannot = ratio * sin_t > 1.0f;
+                float r0 = (1.0f - ratio) * rcp_(1.0f + ratio);
+                r0 = r0 * r0;
+                const float om = 1.0f - cos_t;
+                const float om2 = om * om;
+                const float refl_prob = r0 + (1.0f - r0) * (om2 * om2 * om);   // Schlick, materials.go:226-231
+                bool reflect = cannot;
+                if (!cannot) { reflect = refl_prob > u0; used = 1u; }           // `||` short-circuit: no draw when cannot
+                if (!reflect) {                               // refractVec, math.go:48-64
+                    const float c2 = fminf(-ud.x * n.x - ud.y * n.y - ud.z * n.z, 1.0f);
+                    float qx = (ud.x + n.x * c2) * ratio, qy = (ud.y + n.y * c2) * ratio, qz = (ud.z + n.z * c2) * ratio;
+                    const float par = -sqrt_(fabsf(1.0f - (qx * qx + qy * qy + qz * qz)));
+                    sd = f3(qx + n.x * par, qy + n.y * par, qz + n.z * par);
+                }
+                if (front) {                                  // exit search, renderer.go:316-371
+                    if (STATS) st[ST_EXIT_SCANS]++;
+                    const RayK er = make_ray(p, sd);
+                    float exit_t = FLT_MAX;
+                    bool hit_exit = false;
+                    F3 ep = p;
+                    const int n_diel = c_scene.n_diel;
+                    for (int k = 0; k < n_diel; ++k) {        // only dielectric objects can be accepted (:335)
+                        const int ei = c_scene.diel_idx[k];
+                        const DevObj& eo = c_scene.obj[ei];
+                        const int et = eo.meta & 3;
+                        float t;
+                        if (!hit_any(obj_lo(ei), obj_hi(ei), et, er, 0.0001f, exit_t, t)) continue;
+                        F3 q, qn; bool qf;
+                        surface(eo, et, p, sd, t, q, qn, qf);
+                        if (!qf && t < exit_t) {
+                            float ex = q.x - p.x, ey = q.y - p.y, ez = q.z - p.z;
+                            float d2 = ex * ex + ey * ey + ez * ez;
+                            if (d2 > 1e-8f && d2 < 1000.0f) { hit_exit = true; exit_t = t; ep = q; }
+                        }
+                    }
+                    if (hit_exit) {                           // renderer.go:352-369
+                        float ex = ep.x - p.x, ey = ep.y - p.y, ez = ep.z - p.z;
+                        float dist = sqrt_(ex * ex + ey * ey + ez * ez);
+                        if (m.absorption[0] > 0.0f || m.absorption[1] > 0.0f || m.absorption[2] > 0.0f) {
+                            att = f3(exp_(-m.absorption[0] * dist), exp_(-m.absorption[1] * dist), exp_(-m.absorption[2] * dist));
+                        }
+                        so = ep;
+                    }
+                }
+            }
+            // (CL_SPEC — mirror and smooth metal: sd = refl, att = albedo, the defaults; materials.go:148-158, 205-221)
+
+            bool done = !ok;
+            if (ok) {
+                if (STATS) st[ST_SCATTERS]++;
+                if (depth <= 3) {                             // Russian roulette, renderer.go:374-393
+                    const float mx = fmaxf(att.x, fmaxf(att.y, att.z));
+                    if (mx < 1e-6f) {
+                        done = true;
+                    } else {
+                        const float pr = fminf(mx, 0.95f);
+                        float ur = used == 0u ? u0 : (used == 1u ? u1 : u2);
+                        if (repeek) ur = rng.peek(0);
+                        used += 1u;
+                        if (ur > pr) done = true;
+                        else { const float ip = rcp_(pr); att.x *= ip; att.y *= ip; att.z *= ip; }
+                    }
+                    if (STATS && done) st[ST_END_RR]++;
+                }
+                rng.ctr += used;
+                if (!done) {                                  // renderer.go:398-403
+                    if (--depth <= 0) {                       // renderer.go:287-289
+                        done = true;
+                        if (STATS) st[ST_END_DEPTH]++;
+                    }
+                }
+            }
+            if (done) {
+                S.depth[j] = 0;                               // regenerated next iteration, together with the other finished slots
+            } else {
+                S.bx[j] *= att.x; S.by[j] *= att.y; S.bz[j] *= att.z;
+                S.ox[j] = so.x; S.oy[j] = so.y; S.oz[j] = so.z;
+                S.dx[j] = sd.x; S.dy[j] = sd.y; S.dz[j] = sd.z;
+                S.ctr[j] = rng.ctr;
+                S.depth[j] = depth;
+            }
+        } else if (c == CL_TERM) {                            // sky (renderer.go:304-306) or emissive hit (:308-312)
+            F3 e;
+            const int hb = S.bid[j];
+            if (hb < 0) {
+                e = sky_color(f3(S.dx[j], S.dy[j], S.dz[j]));
+                if (STATS) st[ST_END_SKY]++;
+            } else {
+                const DevObj& ob = s_obj[hb];
+                const DevMat& m = s_mat[ob.meta >> 6];
+                e = f3(m.emit[0], m.emit[1], m.emit[2]);
+                if (STATS) { st[ST_END_EMISSIVE]++; st[ST_ACC_SPHERE + (ob.meta & 3)]++; }
+            }
+            S.ax[j] += S.bx[j] * e.x; S.ay[j] += S.by[j] * e.y; S.az[j] += S.bz[j] * e.z;
+        }
+        if (c == CL_TERM || c == CL_REGEN) regen(j, true);
+        __syncthreads();
+    }
+
+    if (STATS) {
+        for (int k = 0; k < kStatsWords; ++k) {
+            unsigned long long v = st[k];
+            for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+            if (lane == 0 && v) atomicAdd(fp.stats + k, v);
+        }
+    }
+}
+
+}  // namespace ptb

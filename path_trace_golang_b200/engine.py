@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import PROGRESS_FN, PtbCfg, PtbDeviceInfo, PtbError, PtbStats, PTB_FLAG_STATS
+from ._lib import PROGRESS_FN, PtbCfg, PtbDeviceInfo, PtbError, PtbStats, PTB_FLAG_MEGAKERNEL, PTB_FLAG_STATS
 from .scene import RenderSettings, Scene
 
 BackendCPU, BackendGPU, BackendCUDA = 0, 1, 2      # backend.go:7-10 + the CUDA backend
@@ -89,9 +89,10 @@ class Context:
         return out
 
     @staticmethod
-    def cfg(width, height, spp, max_depth, seed=1, sample_begin=0, sample_count=0, stats=False) -> PtbCfg:
+    def cfg(width, height, spp, max_depth, seed=1, sample_begin=0, sample_count=0, stats=False, megakernel=False) -> PtbCfg:
+        flags = (PTB_FLAG_STATS if stats else 0) | (PTB_FLAG_MEGAKERNEL if megakernel else 0)
         return PtbCfg(int(width), int(height), int(spp), int(max_depth), int(seed) & 0xFFFFFFFF, int(sample_begin),
-                      int(sample_count), PTB_FLAG_STATS if stats else 0)
+                      int(sample_count), flags)
 
     def render(self, cfg: PtbCfg, out: np.ndarray | None = None, progress=None) -> np.ndarray:
         """ptb_render: host RGBA8 image (H, W, 4)."""

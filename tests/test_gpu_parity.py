@@ -42,8 +42,9 @@ def test_primary_hit_ids_other_offsets(xi, ctx, host_scenes, oracle_scenes):
     assert (ids == oids).all() and (t.view(np.uint64) == ot.view(np.uint64)).all()
 
 
+@pytest.mark.parametrize("mega", [False, True], ids=["wavefront", "megakernel"])
 @pytest.mark.parametrize("name", SCENES)
-def test_path_for_path_vs_fp32_oracle(name, ctx, host_scenes, oracle_scenes):
+def test_path_for_path_vs_fp32_oracle(name, mega, ctx, host_scenes, oracle_scenes):
     """Same counter RNG on both sides => the device traces the same paths as the binary32 oracle.
     1 spp, so a pixel value IS one path's radiance.  libm differences (sincosf/expf, FMA contraction,
     x^5 vs powf) perturb values by ~1e-6 relative and flip a discrete decision (hit/miss on a
@@ -51,7 +52,7 @@ def test_path_for_path_vs_fp32_oracle(name, ctx, host_scenes, oracle_scenes):
     Tolerance: >= 99.5 % of pixels within |d| <= 1e-3 * max(1, |oracle|) per channel."""
     W, H, depth = 320, 180, SCENE_DEPTH[name]
     ctx.upload(host_scenes[name])
-    dev = ctx.render_accum(ctx.cfg(W, H, 1, depth, seed=7)).astype(np.float64)
+    dev = ctx.render_accum(ctx.cfg(W, H, 1, depth, seed=7, megakernel=mega)).astype(np.float64)
     ora, _ = oracle_scenes[name].render_sum(W, H, 1, depth, seed=7, precision=32)
     ok = (np.abs(dev - ora) <= 1e-3 * np.maximum(1.0, np.abs(ora))).all(axis=2)
     frac = ok.mean()
@@ -59,13 +60,14 @@ def test_path_for_path_vs_fp32_oracle(name, ctx, host_scenes, oracle_scenes):
     assert frac >= 0.995
 
 
+@pytest.mark.parametrize("mega", [False, True], ids=["wavefront", "megakernel"])
 @pytest.mark.parametrize("name", SCENES)
-def test_counters_match_oracle(name, ctx, host_scenes, oracle_scenes):
+def test_counters_match_oracle(name, mega, ctx, host_scenes, oracle_scenes):
     """Segment / exit-scan / termination counters of the device equal the oracle's within 0.5 %
     (identical up to the few paths that diverge numerically)."""
     W, H, spp, depth = 256, 144, 4, SCENE_DEPTH[name]
     ctx.upload(host_scenes[name])
-    ctx.render_accum(ctx.cfg(W, H, spp, depth, seed=3, stats=True))
+    ctx.render_accum(ctx.cfg(W, H, spp, depth, seed=3, stats=True, megakernel=mega))
     d = ctx.stats()
     _, o = oracle_scenes[name].render_sum(W, H, spp, depth, seed=3, precision=32)
     assert d["samples"] == o["samples"] == W * H * spp
@@ -74,18 +76,19 @@ def test_counters_match_oracle(name, ctx, host_scenes, oracle_scenes):
     assert abs(d["end_rr"] - o["end_rr"]) <= 0.02 * max(o["end_rr"], 1000)
     assert sum(d["accepts"]) == d["segments"] - d["end_sky"]
     assert d["samples"] == d["end_sky"] + d["end_emissive"] + d["end_rr"] + d["end_depth"] + d["end_noscatter"]
-    assert 0.3 < d["lane_iters_active"] / d["lane_iters_total"] <= 1.0
+    assert 0.2 < d["lane_iters_active"] / d["lane_iters_total"] <= 1.0
 
 
+@pytest.mark.parametrize("mega", [False, True], ids=["wavefront", "megakernel"])
 @pytest.mark.parametrize("name", ["example_simple", "metal_glass_room"])
-def test_converged_radiance_vs_fp64_oracle(name, ctx, host_scenes, oracle_scenes):
+def test_converged_radiance_vs_fp64_oracle(name, mega, ctx, host_scenes, oracle_scenes):
     """Converged-image check against the Go-faithful binary64 oracle with a DIFFERENT RNG key (independent
     estimates).  160x90, 1024 spp each; 10x10-block means of linear RGB.
     Tolerance: relative RMSE over blocks <= 6 % and mean-luminance ratio within 2 % (noise floor of two
     independent 1024-spp estimates in these emitter-lit scenes; measured oracle-vs-oracle is the same order)."""
     W, H, spp, depth = 160, 90, 1024, SCENE_DEPTH[name]
     ctx.upload(host_scenes[name])
-    dev = ctx.render_accum(ctx.cfg(W, H, spp, depth, seed=11)).astype(np.float64) / spp
+    dev = ctx.render_accum(ctx.cfg(W, H, spp, depth, seed=11, megakernel=mega)).astype(np.float64) / spp
     ora, _ = oracle_scenes[name].render_sum(W, H, spp, depth, seed=99, precision=64)
     ora /= spp
     blk = lambda a: a.reshape(H // 10, 10, W // 10, 10, 3).mean(axis=(1, 3))
@@ -117,12 +120,13 @@ def test_same_seed_image_rmse_c1(ctx, host_scenes, oracle_scenes):
         assert rmse <= max_rmse and close >= min_close
 
 
-def test_epilogue_bit_exact(ctx, host_scenes, oracle_mod):
+@pytest.mark.parametrize("mega", [False, True], ids=["wavefront", "megakernel"])
+def test_epilogue_bit_exact(mega, ctx, host_scenes, oracle_mod):
     """Pixel epilogue (renderer.go:189-221): the RGBA8 image of ptb_render equals the oracle's epilogue applied
     to the device's own fp32 sums, byte for byte (ragged frame, not a multiple of the 16x8 CTA tile)."""
     name, W, H, spp, depth = "test_scene", 333, 211, 5, 10
     ctx.upload(host_scenes[name])
-    cfg = ctx.cfg(W, H, spp, depth, seed=2)
+    cfg = ctx.cfg(W, H, spp, depth, seed=2, megakernel=mega)
     img = ctx.render(cfg)
     sums = ctx.render_accum(cfg)
     ref = oracle_mod.finalize(sums.astype(np.float64), spp)
@@ -131,6 +135,18 @@ def test_epilogue_bit_exact(ctx, host_scenes, oracle_mod):
     parent = np.full((H, W + 9, 4), 7, dtype=np.uint8)
     ctx.render(cfg, out=parent[:, :W])
     assert (parent[:, :W] == ref).all() and (parent[:, W:] == 7).all()
+
+
+def test_wavefront_and_megakernel_agree(ctx, host_scenes):
+    """The two integrators trace the same paths with the same draws: per-pixel sums agree to fp32 rounding
+    (<= 1e-4 relative) on >= 99.8 % of the pixels of every scene (the rest: a path whose discrete decision
+    flipped on a last-bit difference — the two kernels contract FMAs differently)."""
+    for name in SCENES:
+        ctx.upload(host_scenes[name])
+        a = ctx.render_accum(ctx.cfg(240, 136, 6, SCENE_DEPTH[name], seed=9))
+        b = ctx.render_accum(ctx.cfg(240, 136, 6, SCENE_DEPTH[name], seed=9, megakernel=True))
+        ok = (np.abs(a - b) <= 1e-4 * np.maximum(1.0, np.abs(b))).all(axis=2).mean()
+        assert ok >= 0.998, (name, ok)
 
 
 def test_sample_ranges_and_progressive(ctx, host_scenes):
