@@ -278,7 +278,7 @@ def main():
             "mrays_per_s": value * rays_per_sample, "rays_per_sample": rays_per_sample,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
-                         "kernel": "integrate_kernel<false>", "kernel_ms": kernel_ms,
+                         "kernel": "integrate_wf_kernel<false>", "kernel_ms": kernel_ms,
                          "flops_per_sample": fps, "simt_lane_utilisation": simt_util,
                          "peak_source": "measured here: ptb_measure_fp32_peak (FFMA microbenchmark, 2 flop/FMA); "
                                         "MEASURED_PEAKS.json has no fp32 entry; nominal 148x128x2x1.965 GHz = 74.5",

@@ -8,8 +8,11 @@ from __future__ import annotations
 import ctypes as C
 import pathlib
 
+import os
+
 _PKG = pathlib.Path(__file__).resolve().parent
-SO_PATH = _PKG / "libptb200.so"
+# PTB200_LIB: load another build of the SAME library (tuning variants made by tools/build_variants.sh)
+SO_PATH = pathlib.Path(os.environ["PTB200_LIB"]) if os.environ.get("PTB200_LIB") else _PKG / "libptb200.so"
 
 PTB_OK, PTB_ERR_INVALID, PTB_ERR_CUDA, PTB_ERR_NO_SCENE, PTB_ERR_LIMIT = 0, -1, -2, -3, -4
 PTB_OBJ_SPHERE, PTB_OBJ_PLANE, PTB_OBJ_BOX = 0, 1, 2

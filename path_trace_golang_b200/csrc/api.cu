@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -199,14 +200,15 @@ int render_launch(ptb_ctx* c, const ptb_cfg* cfg, int s0, int s1, float* d_accum
     if (e) return fail(c, PTB_ERR_CUDA, "constant upload: %s", cudaGetErrorString((cudaError_t)e));
 
     const bool stats = (cfg->flags & PTB_FLAG_STATS) != 0;
-    if (stats) CK(c, cudaMemsetAsync(c->d_stats, 0, sizeof(unsigned long long) * kStatsWords, stream));
+    const bool dbg_timing = std::getenv("PTB_DEBUG_TIMING") != nullptr;   // only meaningful in -DPTB_WF_TIMING builds
+    if (stats || dbg_timing) CK(c, cudaMemsetAsync(c->d_stats, 0, sizeof(unsigned long long) * (kStatsWords + 8), stream));
 
     FrameParams fp{};
     fp.width = W; fp.height = H; fp.s_begin = s0; fp.s_end = s1;
     fp.spp_total = cfg->samples_per_px; fp.max_depth = cfg->max_depth;
     fp.seed_key = fmix_host(cfg->seed ^ 0x9E3779B9u);
     fp.inv_w = 1.0f / (float)(W - 1); fp.inv_h = 1.0f / (float)(H - 1); fp.h_minus_1 = (float)(H - 1);
-    fp.scene_blob = c->d_blob; fp.accum = d_accum; fp.accum_resume = resume ? 1 : 0; fp.rgba = d_rgba; fp.stats = stats ? c->d_stats : nullptr;
+    fp.scene_blob = c->d_blob; fp.accum = d_accum; fp.accum_resume = resume ? 1 : 0; fp.rgba = d_rgba; fp.stats = (stats || dbg_timing) ? c->d_stats : nullptr;
     const bool mega = (cfg->flags & PTB_FLAG_MEGAKERNEL) != 0 || cfg->max_depth <= 0;
     if (mega) {
         e = launch_integrator(fp, stats, c->h_scene->n_obj, c->h_scene->n_mat, stream);
@@ -221,6 +223,13 @@ int render_launch(ptb_ctx* c, const ptb_cfg* cfg, int s0, int s1, float* d_accum
 
 int fetch_stats(ptb_ctx* c, bool stats, float ms) {
     c->stats.last_render_ms = ms;
+    if (std::getenv("PTB_DEBUG_TIMING")) {
+        unsigned long long t[6];
+        cudaMemcpy(t, c->d_stats + kStatsWords, sizeof t, cudaMemcpyDeviceToHost);
+        double tot = 0; for (int k = 0; k < 6; k++) tot += (double)t[k];
+        if (tot > 0) std::fprintf(stderr, "wf warp-cycles: scan %.1f%% sort-compute %.1f%% wait1 %.1f%% wait2 %.1f%% shade %.1f%% wait3 %.1f%%\n",
+                                  100 * t[0] / tot, 100 * t[1] / tot, 100 * t[2] / tot, 100 * t[3] / tot, 100 * t[4] / tot, 100 * t[5] / tot);
+    }
     if (!stats) return PTB_OK;
     unsigned long long w[kStatsWords];
     CK(c, cudaMemcpy(w, c->d_stats, sizeof w, cudaMemcpyDeviceToHost));
@@ -265,7 +274,7 @@ int ptb_create(int device, ptb_ctx** out) {
     if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMallocHost((void**)&c->h_scene, sizeof(DevScene))) != cudaSuccess) return bail("cudaMallocHost", e);
     std::memset(c->h_scene, 0, sizeof(DevScene));
-    if ((e = cudaMalloc((void**)&c->d_stats, sizeof(unsigned long long) * kStatsWords)) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&c->d_stats, sizeof(unsigned long long) * (kStatsWords + 8))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&c->d_work, sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc", e);
     *out = c;
     return PTB_OK;

@@ -35,7 +35,7 @@ __constant__ DevScene c_scene;
 #define PTB_MIN_BLOCKS 8
 #endif
 #ifndef PTB_WF_MIN_BLOCKS
-#define PTB_WF_MIN_BLOCKS 4
+#define PTB_WF_MIN_BLOCKS 6
 #endif
 
 constexpr uint32_t kGolden = 0x9E3779B9u;

@@ -20,7 +20,10 @@
 
 namespace ptb {
 
-constexpr int WF_THREADS = 256;
+#ifndef PTB_WF_THREADS
+#define PTB_WF_THREADS 256
+#endif
+constexpr int WF_THREADS = PTB_WF_THREADS;
 constexpr int WF_WARPS = WF_THREADS / 32;
 enum : int { CL_DIFFUSE = 0, CL_SPEC = 1, CL_DIEL = 2, CL_TERM = 3, CL_REGEN = 4, CL_DEAD = 5, CL_COUNT = 6 };
 
@@ -113,6 +116,13 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
     if (fp.max_depth > 0) regen(tid, false);
     __syncthreads();
 
+#ifdef PTB_WF_TIMING
+    long long tm[6] = {0, 0, 0, 0, 0, 0};
+    long long tq = clock64();
+#define PTB_TICK(k) { long long now_ = clock64(); tm[k] += now_ - tq; tq = now_; }
+#else
+#define PTB_TICK(k)
+#endif
     for (;;) {
         // ------------------------------------------------------------ SCAN (thread <-> its own slot)
         const F3 o = f3(S.ox[tid], S.oy[tid], S.oz[tid]);
@@ -140,6 +150,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
         S.best[tid] = best; S.bid[tid] = bid;
         if (STATS) { st[ST_LANE_TOTAL]++; if (cls <= CL_TERM) { st[ST_LANE_ACTIVE]++; st[ST_SEGMENTS]++; } }
 
+        PTB_TICK(0)
         // ------------------------------------------------------------ SORT (stable counting sort of the 256 slots by class)
         unsigned mine = 0u, below = 0u;
 #pragma unroll
@@ -149,24 +160,37 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
             if (cls == c) below = m;
         }
         if (lane < CL_COUNT) S.cnt[lane * WF_WARPS + warp] = __popc(mine);
+        PTB_TICK(1)
         __syncthreads();
-        // exclusive prefix over the 48 (class-major, warp-minor) counts, redundantly in every warp
-        int e0 = S.cnt[lane];
-        int e1 = lane < CL_COUNT * WF_WARPS - 32 ? S.cnt[32 + lane] : 0;
-        int i0 = e0, i1 = e1;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int a = __shfl_up_sync(0xffffffffu, i0, off), b = __shfl_up_sync(0xffffffffu, i1, off);
-            if (lane >= off) { i0 += a; i1 += b; }
-        }
-        const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
-        const int x0 = i0 - e0, x1 = i1 - e1 + tot0;                                  // exclusive
-        const int n_dead = __shfl_sync(0xffffffffu, i1, CL_COUNT * WF_WARPS - 33) - __shfl_sync(0xffffffffu, i1, CL_DEAD * WF_WARPS - 33);   // sum of the CL_DEAD row
+        PTB_TICK(2)
+        // exclusive prefix over the CL_COUNT x WF_WARPS (class-major, warp-minor) counts, redundantly in every warp
+        constexpr int kEntries = CL_COUNT * WF_WARPS, kChunks = (kEntries + 31) / 32;
+        int ex[kChunks], run = 0, n_dead = 0;
         const int idx = cls * WF_WARPS + warp;
-        const int b0 = __shfl_sync(0xffffffffu, x0, idx & 31), b1 = __shfl_sync(0xffffffffu, x1, idx & 31);
-        const int dest = (idx < 32 ? b0 : b1) + __popc(below & ((1u << lane) - 1u));
+        int base = 0;
+#pragma unroll
+        for (int k = 0; k < kChunks; ++k) {
+            const int e = (k * 32 + lane < kEntries) ? S.cnt[k * 32 + lane] : 0;
+            int inc = e;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int a = __shfl_up_sync(0xffffffffu, inc, off);
+                if (lane >= off) inc += a;
+            }
+            ex[k] = inc - e + run;
+            const int b = __shfl_sync(0xffffffffu, ex[k], idx & 31);
+            if ((idx >> 5) == k) base = b;
+            // retired slots = sum of the CL_DEAD row
+            const int lo_i = CL_DEAD * WF_WARPS - k * 32, hi_i = lo_i + WF_WARPS;
+            const int mine_dead = (lane >= lo_i && lane < hi_i) ? e : 0;
+            n_dead += __reduce_add_sync(0xffffffffu, mine_dead);
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        const int dest = base + __popc(below & ((1u << lane) - 1u));
         S.perm[dest] = (unsigned short)(tid | (cls << 12));
+        PTB_TICK(1)
         __syncthreads();
+        PTB_TICK(3)
         if (n_dead == WF_THREADS) break;                                              // every slot retired (CTA-uniform)
 
         // ------------------------------------------------------------ SHADE (thread <-> slot perm[tid], one class per warp)
@@ -185,9 +209,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
             Rng rng{S.key[j], S.ctr[j]};
             int depth = S.depth[j];
 
-            const float u0 = rng.peek(0), u1 = rng.peek(1), u2 = rng.peek(2);
-            uint32_t used = 0u;
-            bool repeek = false;
+            uint32_t used = 0u;                               // draws consumed by this bounce (classes are warp-coherent: draw lazily)
             const float a = rd.x * rd.x + rd.y * rd.y + rd.z * rd.z;
             const float len = sqrt_(a);
             const float il = rcp_(len);
@@ -201,14 +223,14 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
                 ok = false;
                 if (STATS) st[ST_END_NOSCATTER]++;
             } else if (c == CL_DIFFUSE) {                     // lambert (materials.go:76-97) / rough metal (:114-147)
-                const F3 cd = cosine_direction(m.type == PTB_MAT_LAMBERT ? n : refl, u0, u1);
+                const F3 cd = cosine_direction(m.type == PTB_MAT_LAMBERT ? n : refl, rng.peek(0), rng.peek(1));
                 used = 2u;
                 if (m.type == PTB_MAT_LAMBERT) {
                     sd = cd;
                     if (m.rough > 1e-6f) {                    // rejection loop: consumes its draws itself (rare path)
                         rng.ctr += 2u;
                         F3 off = in_unit_sphere(rng);
-                        used = 0u; repeek = true;
+                        used = 0u;
                         sd.x += off.x * m.rough * 0.1f; sd.y += off.y * m.rough * 0.1f; sd.z += off.z * m.rough * 0.1f;
                         sd = unit3(sd);
                     }
@@ -235,7 +257,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
                 const float om2 = om * om;
                 const float refl_prob = r0 + (1.0f - r0) * (om2 * om2 * om);   // Schlick, materials.go:226-231
                 bool reflect = cannot;
-                if (!cannot) { reflect = refl_prob > u0; used = 1u; }           // `||` short-circuit: no draw when cannot
+                if (!cannot) { reflect = refl_prob > rng.peek(0); used = 1u; }  // `||` short-circuit: no draw when cannot
                 if (!reflect) {                               // refractVec, math.go:48-64
                     const float c2 = fminf(-ud.x * n.x - ud.y * n.y - ud.z * n.z, 1.0f);
                     float qx = (ud.x + n.x * c2) * ratio, qy = (ud.y + n.y * c2) * ratio, qz = (ud.z + n.z * c2) * ratio;
@@ -284,8 +306,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
                         done = true;
                     } else {
                         const float pr = fminf(mx, 0.95f);
-                        float ur = used == 0u ? u0 : (used == 1u ? u1 : u2);
-                        if (repeek) ur = rng.peek(0);
+                        const float ur = rng.peek(used);
                         used += 1u;
                         if (ur > pr) done = true;
                         else { const float ip = rcp_(pr); att.x *= ip; att.y *= ip; att.z *= ip; }
@@ -324,9 +345,14 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
             S.ax[j] += S.bx[j] * e.x; S.ay[j] += S.by[j] * e.y; S.az[j] += S.bz[j] * e.z;
         }
         if (c == CL_TERM || c == CL_REGEN) regen(j, true);
+        PTB_TICK(4)
         __syncthreads();
+        PTB_TICK(5)
     }
 
+#ifdef PTB_WF_TIMING
+    if (lane == 0 && fp.stats) for (int k = 0; k < 6; ++k) atomicAdd(fp.stats + kStatsWords + k, (unsigned long long)tm[k]);
+#endif
     if (STATS) {
         for (int k = 0; k < kStatsWords; ++k) {
             unsigned long long v = st[k];

@@ -9,6 +9,6 @@ $CMD > gpurun_out/${TAG}_plain.json 2> gpurun_out/${TAG}_plain.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_list.log 2>&1
 echo "launch list rc=$?"
 $CMD > gpurun_out/${TAG}_plain2.json 2> gpurun_out/${TAG}_plain2.err &&
-ncu --set full --clock-control none --import-source on -k regex:integrate_kernel -s 1 -c 1 -o gpurun_out/${TAG}_integrate -f $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:integrate_ -s 1 -c 1 -o gpurun_out/${TAG}_integrate -f $CMD > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "full capture rc=$?"
 ls -la gpurun_out | tail -12
