@@ -8,7 +8,6 @@ partial sums) for every N.  SURVEY.md §8(e).
 """
 from __future__ import annotations
 
-import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -62,14 +61,3 @@ def render_distributed(ctx, cfg_full, out_rgba: torch.Tensor | None = None, grou
         rgba = out_rgba if out_rgba is not None else torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
         ctx.finalize_device(accum.data_ptr(), W, H, cfg_full.samples_per_px, rgba.data_ptr(), stream)
     return accum, rgba
-
-
-def finalize_host(rgb_sum: np.ndarray, spp: int) -> np.ndarray:
-    """Pixel epilogue of renderer.go:189-221 on a host array (used by the CPU/gloo tests of the plumbing)."""
-    v = np.sqrt(rgb_sum.astype(np.float64) * (1.0 / spp)) * 255.999
-    v = np.where(v < 0, 0.0, np.where(v > 255.999, 255.999, v))
-    v = np.where(np.isnan(v), 0.0, v)
-    out = np.empty(rgb_sum.shape[:2] + (4,), dtype=np.uint8)
-    out[..., :3] = v.astype(np.uint8)
-    out[..., 3] = 255
-    return out

@@ -1,0 +1,91 @@
+"""N > 1 host-side logic on CPU: sample-range partition, reduce-to-root (gloo, world_size 2 and 3), epilogue.
+The per-rank "renderer" here is the CPU oracle (test infrastructure) — the plumbing under test is
+path_trace_golang_b200.dist, which the GPU path uses unchanged with NCCL."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import ROOT, scene_path
+
+
+def test_sample_range_partition():
+    from path_trace_golang_b200.dist import sample_range
+    for spp in (1, 2, 7, 16, 256, 1000):
+        for world in (1, 2, 3, 4, 8):
+            ranges = [sample_range(spp, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == spp
+            for (a0, a1), (b0, b1) in zip(ranges, ranges[1:]):
+                assert a1 == b0 and a1 >= a0
+            sizes = [b - a for a, b in ranges]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        sample_range(8, 2, 2)
+
+
+def finalize_host(rgb_sum: np.ndarray, spp: int) -> np.ndarray:
+    """Pixel epilogue of renderer.go:189-221 in numpy — a TEST stand-in for ptb_finalize_device, so that the
+    reduce plumbing can be exercised on a CPU-only box."""
+    v = np.sqrt(rgb_sum.astype(np.float64) * (1.0 / spp)) * 255.999
+    v = np.where(v < 0, 0.0, np.where(v > 255.999, 255.999, v))
+    v = np.where(np.isnan(v), 0.0, v)
+    out = np.empty(rgb_sum.shape[:2] + (4,), dtype=np.uint8)
+    out[..., :3] = v.astype(np.uint8)
+    out[..., 3] = 255
+    return out
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, name, W, H, spp, depth, out_path):
+    import sys
+    sys.path.insert(0, str(ROOT))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import pyoracle
+    from path_trace_golang_b200 import dist as pdist
+    ora = pyoracle.OracleScene.load(scene_path(name))
+    b, e = pdist.sample_range(spp, rank, world)
+    if e > b:
+        part, _ = ora.render_sum(W, H, e - b, depth, seed=5, precision=32, threads=2, s_begin=b)
+    else:
+        part = np.zeros((H, W, 3))
+    accum = torch.from_numpy(part.astype(np.float32))
+    pdist.reduce_to_root(accum)
+    if rank == 0:
+        np.save(out_path, finalize_host(accum.numpy(), spp))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,spp", [(2, 8), (3, 2)])
+def test_partition_reduce_epilogue_gloo(world, spp, tmp_path, oracle_mod):
+    """world ranks each trace their sample range; the reduced buffer + epilogue on rank 0 equals the single-process
+    image (fp32 partial sums re-associated: at most 1 LSB on a handful of channel values)."""
+    name, W, H, depth = "example_simple", 96, 54, 8
+    out = tmp_path / "img.npy"
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, name, W, H, spp, depth, str(out)), nprocs=world, join=True)
+    img = np.load(out)
+    ora = oracle_mod.OracleScene.load(scene_path(name))
+    full, _ = ora.render_sum(W, H, spp, depth, seed=5, precision=32, threads=2)
+    ref = oracle_mod.finalize(full, spp)
+    diff = np.abs(img.astype(int) - ref.astype(int))
+    assert diff.max() <= 1 and (diff > 0).mean() < 0.01
+    assert (img[..., 3] == 255).all()
+
+
+def test_finalize_host_matches_oracle_epilogue(oracle_mod):
+    rng = np.random.default_rng(1)
+    sums = (rng.random((31, 17, 3)) ** 3 * 40).astype(np.float32)
+    sums[0, 0] = [0.0, 1e-9, 1e6]
+    assert (finalize_host(sums, 7) == oracle_mod.finalize(sums.astype(np.float64), 7)).all()

@@ -229,3 +229,26 @@ def test_glass_quirks_on_device(ctx, oracle_mod):
         means[kind] = (d, st["end_depth"] / st["samples"])
     assert means["box"][0] < 0.5 and means["sphere"][0] > 0.9
     assert means["box"][1] > 0.05 and means["sphere"][1] < 0.01
+
+
+def test_partition_render_reduce_finalize_on_device(ctx, host_scenes):
+    """The multi-GPU data path with the ranks emulated on one GPU: dist.render_partition into per-rank device
+    buffers (torch tensors, torch's stream), a sum standing in for ncclReduce, ptb_finalize_device — against the
+    one-launch image of ptb_render.  fp32 partial sums are re-associated: <= 1 LSB on < 1 % of channel values."""
+    import torch
+    from path_trace_golang_b200 import dist as pdist
+    name, W, H, spp, depth = "metal_glass_room", 320, 180, 10, 16
+    ctx.upload(host_scenes[name])
+    cfg = ctx.cfg(W, H, spp, depth, seed=8)
+    ref = ctx.render(cfg)
+    for world in (2, 3, 16):          # 16 > spp: some ranks get no samples and contribute zeros
+        stream = torch.cuda.current_stream().cuda_stream
+        parts = [torch.empty((H, W, 3), dtype=torch.float32, device="cuda") for _ in range(world)]
+        active = [pdist.render_partition(ctx, cfg, r, world, parts[r], stream) for r in range(world)]
+        assert sum(active) == min(world, spp)
+        total = torch.stack(parts).sum(dim=0)
+        rgba = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
+        ctx.finalize_device(total.data_ptr(), W, H, spp, rgba.data_ptr(), stream)
+        img = rgba.cpu().numpy()
+        diff = np.abs(img.astype(int) - ref.astype(int))
+        assert diff.max() <= 1 and (diff > 0).mean() < 0.01, (world, diff.max(), (diff > 0).mean())
