@@ -1,0 +1,222 @@
+// Package cuda is the reference-side binding of libptb200.so: the B200 CUDA backend for the per-pixel render
+// loop.  It sits exactly where internal/engine/gpu sits today (gpu.Render, gpu.go:2534) and has the same
+// signature, so engine.RenderInto only needs one more case (see INTEGRATION.md).
+//
+// This file is SOURCE ONLY in this repository: the build image has no Go toolchain.  It binds
+// include/ptb200.h one to one; nothing here computes pixels.
+//
+// Build (in the reference tree): copy this directory to internal/engine/cuda, put ptb200.h on the include
+// path and libptb200.so on the library path:
+//
+//	CGO_CFLAGS="-I/path/to/ptb200/include" CGO_LDFLAGS="-L/path/to/ptb200/path_trace_golang_b200 -lptb200" go build ./...
+package cuda
+
+/*
+#include <stdlib.h>
+#include "ptb200.h"
+
+extern void ptbGoProgress(void* user);   // exported below
+static ptb_progress_fn ptb_go_progress_ptr(void) { return (ptb_progress_fn)ptbGoProgress; }
+*/
+import "C"
+
+import (
+	"errors"
+	"fmt"
+	"image"
+	"runtime/cgo"
+	"sync"
+	"unsafe"
+
+	"github.com/user/pathtracer/internal/scene"
+)
+
+// RenderConfig is a minimal copy of engine.RenderConfig to avoid an import cycle (same trick as gpu.go:226-232).
+type RenderConfig struct {
+	Width        int
+	Height       int
+	SamplesPerPx int
+	MaxDepth     int
+}
+
+// Seed is the key of the counter RNG (the CPU path seeds from the clock, random.go:14-16).
+var Seed uint32 = 1
+
+// Device is the CUDA device ordinal used by the process-wide context.
+var Device = 0
+
+var (
+	mu      sync.Mutex // one render at a time per context (the GL path serialises on its worker, gpu.go:266-297)
+	ctx     *C.ptb_ctx
+	initErr error
+	once    sync.Once
+)
+
+func lastError(c *C.ptb_ctx) error { return errors.New(C.GoString(C.ptb_last_error(c))) }
+
+func ensureContext() error {
+	once.Do(func() {
+		if rc := C.ptb_create(C.int(Device), &ctx); rc != C.PTB_OK {
+			initErr = fmt.Errorf("CUDA initialization failed: %w", lastError(nil))
+		}
+	})
+	return initErr // sticky, like the GL worker's init failure (gpu.go:279-286)
+}
+
+//export ptbGoProgress
+func ptbGoProgress(user unsafe.Pointer) {
+	h := *(*cgo.Handle)(user)
+	h.Value().(func())()
+}
+
+func materialCode(t scene.MaterialType) C.int32_t { // materials.go:33-54
+	switch t {
+	case scene.MaterialMetal:
+		return C.PTB_MAT_METAL
+	case scene.MaterialDielectric:
+		return C.PTB_MAT_DIELECTRIC
+	case scene.MaterialEmissive:
+		return C.PTB_MAT_EMISSIVE
+	case scene.MaterialMirror:
+		return C.PTB_MAT_MIRROR
+	default:
+		return C.PTB_MAT_LAMBERT
+	}
+}
+
+func objectCode(t scene.ObjectType) C.int32_t { // objects.go:237-266
+	switch t {
+	case scene.ObjectSphere, scene.ObjectSphereLight:
+		return C.PTB_OBJ_SPHERE
+	case scene.ObjectPlane:
+		return C.PTB_OBJ_PLANE
+	case scene.ObjectBox:
+		return C.PTB_OBJ_BOX
+	default:
+		return -1 // dropped by the library, like sceneToWorld drops unknown types
+	}
+}
+
+// flatScene owns the C arrays of one ptb_scene.
+type flatScene struct {
+	s    C.ptb_scene
+	free []unsafe.Pointer
+}
+
+func (f *flatScene) ints(v []int32) *C.int32_t {
+	if len(v) == 0 {
+		return nil
+	}
+	p := C.malloc(C.size_t(len(v) * 4))
+	copy(unsafe.Slice((*int32)(p), len(v)), v)
+	f.free = append(f.free, p)
+	return (*C.int32_t)(p)
+}
+
+func (f *flatScene) doubles(v []float64) *C.double {
+	if len(v) == 0 {
+		return nil
+	}
+	p := C.malloc(C.size_t(len(v) * 8))
+	copy(unsafe.Slice((*float64)(p), len(v)), v)
+	f.free = append(f.free, p)
+	return (*C.double)(p)
+}
+
+func (f *flatScene) release() {
+	for _, p := range f.free {
+		C.free(p)
+	}
+}
+
+// flatten turns a scene.Scene into the SoA view of ptb_scene: RAW fields only — convertMaterial, the box min/max
+// arithmetic and newCamera run inside the library (include/ptb200.h).
+func flatten(sc *scene.Scene) *flatScene {
+	f := &flatScene{}
+	byID := make(map[string]int32, len(sc.Materials)) // later duplicate wins (objects.go:226-229)
+	nm := len(sc.Materials)
+	mt := make([]int32, nm)
+	alb, emit, abs := make([]float64, 3*nm), make([]float64, 3*nm), make([]float64, 3*nm)
+	rough, ior, power, smooth := make([]float64, nm), make([]float64, nm), make([]float64, nm), make([]float64, nm)
+	for i, m := range sc.Materials {
+		byID[m.ID] = int32(i)
+		mt[i] = int32(materialCode(m.Type))
+		alb[3*i], alb[3*i+1], alb[3*i+2] = m.Albedo.R, m.Albedo.G, m.Albedo.B
+		emit[3*i], emit[3*i+1], emit[3*i+2] = m.Emit.R, m.Emit.G, m.Emit.B
+		abs[3*i], abs[3*i+1], abs[3*i+2] = m.Absorption.R, m.Absorption.G, m.Absorption.B
+		rough[i], ior[i], power[i], smooth[i] = m.Rough, m.IOR, m.Power, m.Smoothness
+	}
+	no := len(sc.Objects)
+	ot, om := make([]int32, no), make([]int32, no)
+	pos, size := make([]float64, 3*no), make([]float64, 3*no)
+	for i, o := range sc.Objects {
+		ot[i] = int32(objectCode(o.Type))
+		if idx, ok := byID[o.MaterialID]; ok {
+			om[i] = idx
+		} else {
+			om[i] = -1 // zero material, objects.go:234
+		}
+		pos[3*i], pos[3*i+1], pos[3*i+2] = o.Position.X, o.Position.Y, o.Position.Z
+		size[3*i], size[3*i+1], size[3*i+2] = o.Size.X, o.Size.Y, o.Size.Z
+	}
+	s := &f.s
+	s.n_obj, s.obj_type, s.obj_mat, s.obj_pos, s.obj_size = C.int32_t(no), f.ints(ot), f.ints(om), f.doubles(pos), f.doubles(size)
+	s.n_mat, s.mat_type = C.int32_t(nm), f.ints(mt)
+	s.mat_albedo, s.mat_rough, s.mat_ior, s.mat_emit = f.doubles(alb), f.doubles(rough), f.doubles(ior), f.doubles(emit)
+	s.mat_power, s.mat_absorption, s.mat_smoothness = f.doubles(power), f.doubles(abs), f.doubles(smooth)
+	c := sc.Camera
+	s.camera.position = [3]C.double{C.double(c.Position.X), C.double(c.Position.Y), C.double(c.Position.Z)}
+	s.camera.target = [3]C.double{C.double(c.Target.X), C.double(c.Target.Y), C.double(c.Target.Z)}
+	s.camera.up = [3]C.double{C.double(c.Up.X), C.double(c.Up.Y), C.double(c.Up.Z)}
+	s.camera.fov, s.camera.aperture = C.double(c.FOV), C.double(c.Aperture)
+	s.camera.focus_dist, s.camera.aspect_ratio = C.double(c.FocusDist), C.double(c.AspectRatio)
+	// sky selection of renderIntoCPU, renderer.go:56-92
+	if sc.Sky != nil && sc.Sky.Type == "gradient" {
+		s.sky.kind = C.PTB_SKY_GRADIENT
+		s.sky.horizon = [3]C.double{C.double(sc.Sky.Horizon.R), C.double(sc.Sky.Horizon.G), C.double(sc.Sky.Horizon.B)}
+		s.sky.zenith = [3]C.double{C.double(sc.Sky.Zenith.R), C.double(sc.Sky.Zenith.G), C.double(sc.Sky.Zenith.B)}
+	} else {
+		bg := sc.Background
+		if sc.Sky != nil && sc.Sky.Type == "solid" {
+			bg = sc.Sky.Color
+		}
+		s.sky.kind = C.PTB_SKY_CONST
+		s.sky.color = [3]C.double{C.double(bg.R), C.double(bg.G), C.double(bg.B)}
+	}
+	return f
+}
+
+// Render renders sc into img on the CUDA backend.  Same contract as gpu.Render (gpu.go:2534-2546): the caller owns
+// img; a size mismatch is a silent no-op like renderIntoCPU (renderer.go:46-49); progress may be nil.
+// There is no CPU fallback: the error is returned to the caller.
+func Render(sc *scene.Scene, cfg RenderConfig, img *image.RGBA, progress func()) error {
+	b := img.Bounds()
+	if b.Dx() != cfg.Width || b.Dy() != cfg.Height {
+		return nil
+	}
+	if err := ensureContext(); err != nil {
+		return err
+	}
+	mu.Lock()
+	defer mu.Unlock()
+
+	f := flatten(sc)
+	defer f.release()
+	if rc := C.ptb_scene_upload(ctx, &f.s); rc != C.PTB_OK {
+		return fmt.Errorf("ptb_scene_upload: %w", lastError(ctx))
+	}
+	c := C.ptb_cfg{width: C.int32_t(cfg.Width), height: C.int32_t(cfg.Height), samples_per_px: C.int32_t(cfg.SamplesPerPx),
+		max_depth: C.int32_t(cfg.MaxDepth), seed: C.uint32_t(Seed)}
+	var cb C.ptb_progress_fn
+	var user unsafe.Pointer
+	if progress != nil {
+		h := cgo.NewHandle(progress)
+		defer h.Delete()
+		cb, user = C.ptb_go_progress_ptr(), unsafe.Pointer(&h)
+	}
+	off := img.PixOffset(b.Min.X, b.Min.Y)
+	if rc := C.ptb_render(ctx, &c, (*C.uint8_t)(unsafe.Pointer(&img.Pix[off])), C.size_t(img.Stride), cb, user); rc != C.PTB_OK {
+		return fmt.Errorf("ptb_render: %w", lastError(ctx))
+	}
+	return nil
+}
