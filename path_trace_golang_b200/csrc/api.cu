@@ -372,13 +372,13 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
             float r = (float)w.b[0];
             o.bx = r; o.by = r * r; o.bz = 1.0f / r;    // radiusSq (objects.go:46), invRadius (objects.go:68)
         } else { o.bx = (float)w.b[0]; o.by = (float)w.b[1]; o.bz = (float)w.b[2]; }
-        // shading class of the wavefront kernel: 0 diffuse (lambert, rough metal), 1 specular (mirror, smooth metal),
-        // 2 dielectric, 3 terminate (emissive)
-        int cls = 0;
-        if (w.mat_type == PTB_MAT_METAL) cls = ((float)w.rough > 1e-6f) ? 0 : 1;
-        else if (w.mat_type == PTB_MAT_MIRROR) cls = 1;
-        else if (w.mat_type == PTB_MAT_DIELECTRIC) cls = 2;
-        else if (w.mat_type == PTB_MAT_EMISSIVE) cls = 3;
+        // shading class of the wavefront kernel (enum in wavefront.cuh): 0 dielectric, 1 diffuse (lambert, rough metal),
+        // 2 terminate (emissive), 4 specular (mirror, smooth metal)
+        int cls = 1;
+        if (w.mat_type == PTB_MAT_METAL) cls = ((float)w.rough > 1e-6f) ? 1 : 4;
+        else if (w.mat_type == PTB_MAT_MIRROR) cls = 4;
+        else if (w.mat_type == PTB_MAT_DIELECTRIC) cls = 0;
+        else if (w.mat_type == PTB_MAT_EMISSIVE) cls = 2;
         o.meta = w.type | ((w.mat_type == PTB_MAT_DIELECTRIC) << 2) | (cls << 3) | (w.mat_slot << 6);
         o.world_idx = i;
         w64[i].type = w.type; w64[i].pad = 0;

@@ -35,7 +35,7 @@ __constant__ DevScene c_scene;
 #define PTB_MIN_BLOCKS 8
 #endif
 #ifndef PTB_WF_MIN_BLOCKS
-#define PTB_WF_MIN_BLOCKS 6
+#define PTB_WF_MIN_BLOCKS 4
 #endif
 
 constexpr uint32_t kGolden = 0x9E3779B9u;
@@ -563,7 +563,7 @@ int launch_integrator_wf(const FrameParams& fp, bool stats, int n_obj, int n_mat
     }
     const long long n_pix = (long long)fp.width * fp.height;
     long long grid = (long long)sm_count * blocks_per_sm[stats];
-    const long long need = (n_pix + WF_THREADS - 1) / WF_THREADS;
+    const long long need = (n_pix + WF_SLOTS - 1) / WF_SLOTS;
     if (grid > need) grid = need;
     if (stats) integrate_wf_kernel<true><<<(unsigned)grid, WF_THREADS, smem, (cudaStream_t)stream>>>(fp);
     else integrate_wf_kernel<false><<<(unsigned)grid, WF_THREADS, smem, (cudaStream_t)stream>>>(fp);

@@ -23,22 +23,31 @@ namespace ptb {
 #ifndef PTB_WF_THREADS
 #define PTB_WF_THREADS 256
 #endif
+#ifndef PTB_WF_SPT
+#define PTB_WF_SPT 2                   // path slots per thread: the scan tests two rays against each object record it loads
+#endif
 constexpr int WF_THREADS = PTB_WF_THREADS;
 constexpr int WF_WARPS = WF_THREADS / 32;
-enum : int { CL_DIFFUSE = 0, CL_SPEC = 1, CL_DIEL = 2, CL_TERM = 3, CL_REGEN = 4, CL_DEAD = 5, CL_COUNT = 6 };
+constexpr int WF_SPT = PTB_WF_SPT;
+constexpr int WF_SLOTS = WF_THREADS * WF_SPT;
+constexpr int WF_CHUNKS = WF_SLOTS / 32;
+// Classes in sort order = the order in which warps pull 32-slot chunks in the SHADE phase: heaviest first
+// (longest-processing-time-first keeps the phase balanced), TERM and REGEN adjacent (they share the regeneration code).
+// CL_DIEL..CL_SPEC match the class bits the host writes into DevObj::meta (api.cu).
+enum : int { CL_DIEL = 0, CL_DIFFUSE = 1, CL_TERM = 2, CL_REGEN = 3, CL_SPEC = 4, CL_DEAD = 5, CL_COUNT = 6 };
 
 struct WfState {                       // SoA, one entry per slot
-    float ox[WF_THREADS], oy[WF_THREADS], oz[WF_THREADS];
-    float dx[WF_THREADS], dy[WF_THREADS], dz[WF_THREADS];
-    float bx[WF_THREADS], by[WF_THREADS], bz[WF_THREADS];     // throughput beta
-    float ax[WF_THREADS], ay[WF_THREADS], az[WF_THREADS];     // pixel sum
-    float best[WF_THREADS];
-    int bid[WF_THREADS];
-    uint32_t key[WF_THREADS], ctr[WF_THREADS];
-    int depth[WF_THREADS];             // remaining depth of the live path; 0 = no live path (needs regeneration)
-    int smp[WF_THREADS];               // sample index being traced
-    int pix[WF_THREADS];               // pixel index, -1 = slot retired
-    unsigned short perm[WF_THREADS];   // slot | class << 12
+    float ox[WF_SLOTS], oy[WF_SLOTS], oz[WF_SLOTS];
+    float dx[WF_SLOTS], dy[WF_SLOTS], dz[WF_SLOTS];
+    float bx[WF_SLOTS], by[WF_SLOTS], bz[WF_SLOTS];     // throughput beta
+    float ax[WF_SLOTS], ay[WF_SLOTS], az[WF_SLOTS];     // pixel sum
+    float best[WF_SLOTS];
+    int bid[WF_SLOTS];
+    uint32_t key[WF_SLOTS], ctr[WF_SLOTS];
+    int depth[WF_SLOTS];               // remaining depth of the live path; 0 = no live path (needs regeneration)
+    int smp[WF_SLOTS];                 // sample index being traced
+    int pix[WF_SLOTS];                 // pixel index, -1 = slot retired
+    unsigned short perm[WF_SLOTS];     // slot | class << 12
     int cnt[CL_COUNT * WF_WARPS];
 };
 
@@ -111,9 +120,13 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
         if (STATS) st[ST_SAMPLES]++;
     };
 
-    S.pix[tid] = -1; S.smp[tid] = 0; S.depth[tid] = 0;
-    S.ox[tid] = 0.f; S.oy[tid] = 0.f; S.oz[tid] = 0.f; S.dx[tid] = 0.f; S.dy[tid] = 0.f; S.dz[tid] = 1.f;
-    if (fp.max_depth > 0) regen(tid, false);
+#pragma unroll
+    for (int k = 0; k < WF_SPT; ++k) {
+        const int j = tid + k * WF_THREADS;
+        S.pix[j] = -1; S.smp[j] = 0; S.depth[j] = 0;
+        S.ox[j] = 0.f; S.oy[j] = 0.f; S.oz[j] = 0.f; S.dx[j] = 0.f; S.dy[j] = 0.f; S.dz[j] = 1.f;
+        if (fp.max_depth > 0) regen(j, false);
+    }
     __syncthreads();
 
 #ifdef PTB_WF_TIMING
@@ -124,79 +137,119 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
 #define PTB_TICK(k)
 #endif
     for (;;) {
-        // ------------------------------------------------------------ SCAN (thread <-> its own slot)
-        const F3 o = f3(S.ox[tid], S.oy[tid], S.oz[tid]);
-        const F3 d = f3(S.dx[tid], S.dy[tid], S.dz[tid]);
-        const int my_depth = S.depth[tid], my_pix = S.pix[tid];
-        const RayK ray = make_ray(o, d);
-        float best = FLT_MAX;
-        int bid = -1;
+        // ------------------------------------------------------------ SCAN (thread <-> its own WF_SPT slots)
+        RayK ray[WF_SPT];
+        float best[WF_SPT];
+        int bid[WF_SPT];
+#pragma unroll
+        for (int k = 0; k < WF_SPT; ++k) {
+            const int j = tid + k * WF_THREADS;
+            ray[k] = make_ray(f3(S.ox[j], S.oy[j], S.oz[j]), f3(S.dx[j], S.dy[j], S.dz[j]));
+            best[k] = FLT_MAX; bid[k] = -1;
+        }
 #pragma unroll 2
         for (int i = 0; i < n_box; ++i) {
-            float t;
-            if (hit_box(obj_lo(i), obj_hi(i), ray, 0.001f, best, t)) { best = t; bid = i; }
+            const float4 lo = obj_lo(i), hi = obj_hi(i);
+#pragma unroll
+            for (int k = 0; k < WF_SPT; ++k) {
+                float t;
+                if (hit_box(lo, hi, ray[k], 0.001f, best[k], t)) { best[k] = t; bid[k] = i; }
+            }
         }
         for (int i = n_box; i < n_obj; ++i) {
             const float4 lo = obj_lo(i), hi = obj_hi(i);
-            float t;
-            const bool h = (__float_as_int(lo.w) & 3) == PTB_OBJ_SPHERE ? hit_sphere(lo, hi, ray, 0.001f, best, t) : hit_plane(lo, ray, 0.001f, best, t);
-            if (h) { best = t; bid = i; }
+            const bool is_sphere = (__float_as_int(lo.w) & 3) == PTB_OBJ_SPHERE;
+#pragma unroll
+            for (int k = 0; k < WF_SPT; ++k) {
+                float t;
+                const bool h = is_sphere ? hit_sphere(lo, hi, ray[k], 0.001f, best[k], t) : hit_plane(lo, ray[k], 0.001f, best[k], t);
+                if (h) { best[k] = t; bid[k] = i; }
+            }
         }
-        int cls;
-        if (my_pix < 0) cls = CL_DEAD;
-        else if (my_depth <= 0) cls = CL_REGEN;
-        else if (bid < 0) cls = CL_TERM;
-        else cls = (s_obj[bid].meta >> 3) & 7;
-        S.best[tid] = best; S.bid[tid] = bid;
-        if (STATS) { st[ST_LANE_TOTAL]++; if (cls <= CL_TERM) { st[ST_LANE_ACTIVE]++; st[ST_SEGMENTS]++; } }
+        int cls[WF_SPT];
+#pragma unroll
+        for (int k = 0; k < WF_SPT; ++k) {
+            const int j = tid + k * WF_THREADS;
+            if (S.pix[j] < 0) cls[k] = CL_DEAD;
+            else if (S.depth[j] <= 0) cls[k] = CL_REGEN;
+            else if (bid[k] < 0) cls[k] = CL_TERM;
+            else cls[k] = (s_obj[bid[k]].meta >> 3) & 7;
+            S.best[j] = best[k]; S.bid[j] = bid[k];
+            if (STATS) { st[ST_LANE_TOTAL]++; if (cls[k] != CL_DEAD && cls[k] != CL_REGEN) { st[ST_LANE_ACTIVE]++; st[ST_SEGMENTS]++; } }
+        }
 
         PTB_TICK(0)
-        // ------------------------------------------------------------ SORT (stable counting sort of the 256 slots by class)
-        unsigned mine = 0u, below = 0u;
+        // ------------------------------------------------------------ SORT (stable counting sort of the CTA's slots by class)
+        unsigned mine = 0u;                 // lane c < CL_COUNT: this warp's number of class-c slots
+        unsigned before[WF_SPT];            // slots of the same class that precede mine inside this warp
+        {
+            unsigned run_c[WF_SPT];
 #pragma unroll
-        for (int c = 0; c < CL_COUNT; ++c) {
-            const unsigned m = __ballot_sync(0xffffffffu, cls == c);
-            if (lane == c) mine = m;
-            if (cls == c) below = m;
+            for (int k = 0; k < WF_SPT; ++k) { before[k] = 0u; run_c[k] = 0u; }
+#pragma unroll
+            for (int c = 0; c < CL_COUNT; ++c) {
+                unsigned tot = 0u;
+#pragma unroll
+                for (int k = 0; k < WF_SPT; ++k) {
+                    const unsigned m = __ballot_sync(0xffffffffu, cls[k] == c);
+                    if (cls[k] == c) before[k] = tot + __popc(m & ((1u << lane) - 1u));
+                    tot += __popc(m);
+                }
+                if (lane == c) mine = tot;
+            }
         }
-        if (lane < CL_COUNT) S.cnt[lane * WF_WARPS + warp] = __popc(mine);
+        if (lane < CL_COUNT) S.cnt[lane * WF_WARPS + warp] = (int)mine;
         PTB_TICK(1)
         __syncthreads();
         PTB_TICK(2)
         // exclusive prefix over the CL_COUNT x WF_WARPS (class-major, warp-minor) counts, redundantly in every warp
         constexpr int kEntries = CL_COUNT * WF_WARPS, kChunks = (kEntries + 31) / 32;
-        int ex[kChunks], run = 0, n_dead = 0;
-        const int idx = cls * WF_WARPS + warp;
-        int base = 0;
+        int run = 0, n_dead = 0;
+        int base[WF_SPT];
 #pragma unroll
-        for (int k = 0; k < kChunks; ++k) {
-            const int e = (k * 32 + lane < kEntries) ? S.cnt[k * 32 + lane] : 0;
+        for (int k = 0; k < WF_SPT; ++k) base[k] = 0;
+#pragma unroll
+        for (int q = 0; q < kChunks; ++q) {
+            const int e = (q * 32 + lane < kEntries) ? S.cnt[q * 32 + lane] : 0;
             int inc = e;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
                 const int a = __shfl_up_sync(0xffffffffu, inc, off);
                 if (lane >= off) inc += a;
             }
-            ex[k] = inc - e + run;
-            const int b = __shfl_sync(0xffffffffu, ex[k], idx & 31);
-            if ((idx >> 5) == k) base = b;
+            const int ex = inc - e + run;
+#pragma unroll
+            for (int k = 0; k < WF_SPT; ++k) {
+                const int idx = cls[k] * WF_WARPS + warp;
+                const int b = __shfl_sync(0xffffffffu, ex, idx & 31);
+                if ((idx >> 5) == q) base[k] = b;
+            }
             // retired slots = sum of the CL_DEAD row
-            const int lo_i = CL_DEAD * WF_WARPS - k * 32, hi_i = lo_i + WF_WARPS;
+            const int lo_i = CL_DEAD * WF_WARPS - q * 32, hi_i = lo_i + WF_WARPS;
             const int mine_dead = (lane >= lo_i && lane < hi_i) ? e : 0;
             n_dead += __reduce_add_sync(0xffffffffu, mine_dead);
             run += __shfl_sync(0xffffffffu, inc, 31);
         }
-        const int dest = base + __popc(below & ((1u << lane) - 1u));
-        S.perm[dest] = (unsigned short)(tid | (cls << 12));
+#pragma unroll
+        for (int k = 0; k < WF_SPT; ++k)
+            S.perm[base[k] + (int)before[k]] = (unsigned short)((tid + k * WF_THREADS) | (cls[k] << 12));
         PTB_TICK(1)
         __syncthreads();
         PTB_TICK(3)
-        if (n_dead == WF_THREADS) break;                                              // every slot retired (CTA-uniform)
+        if (n_dead == WF_SLOTS) break;                                                // every slot retired (CTA-uniform)
+        const int live_chunks = (WF_SLOTS - n_dead + 31) >> 5;                         // CL_DEAD sorts last
 
-        // ------------------------------------------------------------ SHADE (thread <-> slot perm[tid], one class per warp)
-        const unsigned pv = S.perm[tid];
+        // ------------------------------------------------------------ SHADE (one class per 32-slot chunk of perm[])
+        // Static, serpentine chunk assignment: perm[] is sorted heaviest class first, so warp w takes chunks w,
+        // 2W-1-w, 2W+w, ... and pairs a heavy chunk with a light one (keeps the phase balanced without atomics,
+        // and keeps the loop structure provably uniform so the scan above stays on the uniform datapath).
+#pragma unroll 1
+        for (int q = 0; q < WF_SPT; ++q) {
+        const int chunk = (q & 1) ? (q + 1) * WF_WARPS - 1 - warp : q * WF_WARPS + warp;
+        if (chunk >= live_chunks) continue;
+        const unsigned pv = S.perm[chunk * 32 + lane];
         const int j = pv & 0xFFF, c = pv >> 12;
-        if (c <= CL_DIEL) {
+        if (c == CL_DIEL || c == CL_DIFFUSE || c == CL_SPEC) {
             const F3 ro = f3(S.ox[j], S.oy[j], S.oz[j]);
             const F3 rd = f3(S.dx[j], S.dy[j], S.dz[j]);
             const float t_hit = S.best[j];
@@ -345,6 +398,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
             S.ax[j] += S.bx[j] * e.x; S.ay[j] += S.by[j] * e.y; S.az[j] += S.bz[j] * e.z;
         }
         if (c == CL_TERM || c == CL_REGEN) regen(j, true);
+        }   // chunk loop
         PTB_TICK(4)
         __syncthreads();
         PTB_TICK(5)
