@@ -227,8 +227,12 @@ int fetch_stats(ptb_ctx* c, bool stats, float ms) {
         unsigned long long t[6];
         cudaMemcpy(t, c->d_stats + kStatsWords, sizeof t, cudaMemcpyDeviceToHost);
         double tot = 0; for (int k = 0; k < 6; k++) tot += (double)t[k];
-        if (tot > 0) std::fprintf(stderr, "wf warp-cycles: scan %.1f%% sort-compute %.1f%% wait1 %.1f%% wait2 %.1f%% shade %.1f%% wait3 %.1f%%\n",
-                                  100 * t[0] / tot, 100 * t[1] / tot, 100 * t[2] / tot, 100 * t[3] / tot, 100 * t[4] / tot, 100 * t[5] / tot);
+        if (tot > 0 && t[4] > 0) {
+            const double iters = (double)t[4];                 // CTA-iterations (thread 0 of every CTA)
+            const double warps_iters = iters * 8.0;            // lane 0 of every warp contributes to t[0..2]
+            std::fprintf(stderr, "wf cycles per CTA-iteration: scan %.0f  sort %.0f  shade(mean over warps) %.0f  shade(max over warps) %.0f\n",
+                         t[0] / warps_iters, t[1] / warps_iters, t[2] / warps_iters, t[3] / iters);
+        }
     }
     if (!stats) return PTB_OK;
     unsigned long long w[kStatsWords];

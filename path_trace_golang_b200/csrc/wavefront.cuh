@@ -130,11 +130,16 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
     __syncthreads();
 
 #ifdef PTB_WF_TIMING
+    // tm: 0 scan, 1 sort (both halves), 2 shade (own), 3 shade (CTA max, thread 0 only), 4 iterations
     long long tm[6] = {0, 0, 0, 0, 0, 0};
     long long tq = clock64();
+    __shared__ int s_tmax;
+    if (tid == 0) s_tmax = 0;
 #define PTB_TICK(k) { long long now_ = clock64(); tm[k] += now_ - tq; tq = now_; }
+#define PTB_MARK() { tq = clock64(); }
 #else
 #define PTB_TICK(k)
+#define PTB_MARK()
 #endif
     for (;;) {
         // ------------------------------------------------------------ SCAN (thread <-> its own WF_SPT slots)
@@ -201,7 +206,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
         if (lane < CL_COUNT) S.cnt[lane * WF_WARPS + warp] = (int)mine;
         PTB_TICK(1)
         __syncthreads();
-        PTB_TICK(2)
+        PTB_MARK()
         // exclusive prefix over the CL_COUNT x WF_WARPS (class-major, warp-minor) counts, redundantly in every warp
         constexpr int kEntries = CL_COUNT * WF_WARPS, kChunks = (kEntries + 31) / 32;
         int run = 0, n_dead = 0;
@@ -235,7 +240,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
             S.perm[base[k] + (int)before[k]] = (unsigned short)((tid + k * WF_THREADS) | (cls[k] << 12));
         PTB_TICK(1)
         __syncthreads();
-        PTB_TICK(3)
+        PTB_MARK()
         if (n_dead == WF_SLOTS) break;                                                // every slot retired (CTA-uniform)
         const int live_chunks = (WF_SLOTS - n_dead + 31) >> 5;                         // CL_DEAD sorts last
 
@@ -399,9 +404,16 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
         }
         if (c == CL_TERM || c == CL_REGEN) regen(j, true);
         }   // chunk loop
-        PTB_TICK(4)
+#ifdef PTB_WF_TIMING
+        { long long now_ = clock64(); int dt_ = (int)(now_ - tq); tm[2] += dt_; if (lane == 0) atomicMax(&s_tmax, dt_); }
+#endif
         __syncthreads();
-        PTB_TICK(5)
+#ifdef PTB_WF_TIMING
+        if (tid == 0) { tm[3] += s_tmax; tm[4] += 1; }
+        __syncthreads();
+        if (tid == 0) s_tmax = 0;
+#endif
+        PTB_MARK()
     }
 
 #ifdef PTB_WF_TIMING
