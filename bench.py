@@ -96,6 +96,17 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm)}
 
 
+def cpu_calibrate_spp(name, W, H, depth, threads, target_s, max_spp):
+    """Pick the spp of the bounded CPU sample so that one full-resolution step takes about target_s seconds."""
+    from oracle import pyoracle
+    ora = pyoracle.OracleScene.load(ROOT / "scenes" / f"{name}.json")
+    hh = max(32, H // 8)
+    t0 = time.perf_counter()
+    ora.render_rgba(W, hh, 1, depth, seed=1, threads=threads)       # also warms the thread pool / caches
+    rate = W * hh / max(time.perf_counter() - t0, 1e-6)               # samples/s (slightly pessimistic: includes start-up)
+    return int(max(1, min(max_spp, round(target_s * rate / (W * H)))))
+
+
 def cpu_reference_run(name, W, H, depth, spp_sample, steps, warmup, threads):
     """Times the oracle's renderIntoCPU equivalent (fp64, 32x32 tile queue, `threads` workers)."""
     from oracle import pyoracle
@@ -118,7 +129,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-spp", type=int, default=0, help="spp of the bounded CPU sample (0 = auto, ~15 s)")
+    ap.add_argument("--cpu-spp", type=int, default=0, help="spp of the bounded CPU sample (0 = calibrate: ~15 s, or ~6 s per step for --impl reference)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
@@ -138,7 +149,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cpu_spp = args.cpu_spp or 2
+        cpu_spp = args.cpu_spp or cpu_calibrate_spp(name, W, H, depth, cores, 6.0, spp)
         msps, rays_per_sample, dt = cpu_reference_run(name, W, H, depth, cpu_spp, args.steps, min(args.warmup, 1), cores)
         sample = f"{W}x{H}, {cpu_spp} of {spp} spp per step (samples/s is spp-independent), depth {depth}"
         print(json.dumps({
@@ -277,7 +288,10 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "mrays_per_s": value * rays_per_sample, "rays_per_sample": rays_per_sample,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp32_peak if fp32_peak else None, "traffic": None,
+                         "frac": achieved / fp32_peak if fp32_peak else None, "traffic": 41472,
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one integrate_wf_kernel launch from the ncu "
+                                         "--set full capture profiles/r01e_ncu_details.txt (40 KB read, 1.5 KB written: the scene is "
+                                         "constant/shared-memory resident and the 33 MB image stays in the 126 MB L2 for the kernel's lifetime)",
                          "kernel": "integrate_wf_kernel<false>", "kernel_ms": kernel_ms,
                          "flops_per_sample": fps, "simt_lane_utilisation": simt_util,
                          "peak_source": "measured here: ptb_measure_fp32_peak (FFMA microbenchmark, 2 flop/FMA); "
@@ -292,7 +306,7 @@ def main():
             "clocks": clocks,
         }
         if not args.no_cpu and world == 1:
-            cpu_spp = args.cpu_spp or 4
+            cpu_spp = args.cpu_spp or cpu_calibrate_spp(name, W, H, depth, cores, 15.0, spp)
             msps, _, dt = cpu_reference_run(name, W, H, depth, cpu_spp, 1, 0, cores)
             out["cpu_baseline"] = {"value": msps, "unit": "Msamples/s", "cores": cores, "kind": "port",
                                    "sample": f"{W}x{H}, {cpu_spp} of {spp} spp, depth {depth}, {dt:.1f} s, {cores} worker threads",
