@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 1
+#define PTB_ABI_VERSION 2
 
 enum {
     PTB_OK = 0,
@@ -41,7 +41,8 @@ enum {
 /* Object type codes — same values as the GL plug-in's OBJ_* (gpu.go:244-248).
  * "sphere_light" is a sphere (objects.go:246-252).  Any other code: the object is dropped,
  * like unknown types in sceneToWorld (objects.go:237-266). */
-enum { PTB_OBJ_SPHERE = 0, PTB_OBJ_PLANE = 1, PTB_OBJ_BOX = 2 };
+enum { PTB_OBJ_SPHERE = 0, PTB_OBJ_PLANE = 1, PTB_OBJ_BOX = 2,
+       PTB_OBJ_MESH = 3 /* EXTENSION (not in the reference): triangle mesh, see ptb_scene.n_mesh */ };
 
 /* Material type codes — materialType iota (materials.go:11-17) == MAT_* (gpu.go:236-242).
  * Any scene type string other than metal/dielectric/emissive/mirror maps to LAMBERT
@@ -94,6 +95,15 @@ typedef struct {
     const double* mat_smoothness;  /* [n_mat] */
     ptb_camera camera;
     ptb_sky sky;
+    /* EXTENSION — triangle meshes (the reference has none; north-star: "internal/scene gains a BVH builder that emits
+     * a flattened, cache-line-aligned node array").  An object of type PTB_OBJ_MESH is ONE world entry; obj_mesh[i]
+     * names its mesh; triangles are given in world space, binary32, 9 floats each (v0, v1, v2).  The library builds
+     * the BVH (binned SAH, 64-byte nodes).  Hit rule: Moeller-Trumbore, two-sided, t in [tMin, closest); among
+     * triangles of equal t the lowest triangle index wins; geometric normal.  n_mesh == 0: all three may be NULL. */
+    int32_t n_mesh;
+    const int32_t* obj_mesh;         /* [n_obj] mesh index for PTB_OBJ_MESH objects, -1 otherwise */
+    const int64_t* mesh_tri_begin;   /* [n_mesh+1] triangle range of mesh k = [begin[k], begin[k+1]) */
+    const float* tri_vertices;       /* [9 * mesh_tri_begin[n_mesh]] */
 } ptb_scene;
 
 /* engine.RenderConfig (renderer.go:17-22) + the extra knobs a GPU backend needs. */
@@ -125,7 +135,17 @@ typedef struct {
     uint64_t lane_iters_active; /* integrator loop iterations with the lane alive           */
     uint64_t lane_iters_total;  /* 32 x warp loop iterations (SIMT utilisation denominator) */
     double last_render_ms;      /* device time of the last render call (CUDA events) */
+    uint64_t accepts_mesh;      /* EXTENSION: winning hits on mesh triangles */
+    uint64_t bvh_nodes_visited; /* 64-byte node fetches */
+    uint64_t bvh_tris_tested;   /* 48-byte triangle fetches */
 } ptb_stats;
+
+/* EXTENSION: the BVH built by ptb_scene_upload over the mesh triangles (all zero when the scene has no mesh). */
+typedef struct {
+    int64_t n_triangles, n_nodes;
+    int32_t max_depth, node_bytes, triangle_bytes, reserved;
+    double sah_cost, build_ms;
+} ptb_bvh_info;
 
 typedef struct {
     char name[128];
@@ -179,6 +199,7 @@ int ptb_primary_hits(ptb_ctx* ctx, const ptb_cfg* cfg, double xi_u, double xi_v,
 
 /* Counters of the last render that ran with PTB_FLAG_STATS (last_render_ms is always valid). */
 int ptb_get_stats(ptb_ctx* ctx, ptb_stats* out);
+int ptb_get_bvh_info(ptb_ctx* ctx, ptb_bvh_info* out);
 
 /* Measurement helper: FP32 FMA throughput of the device (2 flop per FMA), the roofline
  * denominator MEASURED_PEAKS.json does not carry. */

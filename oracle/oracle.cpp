@@ -26,7 +26,9 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <algorithm>
 #include <map>
+#include <memory>
 #include <string>
 #include <thread>
 #include <vector>
@@ -156,7 +158,75 @@ template <class R> Material<R> castMat(const Material<double>& m) {
 }
 
 // ---------------------------------------------------------------- primitives (objects.go:9-222)
-enum { objSphere = 0, objPlane = 1, objBox = 2 };
+enum { objSphere = 0, objPlane = 1, objBox = 2, objMesh = 3 };
+
+// ---------------------------------------------------------------- EXTENSION: triangle meshes (not in the reference)
+struct OTri { float v0[3], e1[3], e2[3]; int32_t id; };      // e1 = v1 - v0, e2 = v2 - v0 in binary32, like the device records
+struct OBvhNode { double lo[3], hi[3]; int32_t left, right, first, count; };   // leaf: count > 0
+struct OMesh {
+    std::vector<OTri> tris;
+    std::vector<OBvhNode> nodes;      // median-split BVH, the oracle's own (independent of the product's SAH builder)
+    std::vector<int32_t> order;       // triangle permutation of the BVH leaves
+    bool accel = true;
+    int build(int first, int count, double pad) {
+        OBvhNode n{};
+        for (int k = 0; k < 3; k++) { n.lo[k] = 1e300; n.hi[k] = -1e300; }
+        double clo[3] = {1e300, 1e300, 1e300}, chi[3] = {-1e300, -1e300, -1e300};
+        for (int i = first; i < first + count; i++) {
+            const OTri& t = tris[order[i]];
+            for (int k = 0; k < 3; k++) {
+                const double a = t.v0[k], b = (double)t.v0[k] + t.e1[k], c = (double)t.v0[k] + t.e2[k];
+                n.lo[k] = std::min(n.lo[k], std::min(a, std::min(b, c)) - pad);
+                n.hi[k] = std::max(n.hi[k], std::max(a, std::max(b, c)) + pad);
+                const double ce = (a + b + c) / 3;
+                clo[k] = std::min(clo[k], ce); chi[k] = std::max(chi[k], ce);
+            }
+        }
+        n.first = first; n.count = count; n.left = n.right = -1;
+        const int me = (int)nodes.size();
+        nodes.push_back(n);
+        if (count > 8) {
+            int ax = 0;
+            if (chi[1] - clo[1] > chi[ax] - clo[ax]) ax = 1;
+            if (chi[2] - clo[2] > chi[ax] - clo[ax]) ax = 2;
+            const int mid = first + count / 2;
+            std::nth_element(order.begin() + first, order.begin() + mid, order.begin() + first + count, [&](int32_t a, int32_t b) {
+                const OTri& A = tris[a]; const OTri& B = tris[b];
+                return 3.0 * A.v0[ax] + A.e1[ax] + A.e2[ax] < 3.0 * B.v0[ax] + B.e1[ax] + B.e2[ax];
+            });
+            const int l = build(first, mid - first, pad), r = build(mid, first + count - mid, pad);
+            nodes[me].left = l; nodes[me].right = r; nodes[me].count = 0;
+        }
+        return me;
+    }
+    void finish() {
+        order.resize(tris.size());
+        for (size_t i = 0; i < tris.size(); i++) order[i] = (int32_t)i;
+        double amax = 1;
+        for (auto& t : tris) for (int k = 0; k < 3; k++) amax = std::max(amax, std::fabs((double)t.v0[k]) + std::fabs((double)t.e1[k]) + std::fabs((double)t.e2[k]));
+        nodes.clear();
+        if (!tris.empty()) build(0, (int)tris.size(), 1e-5 * amax);
+    }
+};
+
+// Moeller-Trumbore in Real, operation order shared with the CUDA kernels (primary_fp64.cu / bvh.cuh).
+template <class R> inline bool hitTri(const OTri& tr, const R o[3], const R d[3], R tMin, R tMax, R& tOut) {
+    const R e1x = tr.e1[0], e1y = tr.e1[1], e1z = tr.e1[2], e2x = tr.e2[0], e2y = tr.e2[1], e2z = tr.e2[2];
+    const R px = d[1] * e2z - d[2] * e2y, py = d[2] * e2x - d[0] * e2z, pz = d[0] * e2y - d[1] * e2x;
+    const R det = e1x * px + e1y * py + e1z * pz;
+    if (det == 0) return false;
+    const R idet = (R)1.0 / det;
+    const R tx = o[0] - (R)tr.v0[0], ty = o[1] - (R)tr.v0[1], tz = o[2] - (R)tr.v0[2];
+    const R u = (tx * px + ty * py + tz * pz) * idet;
+    if (u < 0 || u > 1) return false;
+    const R qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
+    const R v = (d[0] * qx + d[1] * qy + d[2] * qz) * idet;
+    if (v < 0 || u + v > 1) return false;
+    const R t = (e2x * qx + e2y * qy + e2z * qz) * idet;
+    if (t < tMin || t > tMax) return false;
+    tOut = t;
+    return true;
+}
 template <class R> struct HitRecord {                                                                  // objects.go:9-15
     V3<R> p{0, 0, 0}, normal{0, 0, 0};
     R t = 0;
@@ -166,9 +236,40 @@ template <class R> struct HitRecord {                                           
 };
 template <class R> struct Object {
     int type;
-    V3<R> a, b;     // sphere: a=centre, b.x=radius | plane: a=point, b=normal | box: a=min, b=max
+    V3<R> a, b;     // sphere: a=centre, b.x=radius | plane: a=point, b=normal | box: a=min, b=max | mesh: bounding box
     Material<R> mat;
+    const OMesh* mesh = nullptr;   // EXTENSION
 };
+
+// Closest triangle of a mesh for t in [tMin, closest): updates closest / best_tri (lowest id wins exact ties).
+template <class R> inline bool hitMesh(const OMesh& m, const Ray<R>& r, R tMin, R& closest, int& best_tri, const OTri*& hit) {
+    const R o[3] = {r.orig.x, r.orig.y, r.orig.z}, d[3] = {r.dir.x, r.dir.y, r.dir.z};
+    bool any = false;
+    auto test = [&](const OTri& tr) {
+        R t;
+        if (!hitTri<R>(tr, o, d, tMin, closest, t)) return;
+        if (t < closest || (best_tri >= 0 && tr.id < best_tri)) { closest = t; best_tri = tr.id; hit = &tr; any = true; }
+    };
+    if (!m.accel || m.tris.size() <= 64) { for (auto& tr : m.tris) test(tr); return any; }
+    int stack[128]; int sp = 0; stack[sp++] = 0;
+    while (sp) {
+        const OBvhNode& n = m.nodes[stack[--sp]];
+        double t0 = (double)tMin, t1 = (double)closest;
+        bool miss = false;
+        for (int k = 0; k < 3 && !miss; k++) {
+            const double invD = 1.0 / (double)d[k];
+            double tn = (n.lo[k] - (double)o[k]) * invD, tf = (n.hi[k] - (double)o[k]) * invD;
+            if (invD < 0) std::swap(tn, tf);
+            if (tn > t0) t0 = tn;
+            if (tf < t1) t1 = tf;
+            if (t1 < t0) miss = true;
+        }
+        if (miss) continue;
+        if (n.count > 0) { for (int i = n.first; i < n.first + n.count; i++) test(m.tris[m.order[i]]); }
+        else { stack[sp++] = n.left; stack[sp++] = n.right; }
+    }
+    return any;
+}
 
 template <class R> inline bool hitSphere(const Object<R>& s, const Ray<R>& r, R tMin, R tMax, HitRecord<R>& rec) {   // objects.go:37-89
     R ocX = r.orig.x - s.a.x, ocY = r.orig.y - s.a.y, ocZ = r.orig.z - s.a.z;
@@ -251,6 +352,7 @@ template <class R> inline bool hitObject(const Object<R>& o, const Ray<R>& r, R 
     switch (o.type) {
     case objSphere: return hitSphere(o, r, tMin, tMax, rec);
     case objPlane: return hitPlane(o, r, tMin, tMax, rec);
+    case objMesh: return false;      // meshes are scanned by closestHit() after the analytic objects
     default: return hitBox(o, r, tMin, tMax, rec);
     }
 }
@@ -398,6 +500,39 @@ template <class R> inline Ray<R> getRay(const Camera<R>& c, R s, R t, Rng* rng) 
     return {c.origin, sub(add(add(c.lowerLeftCorner, mul(c.horizontal, s)), mul(c.vertical, t)), c.origin)};
 }
 
+// Closest-hit scan of renderer.go:292-302 over the analytic objects, then (EXTENSION) over the meshes.
+template <class R>
+inline bool closestHit(const std::vector<Object<R>>& world, const Ray<R>& r, R tMin, HitRecord<R>& rec, orc_stats* st) {
+    bool hitAnything = false;
+    R closest = std::numeric_limits<R>::max();
+    bool any_mesh = false;
+    for (size_t i = 0; i < world.size(); i++) {
+        if (world[i].type == objMesh) { any_mesh = true; continue; }
+        if (st) st->prim_tests++;
+        if (hitObject(world[i], r, tMin, closest, rec)) {
+            hitAnything = true; closest = rec.t; rec.index = (int)i;
+            if (st) st->accepts[world[i].type]++;
+        }
+    }
+    if (any_mesh) {
+        int best_tri = -1; const OTri* tri = nullptr; int mesh_obj = -1;
+        for (size_t i = 0; i < world.size(); i++) {
+            if (world[i].type != objMesh) continue;
+            if (hitMesh<R>(*world[i].mesh, r, tMin, closest, best_tri, tri)) mesh_obj = (int)i;
+        }
+        if (mesh_obj >= 0) {
+            hitAnything = true;
+            rec.t = closest; rec.index = mesh_obj; rec.mat = &world[mesh_obj].mat;
+            rec.p = {r.orig.x + r.dir.x * closest, r.orig.y + r.dir.y * closest, r.orig.z + r.dir.z * closest};
+            V3<R> e1 = {(R)tri->e1[0], (R)tri->e1[1], (R)tri->e1[2]}, e2 = {(R)tri->e2[0], (R)tri->e2[1], (R)tri->e2[2]};
+            V3<R> g = unit(cross(e1, e2));
+            rec.frontFace = dot(r.dir, g) < 0;                 // setFaceNormal, objects.go:17-24
+            rec.normal = rec.frontFace ? g : mul(g, (R)-1);
+        }
+    }
+    return hitAnything;
+}
+
 // ---------------------------------------------------------------- integrator (renderer.go:286-404)
 struct PathLog { int cap = 0, n = 0; int32_t* ids = nullptr; double* t = nullptr; int32_t* ff = nullptr; };
 
@@ -406,19 +541,9 @@ V3<R> rayColorOpt(const Ray<R>& r, const std::vector<Object<R>>& world, const Sk
                   Rng& rng, orc_stats& st, PathLog* log) {
     if (depth <= 0) { st.end_depth++; return {0, 0, 0}; }                                              // :287-289
     const R tMin = (R)0.001;                                                                           // :292
-    bool hitAnything = false;
-    R closest = std::numeric_limits<R>::max();                                                        // math.MaxFloat64 (:294)
     HitRecord<R> rec;
     st.segments++;
-    for (size_t i = 0; i < world.size(); i++) {                                                       // :297-302
-        st.prim_tests++;
-        if (hitObject(world[i], r, tMin, closest, rec)) {
-            hitAnything = true;
-            closest = rec.t;
-            rec.index = (int)i;
-            st.accepts[world[i].type]++;
-        }
-    }
+    const bool hitAnything = closestHit(world, r, tMin, rec, &st);                                     // :294-302
     if (log && log->n < log->cap) {
         log->ids[log->n] = hitAnything ? rec.index : -1;
         log->t[log->n] = hitAnything ? (double)rec.t : 0.0;
@@ -486,6 +611,7 @@ V3<R> rayColorOpt(const Ray<R>& r, const std::vector<Object<R>>& world, const Sk
 
 // ---------------------------------------------------------------- scene handle
 struct orc_scene {
+    std::vector<std::unique_ptr<OMesh>> meshes;   // EXTENSION
     std::vector<Object<double>> world;       // sceneToWorld result (objects.go:225-269)
     orc_raw_camera cam;
     Sky<double> sky;
@@ -496,7 +622,7 @@ template <class R> std::vector<Object<R>> castWorld(const std::vector<Object<dou
     std::vector<Object<R>> out;
     out.reserve(w.size());
     auto cv = [](V3<double> a) { return V3<R>{(R)a.x, (R)a.y, (R)a.z}; };
-    for (auto& o : w) out.push_back({o.type, cv(o.a), cv(o.b), castMat<R>(o.mat)});
+    for (auto& o : w) out.push_back({o.type, cv(o.a), cv(o.b), castMat<R>(o.mat), o.mesh});
     return out;
 }
 template <class R> Sky<R> castSky(const Sky<double>& s) {
@@ -569,6 +695,7 @@ orc_scene* orc_scene_create(const orc_raw_object* objs, int n_objs, const orc_ra
     orc_scene* sc = new orc_scene();
     std::map<std::string, Material<double>> materials;                                                 // objects.go:226-229 (later duplicate wins)
     for (int i = 0; i < n_mats; i++) materials[mats[i].id ? mats[i].id : ""] = convertMaterial(mats[i]);
+    int32_t n_tri_total = 0;
     for (int i = 0; i < n_objs; i++) {                                                                 // objects.go:232-267
         const orc_raw_object& o = objs[i];
         Material<double> mat;                                                                          // missing id -> zero material
@@ -580,6 +707,24 @@ orc_scene* orc_scene_create(const orc_raw_object* objs, int n_objs, const orc_ra
         if (t == "sphere" || t == "sphere_light") sc->world.push_back({objSphere, pos, {size.x, 0, 0}, mat});
         else if (t == "plane") sc->world.push_back({objPlane, pos, {0, 1, 0}, mat});
         else if (t == "box") sc->world.push_back({objBox, sub(pos, mul(size, 0.5)), add(pos, mul(size, 0.5)), mat});
+        else if (t == "mesh" && o.tri_vertices && o.n_tri > 0) {          // EXTENSION
+            auto m = std::make_unique<OMesh>();
+            V3<double> lo = {1e300, 1e300, 1e300}, hi = {-1e300, -1e300, -1e300};
+            for (int64_t q = 0; q < o.n_tri; q++) {
+                const float* v = o.tri_vertices + 9 * q;
+                OTri tr;
+                for (int k = 0; k < 3; k++) { tr.v0[k] = v[k]; tr.e1[k] = v[3 + k] - v[k]; tr.e2[k] = v[6 + k] - v[k]; }
+                tr.id = n_tri_total++;
+                m->tris.push_back(tr);
+                for (int c = 0; c < 3; c++) {
+                    lo.x = std::min(lo.x, (double)v[3 * c]); lo.y = std::min(lo.y, (double)v[3 * c + 1]); lo.z = std::min(lo.z, (double)v[3 * c + 2]);
+                    hi.x = std::max(hi.x, (double)v[3 * c]); hi.y = std::max(hi.y, (double)v[3 * c + 1]); hi.z = std::max(hi.z, (double)v[3 * c + 2]);
+                }
+            }
+            m->finish();
+            sc->world.push_back({objMesh, lo, hi, mat, m.get()});
+            sc->meshes.push_back(std::move(m));
+        }
         /* unknown object types are dropped */
     }
     sc->cam = *cam;
@@ -620,10 +765,7 @@ void orc_primary_hits(const orc_scene* sc, int W, int H, double xi_u, double xi_
             double vv = (flipY + xi_v) * invHeight;
             Ray<double> r = getRay<double>(cam, u, vv, nullptr);                                       // camera.go:70-73
             HitRecord<double> rec;
-            bool hitAnything = false;
-            double closest = std::numeric_limits<double>::max();
-            for (size_t i = 0; i < sc->world.size(); i++)                                              // renderer.go:297-302
-                if (hitObject(sc->world[i], r, 0.001, closest, rec)) { hitAnything = true; closest = rec.t; rec.index = (int)i; }
+            const bool hitAnything = closestHit<double>(sc->world, r, 0.001, rec, nullptr);            // renderer.go:292-302
             ids[(size_t)y * W + x] = hitAnything ? rec.index : -1;
             tOut[(size_t)y * W + x] = hitAnything ? rec.t : 0.0;
         }
@@ -668,6 +810,8 @@ int orc_trace_path(const orc_scene* sc, const double orig[3], const double dir[3
     rgb[0] = c.x; rgb[1] = c.y; rgb[2] = c.z;
     return log.n;
 }
+
+void orc_set_mesh_accel(orc_scene* sc, int enabled) { for (auto& m : sc->meshes) m->accel = enabled != 0; }
 
 double orc_rng_uniform(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t i) {
     Rng rng(seed, pixel, sample);

@@ -41,6 +41,12 @@ typedef struct {
     double position[3];      /* scene.go:85 */
     double size[3];          /* scene.go:86 */
     const char* material_id; /* scene.go:88 */
+    /* EXTENSION (type "mesh", not in the reference): world-space triangles of this object, binary32, 9 floats each.
+     * Hit rule (DESIGN.md "Meshes"): Moeller-Trumbore, two-sided, geometric normal; meshes are tested after all
+     * analytic objects and win only with t < closest; among triangles of equal t the lowest triangle id wins
+     * (ids count over all meshes in world order). */
+    const float* tri_vertices;
+    int64_t n_tri;
 } orc_raw_object;
 
 typedef struct {
@@ -59,7 +65,7 @@ typedef struct orc_scene orc_scene;
 
 /* Converted world entry (objects.go:225-269 + materials.go:28-55), for flatten parity. */
 typedef struct {
-    int32_t type;      /* 0 sphere, 1 plane, 2 box */
+    int32_t type;      /* 0 sphere, 1 plane, 2 box, 3 mesh (a/b = bounding box) */
     int32_t mat_type;  /* materials.go:11-17: 0 lambert 1 metal 2 dielectric 3 emissive 4 mirror */
     double a[3];       /* sphere centre | plane point | box min */
     double b[3];       /* sphere (radius,0,0) | plane normal | box max */
@@ -116,6 +122,9 @@ void orc_render_rgba(const orc_scene*, int width, int height, int spp, int max_d
 int orc_trace_path(const orc_scene*, const double orig[3], const double dir[3], int max_depth,
                    uint32_t seed, int cap, int32_t* hit_ids, double* hit_t, int32_t* front_face,
                    double rgb[3]);
+
+/* EXTENSION: 1 (default) = meshes with more than 64 triangles use the oracle's own median-split BVH, 0 = brute force. */
+void orc_set_mesh_accel(orc_scene*, int enabled);
 
 /* The shared RNG spec, exposed for tests: i-th uniform of path (seed,pixel,sample). */
 double orc_rng_uniform(uint32_t seed, uint32_t pixel, uint32_t sample, uint32_t i);

@@ -26,7 +26,7 @@ class RawMaterial(C.Structure):
 
 class RawObject(C.Structure):
     _fields_ = [("type", C.c_char_p), ("position", C.c_double * 3), ("size", C.c_double * 3),
-                ("material_id", C.c_char_p)]
+                ("material_id", C.c_char_p), ("tri_vertices", C.POINTER(C.c_float)), ("n_tri", C.c_int64)]
 
 
 class RawCamera(C.Structure):
@@ -90,6 +90,7 @@ def lib():
         L.orc_trace_path.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int,
                                      C.c_uint32, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.POINTER(C.c_double)]
+        L.orc_set_mesh_accel.argtypes = [C.c_void_p, C.c_int]
         L.orc_rng_uniform.restype = C.c_double
         L.orc_rng_uniform.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         _LIB = L
@@ -108,7 +109,10 @@ def _b(s):
 class OracleScene:
     """Scene handle built from a decoded scene JSON dict (schema: internal/scene/scene.go)."""
 
-    def __init__(self, sc: dict):
+    def __init__(self, sc: dict, mesh_triangles: dict | None = None):
+        """mesh_triangles: {object index: float32 array (n_tri, 9) of WORLD-space triangles} for objects of type "mesh"
+        (EXTENSION).  Tests take them from the product's flattener so that the mesh generator is not part of the
+        parity surface; inline "mesh": {"vertices", "triangles"} objects are expanded here."""
         L = lib()
         mats = sc.get("materials") or []
         objs = sc.get("objects") or []
@@ -122,7 +126,20 @@ class OracleScene:
         RO = (RawObject * max(1, len(objs)))()
         for i, o in enumerate(objs):
             RO[i] = RawObject(_b(o.get("type")), _v3(o.get("position"), "xyz"), _v3(o.get("size"), "xyz"),
-                              _b(o.get("material_id")))
+                              _b(o.get("material_id")), None, 0)
+            if o.get("type") == "mesh":
+                tri = (mesh_triangles or {}).get(i)
+                if tri is None and isinstance(o.get("mesh"), dict) and "vertices" in o["mesh"]:
+                    v = np.asarray(o["mesh"]["vertices"], dtype=np.float32).reshape(-1, 3).astype(np.float64)
+                    idx = np.asarray(o["mesh"]["triangles"], dtype=np.int64).reshape(-1, 3)
+                    pos = np.array([float((o.get("position") or {}).get(k, 0)) for k in "xyz"])
+                    size = np.array([float((o.get("size") or {}).get(k, 0)) or 1.0 for k in "xyz"])
+                    tri = (pos + size * v)[idx].reshape(-1, 9).astype(np.float32)
+                if tri is not None and len(tri):
+                    tri = np.ascontiguousarray(tri, dtype=np.float32).reshape(-1, 9)
+                    self._keep.append(tri)
+                    RO[i].tri_vertices = tri.ctypes.data_as(C.POINTER(C.c_float))
+                    RO[i].n_tri = len(tri)
         cam = sc.get("camera") or {}
         rc = RawCamera(_v3(cam.get("position"), "xyz"), _v3(cam.get("target"), "xyz"), _v3(cam.get("up"), "xyz"),
                        float(cam.get("fov", 0) or 0), float(cam.get("aperture", 0) or 0),
@@ -145,6 +162,9 @@ class OracleScene:
                 self._h = None
         except Exception:
             pass
+
+    def set_mesh_accel(self, enabled: bool):
+        lib().orc_set_mesh_accel(self._h, 1 if enabled else 0)
 
     def world(self):
         L = lib()

@@ -15,7 +15,7 @@ _PKG = pathlib.Path(__file__).resolve().parent
 SO_PATH = pathlib.Path(os.environ["PTB200_LIB"]) if os.environ.get("PTB200_LIB") else _PKG / "libptb200.so"
 
 PTB_OK, PTB_ERR_INVALID, PTB_ERR_CUDA, PTB_ERR_NO_SCENE, PTB_ERR_LIMIT = 0, -1, -2, -3, -4
-PTB_OBJ_SPHERE, PTB_OBJ_PLANE, PTB_OBJ_BOX = 0, 1, 2
+PTB_OBJ_SPHERE, PTB_OBJ_PLANE, PTB_OBJ_BOX, PTB_OBJ_MESH = 0, 1, 2, 3
 PTB_MAT_LAMBERT, PTB_MAT_METAL, PTB_MAT_DIELECTRIC, PTB_MAT_EMISSIVE, PTB_MAT_MIRROR = 0, 1, 2, 3, 4
 PTB_SKY_CONST, PTB_SKY_GRADIENT = 0, 1
 PTB_FLAG_STATS = 1
@@ -40,7 +40,9 @@ class PtbScene(C.Structure):
     _fields_ = [("n_obj", C.c_int32), ("obj_type", _ip), ("obj_mat", _ip), ("obj_pos", _dp), ("obj_size", _dp),
                 ("n_mat", C.c_int32), ("mat_type", _ip), ("mat_albedo", _dp), ("mat_rough", _dp), ("mat_ior", _dp),
                 ("mat_emit", _dp), ("mat_power", _dp), ("mat_absorption", _dp), ("mat_smoothness", _dp),
-                ("camera", PtbCamera), ("sky", PtbSky)]
+                ("camera", PtbCamera), ("sky", PtbSky),
+                ("n_mesh", C.c_int32), ("obj_mesh", _ip), ("mesh_tri_begin", C.POINTER(C.c_int64)),
+                ("tri_vertices", C.POINTER(C.c_float))]
 
 
 class PtbCfg(C.Structure):
@@ -54,12 +56,21 @@ class PtbStats(C.Structure):
                 ("accepts", C.c_uint64 * 3), ("scatters", C.c_uint64), ("end_sky", C.c_uint64),
                 ("end_emissive", C.c_uint64), ("end_rr", C.c_uint64), ("end_depth", C.c_uint64),
                 ("end_noscatter", C.c_uint64), ("lane_iters_active", C.c_uint64),
-                ("lane_iters_total", C.c_uint64), ("last_render_ms", C.c_double)]
+                ("lane_iters_total", C.c_uint64), ("last_render_ms", C.c_double),
+                ("accepts_mesh", C.c_uint64), ("bvh_nodes_visited", C.c_uint64), ("bvh_tris_tested", C.c_uint64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "accepts"}
         d["accepts"] = list(self.accepts)
         return d
+
+
+class PtbBvhInfo(C.Structure):
+    _fields_ = [("n_triangles", C.c_int64), ("n_nodes", C.c_int64), ("max_depth", C.c_int32), ("node_bytes", C.c_int32),
+                ("triangle_bytes", C.c_int32), ("reserved", C.c_int32), ("sah_cost", C.c_double), ("build_ms", C.c_double)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
 
 
 class PtbDeviceInfo(C.Structure):
@@ -86,6 +97,7 @@ SYMBOLS = {
     "ptb_render_device": (C.c_int, [C.c_void_p, C.POINTER(PtbCfg), C.c_void_p, C.c_void_p]),
     "ptb_primary_hits": (C.c_int, [C.c_void_p, C.POINTER(PtbCfg), C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "ptb_get_stats": (C.c_int, [C.c_void_p, C.POINTER(PtbStats)]),
+    "ptb_get_bvh_info": (C.c_int, [C.c_void_p, C.POINTER(PtbBvhInfo)]),
     "ptb_measure_fp32_peak": (C.c_int, [C.c_void_p, _dp]),
     # host mirror
     "ptb_host_last_error": (C.c_char_p, []),

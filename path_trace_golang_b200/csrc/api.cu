@@ -14,6 +14,9 @@
 #include <string>
 #include <vector>
 
+#include <thread>
+
+#include "bvh.h"
 #include "scene_dev.h"
 
 using namespace ptb;
@@ -46,6 +49,10 @@ struct ptb_ctx {
     uint4* d_blob = nullptr;            // obj[] then mat[] (global copy for the smem fill)
     size_t blob_words = 0;
     Obj64* d_world64 = nullptr;
+    int n_world64 = 0;
+    BvhNode* d_bvh_nodes = nullptr;      // EXTENSION: mesh BVH
+    BvhTri* d_bvh_tris = nullptr;
+    ptb_bvh_info bvh{};
 
     // scratch device buffers, grown on demand
     float* d_accum = nullptr; size_t accum_cap = 0;
@@ -209,7 +216,9 @@ int render_launch(ptb_ctx* c, const ptb_cfg* cfg, int s0, int s1, float* d_accum
     fp.seed_key = fmix_host(cfg->seed ^ 0x9E3779B9u);
     fp.inv_w = 1.0f / (float)(W - 1); fp.inv_h = 1.0f / (float)(H - 1); fp.h_minus_1 = (float)(H - 1);
     fp.scene_blob = c->d_blob; fp.accum = d_accum; fp.accum_resume = resume ? 1 : 0; fp.rgba = d_rgba; fp.stats = (stats || dbg_timing) ? c->d_stats : nullptr;
+    fp.bvh_nodes = (const float4*)c->d_bvh_nodes; fp.bvh_tris = (const float4*)c->d_bvh_tris;
     const bool mega = (cfg->flags & PTB_FLAG_MEGAKERNEL) != 0 || cfg->max_depth <= 0;
+    if (mega && cfg->max_depth > 0 && c->d_bvh_nodes) return fail(c, PTB_ERR_INVALID, "the megakernel integrator does not support meshes");
     if (mega) {
         e = launch_integrator(fp, stats, c->h_scene->n_obj, c->h_scene->n_mat, stream);
     } else {
@@ -243,6 +252,7 @@ int fetch_stats(ptb_ctx* c, bool stats, float ms) {
     s.scatters = w[ST_SCATTERS]; s.end_sky = w[ST_END_SKY]; s.end_emissive = w[ST_END_EMISSIVE];
     s.end_rr = w[ST_END_RR]; s.end_depth = w[ST_END_DEPTH]; s.end_noscatter = w[ST_END_NOSCATTER];
     s.lane_iters_active = w[ST_LANE_ACTIVE]; s.lane_iters_total = w[ST_LANE_TOTAL];
+    s.accepts_mesh = w[ST_ACC_MESH]; s.bvh_nodes_visited = w[ST_BVH_NODES]; s.bvh_tris_tested = w[ST_BVH_TRIS];
     return PTB_OK;
 }
 
@@ -288,7 +298,7 @@ void ptb_destroy(ptb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_blob); cudaFree(c->d_world64); cudaFree(c->d_accum); cudaFree(c->d_rgba); cudaFree(c->d_stats); cudaFree(c->d_work);
+    cudaFree(c->d_blob); cudaFree(c->d_world64); cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_tris); cudaFree(c->d_accum); cudaFree(c->d_rgba); cudaFree(c->d_stats); cudaFree(c->d_work);
     if (c->h_scene) cudaFreeHost(c->h_scene);
     if (c->h_rgba) cudaFreeHost(c->h_rgba);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -330,11 +340,17 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
         std::memset(&z, 0, sizeof z);
         z.mat_type = PTB_MAT_LAMBERT;
     }
-    // objects (sceneToWorld)
+    // objects (sceneToWorld); EXTENSION: mesh objects are world entries too (type PTB_OBJ_MESH, a/b = bounding box)
+    if (s->n_mesh < 0 || (s->n_mesh > 0 && (!s->obj_mesh || !s->mesh_tri_begin || !s->tri_vertices)))
+        return fail(c, PTB_ERR_INVALID, "mesh arrays are NULL");
     std::vector<World64Entry> world;
+    std::vector<float> tri_v;                  // triangles of the mesh objects, concatenated in world order
+    std::vector<int32_t> tri_world;            // per triangle: world index of its mesh object
+    std::vector<char> mesh_used(s->n_mesh > 0 ? s->n_mesh : 0, 0);
+    int n_analytic = 0;
     for (int i = 0; i < s->n_obj; i++) {
         const int t = s->obj_type[i];
-        if (t != PTB_OBJ_SPHERE && t != PTB_OBJ_PLANE && t != PTB_OBJ_BOX) continue;   // dropped (objects.go:237-266)
+        if (t != PTB_OBJ_SPHERE && t != PTB_OBJ_PLANE && t != PTB_OBJ_BOX && t != PTB_OBJ_MESH) continue;   // dropped (objects.go:237-266)
         int mi = s->obj_mat[i];
         if (mi >= s->n_mat) return fail(c, PTB_ERR_INVALID, "obj_mat[%d]=%d out of range", i, mi);
         if (mi < 0) mi = s->n_mat;
@@ -345,27 +361,64 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
         const double* size = s->obj_size + 3 * i;
         if (t == PTB_OBJ_SPHERE) { for (int k = 0; k < 3; k++) { w.a[k] = pos[k]; w.b[k] = 0; } w.b[0] = size[0]; }
         else if (t == PTB_OBJ_PLANE) { for (int k = 0; k < 3; k++) w.a[k] = pos[k]; w.b[0] = 0; w.b[1] = 1; w.b[2] = 0; }
-        else { for (int k = 0; k < 3; k++) { w.a[k] = pos[k] - size[k] * 0.5; w.b[k] = pos[k] + size[k] * 0.5; } }
+        else if (t == PTB_OBJ_BOX) { for (int k = 0; k < 3; k++) { w.a[k] = pos[k] - size[k] * 0.5; w.b[k] = pos[k] + size[k] * 0.5; } }
+        else {
+            const int m = s->n_mesh > 0 ? s->obj_mesh[i] : -1;
+            if (m < 0 || m >= s->n_mesh) return fail(c, PTB_ERR_INVALID, "obj_mesh[%d]=%d out of range", i, m);
+            if (mesh_used[m]) return fail(c, PTB_ERR_INVALID, "mesh %d is referenced by more than one object", m);
+            mesh_used[m] = 1;
+            const int64_t t0 = s->mesh_tri_begin[m], t1 = s->mesh_tri_begin[m + 1];
+            if (t0 < 0 || t1 < t0) return fail(c, PTB_ERR_INVALID, "mesh_tri_begin is not monotone");
+            if (t1 == t0) continue;            // empty mesh: dropped
+            if ((int64_t)(tri_v.size() / 9) + (t1 - t0) > (1ll << 28)) return fail(c, PTB_ERR_LIMIT, "more than 2^28 triangles");
+            for (int k = 0; k < 3; k++) { w.a[k] = INFINITY; w.b[k] = -INFINITY; }
+            for (int64_t q = t0 * 9; q < t1 * 9; q++) {
+                const float v = s->tri_vertices[q];
+                if (!(v == v) || std::fabs(v) > 1e18f) return fail(c, PTB_ERR_INVALID, "non-finite mesh vertex");
+                const int k = (int)(q % 3);
+                w.a[k] = std::fmin(w.a[k], (double)v); w.b[k] = std::fmax(w.b[k], (double)v);
+            }
+            tri_v.insert(tri_v.end(), s->tri_vertices + t0 * 9, s->tri_vertices + t1 * 9);
+            tri_world.insert(tri_world.end(), (size_t)(t1 - t0), (int32_t)world.size());
+        }
+        if (t != PTB_OBJ_MESH) n_analytic++;
         world.push_back(w);
     }
-    if ((int)world.size() > PTB_MAX_OBJECTS) return fail(c, PTB_ERR_LIMIT, "%zu objects > PTB_MAX_OBJECTS=%d", world.size(), PTB_MAX_OBJECTS);
+    if (n_analytic > PTB_MAX_OBJECTS) return fail(c, PTB_ERR_LIMIT, "%d analytic objects > PTB_MAX_OBJECTS=%d", n_analytic, PTB_MAX_OBJECTS);
+    auto meta_of = [](const World64Entry& w) {
+        // shading class of the wavefront kernel (enum in wavefront.cuh): 0 dielectric, 1 diffuse (lambert, rough metal),
+        // 2 terminate (emissive), 4 specular (mirror, smooth metal)
+        int cls = 1;
+        if (w.mat_type == PTB_MAT_METAL) cls = ((float)w.rough > 1e-6f) ? 1 : 4;
+        else if (w.mat_type == PTB_MAT_MIRROR) cls = 4;
+        else if (w.mat_type == PTB_MAT_DIELECTRIC) cls = 0;
+        else if (w.mat_type == PTB_MAT_EMISSIVE) cls = 2;
+        return w.type | ((w.mat_type == PTB_MAT_DIELECTRIC) << 2) | (cls << 3) | (w.mat_slot << 6);
+    };
 
     // binary32 device tables
     DevScene& hs = *c->h_scene;
-    hs.n_obj = (int)world.size(); hs.n_mat = s->n_mat + 1; hs.n_diel = 0;
+    hs.n_obj = n_analytic; hs.n_mat = s->n_mat + 1; hs.n_diel = 0;
     for (int i = 0; i < hs.n_mat; i++) {
         DevMat& m = hs.mat[i];
         const World64Entry& w = mats[i];
         m.type = w.mat_type; m.rough = (float)w.rough; m.ior = (float)w.ior;
         for (int k = 0; k < 3; k++) { m.albedo[k] = (float)w.albedo[k]; m.emit[k] = (float)w.emit[k]; m.absorption[k] = (float)w.absorption[k]; }
     }
-    std::vector<Obj64> w64(world.size());
-    // device order: boxes first (world order), then spheres/planes (world order); see integrator.cu for why the
-    // reference's tie rule survives this grouping
-    std::vector<int> order, dev_of(world.size());
+    // device order of the analytic objects: boxes first (world order), then spheres/planes (world order); see
+    // integrator.cu for why the reference's tie rule survives this grouping
+    std::vector<int> order, dev_of(world.size(), -1);
     for (int i = 0; i < (int)world.size(); i++) if (world[i].type == PTB_OBJ_BOX) order.push_back(i);
     hs.n_box = (int)order.size();
-    for (int i = 0; i < (int)world.size(); i++) if (world[i].type != PTB_OBJ_BOX) order.push_back(i);
+    for (int i = 0; i < (int)world.size(); i++) if (world[i].type == PTB_OBJ_SPHERE || world[i].type == PTB_OBJ_PLANE) order.push_back(i);
+    std::vector<Obj64> w64;
+    for (int i = 0; i < (int)world.size(); i++) {
+        if (world[i].type == PTB_OBJ_MESH) continue;
+        Obj64 o64;
+        o64.type = world[i].type; o64.pad = i;
+        for (int j = 0; j < 3; j++) { o64.a[j] = world[i].a[j]; o64.b[j] = world[i].b[j]; }
+        w64.push_back(o64);
+    }
     for (int k = 0; k < hs.n_obj; k++) {
         const int i = order[k];
         dev_of[i] = k;
@@ -376,20 +429,32 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
             float r = (float)w.b[0];
             o.bx = r; o.by = r * r; o.bz = 1.0f / r;    // radiusSq (objects.go:46), invRadius (objects.go:68)
         } else { o.bx = (float)w.b[0]; o.by = (float)w.b[1]; o.bz = (float)w.b[2]; }
-        // shading class of the wavefront kernel (enum in wavefront.cuh): 0 dielectric, 1 diffuse (lambert, rough metal),
-        // 2 terminate (emissive), 4 specular (mirror, smooth metal)
-        int cls = 1;
-        if (w.mat_type == PTB_MAT_METAL) cls = ((float)w.rough > 1e-6f) ? 1 : 4;
-        else if (w.mat_type == PTB_MAT_MIRROR) cls = 4;
-        else if (w.mat_type == PTB_MAT_DIELECTRIC) cls = 0;
-        else if (w.mat_type == PTB_MAT_EMISSIVE) cls = 2;
-        o.meta = w.type | ((w.mat_type == PTB_MAT_DIELECTRIC) << 2) | (cls << 3) | (w.mat_slot << 6);
+        o.meta = meta_of(w);
         o.world_idx = i;
-        w64[i].type = w.type; w64[i].pad = 0;
-        for (int j = 0; j < 3; j++) { w64[i].a[j] = w.a[j]; w64[i].b[j] = w.b[j]; }
     }
-    for (int i = 0; i < (int)world.size(); i++)
-        if (world[i].mat_type == PTB_MAT_DIELECTRIC) hs.diel_idx[hs.n_diel++] = dev_of[i];
+    for (int i = 0; i < (int)world.size(); i++)      // exit-search candidates: analytic dielectric objects (meshes are not searched)
+        if (world[i].type != PTB_OBJ_MESH && world[i].mat_type == PTB_MAT_DIELECTRIC) hs.diel_idx[hs.n_diel++] = dev_of[i];
+
+    // EXTENSION: BVH over the mesh triangles
+    cudaFree(c->d_bvh_nodes); c->d_bvh_nodes = nullptr;
+    cudaFree(c->d_bvh_tris); c->d_bvh_tris = nullptr;
+    c->bvh = ptb_bvh_info{};
+    if (!tri_world.empty()) {
+        std::vector<int32_t> tri_meta(tri_world.size());
+        for (size_t q = 0; q < tri_world.size(); q++) tri_meta[q] = meta_of(world[tri_world[q]]);
+        BvhBuildInput in{tri_v.data(), (int64_t)tri_world.size(), tri_meta.data(), tri_world.data()};
+        BvhBuildOutput out;
+        unsigned hw = std::thread::hardware_concurrency();
+        build_bvh(in, out, hw ? (int)hw : 4);
+        CK(c, cudaMalloc((void**)&c->d_bvh_nodes, out.nodes.size() * sizeof(BvhNode)));
+        CK(c, cudaMalloc((void**)&c->d_bvh_tris, out.tris.size() * sizeof(BvhTri)));
+        CK(c, cudaMemcpy(c->d_bvh_nodes, out.nodes.data(), out.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+        CK(c, cudaMemcpy(c->d_bvh_tris, out.tris.data(), out.tris.size() * sizeof(BvhTri), cudaMemcpyHostToDevice));
+        c->bvh.n_triangles = (int64_t)out.tris.size(); c->bvh.n_nodes = (int64_t)out.nodes.size();
+        c->bvh.max_depth = out.max_depth; c->bvh.sah_cost = out.sah_cost; c->bvh.build_ms = out.build_ms;
+        c->bvh.node_bytes = sizeof(BvhNode); c->bvh.triangle_bytes = sizeof(BvhTri);
+        if (out.max_depth > 38) return fail(c, PTB_ERR_LIMIT, "BVH depth %d exceeds the traversal stack", out.max_depth);
+    }
     hs.sky.kind = s->sky.kind == PTB_SKY_GRADIENT ? PTB_SKY_GRADIENT : PTB_SKY_CONST;
     for (int k = 0; k < 3; k++) { hs.sky.color[k] = (float)s->sky.color[k]; hs.sky.horizon[k] = (float)s->sky.horizon[k]; hs.sky.zenith[k] = (float)s->sky.zenith[k]; }
 
@@ -403,6 +468,7 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
     c->blob_words = words;
     CK(c, cudaMalloc((void**)&c->d_world64, sizeof(Obj64) * (w64.size() + 1)));
     if (!w64.empty()) CK(c, cudaMemcpy(c->d_world64, w64.data(), sizeof(Obj64) * w64.size(), cudaMemcpyHostToDevice));
+    c->n_world64 = (int)w64.size();
 
     c->world = world;
     c->cam = s->camera;
@@ -553,13 +619,22 @@ int ptb_primary_hits(ptb_ctx* c, const ptb_cfg* cfg, double xi_u, double xi_v, i
     Cam64 cam = new_camera(c->cam, W, H);
     Camera64 dc;
     for (int k = 0; k < 3; k++) { dc.origin[k] = cam.origin[k]; dc.llc[k] = cam.llc[k]; dc.horizontal[k] = cam.horizontal[k]; dc.vertical[k] = cam.vertical[k]; }
-    int e = launch_primary_hits(c->d_world64, (int)c->world.size(), dc, W, H, xi_u, xi_v, d_ids, d_t, c->stream);
+    int e = launch_primary_hits(c->d_world64, c->n_world64, (const float4*)c->d_bvh_nodes, (const float4*)c->d_bvh_tris, dc, W, H, xi_u, xi_v,
+                                d_ids, d_t, c->stream);
     cudaError_t ce = (cudaError_t)e;
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(ids, d_ids, n * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(t, d_t, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
     cudaFree(d_ids); cudaFree(d_t);
     if (ce != cudaSuccess) return fail(c, PTB_ERR_CUDA, "primary hits: %s", cudaGetErrorString(ce));
+    return PTB_OK;
+}
+
+int ptb_get_bvh_info(ptb_ctx* c, ptb_bvh_info* out) {
+    if (!c || !out) return PTB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!c->has_scene) return fail(c, PTB_ERR_NO_SCENE, "no scene uploaded");
+    *out = c->bvh;
     return PTB_OK;
 }
 

@@ -198,6 +198,32 @@ std::unique_ptr<Scene> decode(const JValue& root) {
             if (e.kind == JValue::Object) {
                 get(e, "id", o.ID); get(e, "type", o.Type); get(e, "position", o.Position); get(e, "size", o.Size);
                 get(e, "material_id", o.MaterialID);
+                Fields{e}.each("mesh", [&](const JValue& mv) {          // EXTENSION
+                    if (mv.kind != JValue::Object) return;
+                    auto mesh = std::make_shared<MeshData>();
+                    Fields{mv}.each("vertices", [&](const JValue& a) {
+                        if (a.kind != JValue::Array) type_err("mesh.vertices", "[]float32");
+                        mesh->vertices.clear();
+                        for (auto& x : a.arr) { if (x.kind != JValue::Number) type_err("mesh.vertices", "[]float32"); mesh->vertices.push_back((float)x.num); }
+                    });
+                    Fields{mv}.each("triangles", [&](const JValue& a) {
+                        if (a.kind != JValue::Array) type_err("mesh.triangles", "[]uint32");
+                        mesh->triangles.clear();
+                        for (auto& x : a.arr) { if (x.kind != JValue::Number || x.num < 0) type_err("mesh.triangles", "[]uint32"); mesh->triangles.push_back((uint32_t)x.num); }
+                    });
+                    Fields{mv}.each("heightfield", [&](const JValue& h) {
+                        if (h.kind != JValue::Object) return;
+                        int seed = 0;
+                        get(h, "nx", mesh->nx); get(h, "nz", mesh->nz); get(h, "seed", seed); get(h, "octaves", mesh->octaves);
+                        get(h, "amplitude", mesh->amplitude); get(h, "frequency", mesh->frequency);
+                        mesh->seed = (uint32_t)seed;
+                        mesh->generated = true;
+                        GenerateHeightfield(*mesh);
+                    });
+                    if (mesh->vertices.size() % 3 || mesh->triangles.size() % 3) type_err("mesh", "triples");
+                    for (uint32_t idx : mesh->triangles) if ((size_t)idx >= mesh->vertices.size() / 3) type_err("mesh.triangles", "vertex index in range");
+                    o.Mesh = mesh;
+                });
             } else if (e.kind != JValue::Null) type_err("objects", "scene.Object");
             sc->Objects.push_back(std::move(o));
         }
@@ -339,6 +365,23 @@ std::string Marshal(const Scene& sc) {
         e.elem(); e.open('{');
         e.str("id", o.ID); e.str("type", o.Type); e.vec3("position", o.Position); e.vec3("size", o.Size);
         e.str("material_id", o.MaterialID);
+        if (o.Mesh) {                                                   // EXTENSION (omitted when absent)
+            e.key("mesh"); e.open('{');
+            if (o.Mesh->generated) {
+                e.key("heightfield"); e.open('{');
+                e.integer("nx", o.Mesh->nx); e.integer("nz", o.Mesh->nz); e.integer("seed", (int)o.Mesh->seed);
+                e.integer("octaves", o.Mesh->octaves); e.num("amplitude", o.Mesh->amplitude); e.num("frequency", o.Mesh->frequency);
+                e.close('}');
+            } else {
+                e.key("vertices"); e.out += "[";
+                for (size_t i = 0; i < o.Mesh->vertices.size(); i++) { if (i) e.out += ","; e.out += fmt_float((double)o.Mesh->vertices[i]); }
+                e.out += "]";
+                e.key("triangles"); e.out += "[";
+                for (size_t i = 0; i < o.Mesh->triangles.size(); i++) { if (i) e.out += ","; e.out += std::to_string(o.Mesh->triangles[i]); }
+                e.out += "]";
+            }
+            e.close('}');
+        }
         e.close('}');
     }
     e.close(']');
@@ -397,6 +440,7 @@ static int32_t object_code(const std::string& t) {             // objects.go:237
     if (t == ObjectSphere || t == ObjectSphereLight) return PTB_OBJ_SPHERE;
     if (t == ObjectPlane) return PTB_OBJ_PLANE;
     if (t == ObjectBox) return PTB_OBJ_BOX;
+    if (t == ObjectMesh) return PTB_OBJ_MESH;                  // EXTENSION
     return -1;                                                 // dropped
 }
 
@@ -415,8 +459,24 @@ Flat Flatten(const Scene& sc) {
         f.mat_absorption.insert(f.mat_absorption.end(), {m.Absorption.R, m.Absorption.G, m.Absorption.B});
         f.mat_smoothness.push_back(m.Smoothness);
     }
+    f.mesh_tri_begin.push_back(0);
     for (const Object& o : sc.Objects) {
-        f.obj_type.push_back(object_code(o.Type));
+        int32_t code = object_code(o.Type);
+        if (code == PTB_OBJ_MESH && (!o.Mesh || o.Mesh->triangles.empty())) code = -1;   // a mesh object without triangles is dropped
+        if (code == PTB_OBJ_MESH) {
+            f.obj_mesh.push_back((int32_t)f.mesh_tri_begin.size() - 1);
+            const double sx = o.Size.X != 0 ? o.Size.X : 1.0, sy = o.Size.Y != 0 ? o.Size.Y : 1.0, sz = o.Size.Z != 0 ? o.Size.Z : 1.0;
+            const MeshData& m = *o.Mesh;
+            for (uint32_t idx : m.triangles) {
+                f.tri_vertices.push_back((float)(o.Position.X + sx * (double)m.vertices[3 * idx]));
+                f.tri_vertices.push_back((float)(o.Position.Y + sy * (double)m.vertices[3 * idx + 1]));
+                f.tri_vertices.push_back((float)(o.Position.Z + sz * (double)m.vertices[3 * idx + 2]));
+            }
+            f.mesh_tri_begin.push_back((int64_t)f.tri_vertices.size() / 9);
+        } else {
+            f.obj_mesh.push_back(-1);
+        }
+        f.obj_type.push_back(code);
         auto it = by_id.find(o.MaterialID);
         f.obj_mat.push_back(it == by_id.end() ? -1 : it->second);
         f.obj_pos.insert(f.obj_pos.end(), {o.Position.X, o.Position.Y, o.Position.Z});
@@ -440,6 +500,45 @@ Flat Flatten(const Scene& sc) {
     return f;
 }
 
+// ---- EXTENSION: heightfield generator.  y(x,z) = amplitude * sum_o 0.5^o * vnoise(x*f*2^o, z*f*2^o) with vnoise =
+// smoothstep-interpolated lattice values in [-1,1] from an integer hash of (ix, iz, seed, octave).  binary64 throughout.
+static double lattice(int ix, int iz, uint32_t seed, int oct) {
+    uint32_t h = (uint32_t)ix * 0x9E3779B1u ^ (uint32_t)iz * 0x85EBCA77u ^ (seed + (uint32_t)oct * 0xC2B2AE3Du);
+    h ^= h >> 16; h *= 0x21f0aaadu; h ^= h >> 15; h *= 0x735a2d97u; h ^= h >> 15;
+    return (double)h * (2.0 / 4294967296.0) - 1.0;
+}
+static double vnoise(double x, double z, uint32_t seed, int oct) {
+    const double fx = std::floor(x), fz = std::floor(z);
+    const int ix = (int)fx, iz = (int)fz;
+    double tx = x - fx, tz = z - fz;
+    tx = tx * tx * (3.0 - 2.0 * tx); tz = tz * tz * (3.0 - 2.0 * tz);
+    const double a = lattice(ix, iz, seed, oct), b = lattice(ix + 1, iz, seed, oct);
+    const double c = lattice(ix, iz + 1, seed, oct), d = lattice(ix + 1, iz + 1, seed, oct);
+    return (a + (b - a) * tx) + ((c + (d - c) * tx) - (a + (b - a) * tx)) * tz;
+}
+void GenerateHeightfield(MeshData& m) {
+    if (m.nx < 1 || m.nz < 1 || (long long)m.nx * m.nz > 50000000LL) throw std::runtime_error("decode scene: heightfield nx/nz out of range");
+    const int oct = m.octaves > 0 ? m.octaves : 4;
+    const double freq = m.frequency != 0 ? m.frequency : 4.0;
+    m.vertices.resize((size_t)(m.nx + 1) * (m.nz + 1) * 3);
+    for (int j = 0; j <= m.nz; j++)
+        for (int i = 0; i <= m.nx; i++) {
+            const double x = (double)i / m.nx - 0.5, z = (double)j / m.nz - 0.5;
+            double y = 0, w = 1, f = freq;
+            for (int o = 0; o < oct; o++) { y += w * vnoise((x + 0.5) * f, (z + 0.5) * f, m.seed, o); w *= 0.5; f *= 2; }
+            float* v = &m.vertices[((size_t)j * (m.nx + 1) + i) * 3];
+            v[0] = (float)x; v[1] = (float)(m.amplitude * y); v[2] = (float)z;
+        }
+    m.triangles.resize((size_t)m.nx * m.nz * 6);
+    size_t k = 0;
+    for (int j = 0; j < m.nz; j++)
+        for (int i = 0; i < m.nx; i++) {
+            const uint32_t a = (uint32_t)(j * (m.nx + 1) + i), b = a + 1, c = a + (uint32_t)(m.nx + 1), d = c + 1;
+            m.triangles[k++] = a; m.triangles[k++] = c; m.triangles[k++] = b;      // counter-clockwise seen from +y
+            m.triangles[k++] = b; m.triangles[k++] = c; m.triangles[k++] = d;
+        }
+}
+
 ptb_scene Flat::view() const {
     ptb_scene s{};
     s.n_obj = (int32_t)obj_type.size();
@@ -449,6 +548,8 @@ ptb_scene Flat::view() const {
     s.mat_emit = mat_emit.data(); s.mat_power = mat_power.data(); s.mat_absorption = mat_absorption.data();
     s.mat_smoothness = mat_smoothness.data();
     s.camera = camera; s.sky = sky;
+    s.n_mesh = (int32_t)mesh_tri_begin.size() - 1;
+    s.obj_mesh = obj_mesh.data(); s.mesh_tri_begin = mesh_tri_begin.data(); s.tri_vertices = tri_vertices.data();
     return s;
 }
 

@@ -45,11 +45,30 @@ constexpr const char* ObjectSphere = "sphere";
 constexpr const char* ObjectPlane = "plane";
 constexpr const char* ObjectBox = "box";
 constexpr const char* ObjectSphereLight = "sphere_light";
+constexpr const char* ObjectMesh = "mesh";   // EXTENSION (not in the reference): triangle mesh, see MeshData
+
+// EXTENSION: triangle mesh attached to an Object of type "mesh" (north-star: "internal/scene gains a BVH builder").
+// JSON:  "mesh": {"vertices": [x0,y0,z0, x1,...], "triangles": [a0,b0,c0, ...]}            inline, or
+//        "mesh": {"heightfield": {"nx":..,"nz":..,"seed":..,"amplitude":..,"frequency":..,"octaves":..}}   generator:
+//        nx x nz quads (2 triangles each) over [-0.5,0.5]^2 in x,z with y = amplitude * fractal value noise.
+// World vertex = position + size * local vertex (a zero size component means 1).  The reference's Go decoder
+// ignores the unknown "mesh" key and sceneToWorld drops the unknown object type (objects.go:237-266), so scene
+// files with meshes still load there (without the mesh).
+struct MeshData {
+    std::vector<float> vertices;       // 3 per vertex, local space
+    std::vector<uint32_t> triangles;   // 3 vertex indices per triangle
+    bool generated = false;            // true: came from the heightfield generator (Save writes the parameters back)
+    int nx = 0, nz = 0, octaves = 0;
+    uint32_t seed = 0;
+    double amplitude = 0, frequency = 0;
+};
+void GenerateHeightfield(MeshData& m);
 
 struct Object {                                              // scene.go:81-89
     std::string ID, Type;
     Vec3 Position, Size;
     std::string MaterialID;
+    std::shared_ptr<MeshData> Mesh;                          // EXTENSION, only for Type == "mesh"
 };
 
 struct RenderSettings { int Width = 0, Height = 0, SamplesPerPx = 0, MaxDepth = 0; };   // scene.go:92-97
@@ -91,6 +110,10 @@ struct Flat {
     std::vector<double> obj_pos, obj_size, mat_albedo, mat_rough, mat_ior, mat_emit, mat_power, mat_absorption, mat_smoothness;
     ptb_camera camera{};
     ptb_sky sky{};
+    // EXTENSION: meshes of the "mesh" objects, world space, binary32
+    std::vector<int32_t> obj_mesh;          // [n_obj] mesh index or -1
+    std::vector<int64_t> mesh_tri_begin;    // [n_mesh+1] prefix of triangle counts
+    std::vector<float> tri_vertices;        // 9 floats per triangle (v0, v1, v2), world space
     ptb_scene view() const;
 };
 Flat Flatten(const Scene& sc);

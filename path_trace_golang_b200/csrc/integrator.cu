@@ -499,6 +499,7 @@ integrate_kernel(const __grid_constant__ FrameParams fp) {
 }
 
 }  // namespace ptb
+#include "bvh.cuh"
 #include "wavefront.cuh"
 namespace ptb {
 

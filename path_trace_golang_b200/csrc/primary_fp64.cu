@@ -58,7 +58,65 @@ __device__ __forceinline__ bool hit64(const Obj64& ob, const double o[3], const 
     }
 }
 
-__global__ void primary_hits_kernel(const Obj64* __restrict__ world, int n_obj, Camera64 cam, int W, int H,
+// EXTENSION (triangle meshes): binary64 traversal of the BVH of bvh.h.  Boxes are binary32 padded boxes widened to
+// binary64 (conservative), triangles are the binary32 (v0, e1, e2) records widened to binary64; Moeller-Trumbore
+// without FMA.  Result = the triangle of smallest t (lowest triangle id on ties), independent of the traversal order,
+// so it equals the oracle's brute-force scan bit for bit.
+__device__ __forceinline__ bool slab64(const float lo[3], const float hi[3], const double o[3], const double d[3], double tMin, double tMax) {
+    double t0 = tMin, t1 = tMax;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        double invD = 1 / d[i];
+        double tNear = ((double)lo[i] - o[i]) * invD;
+        double tFar = ((double)hi[i] - o[i]) * invD;
+        if (invD < 0) { double s = tNear; tNear = tFar; tFar = s; }
+        if (tNear > t0) t0 = tNear;
+        if (tFar < t1) t1 = tFar;
+    }
+    return t1 >= t0;
+}
+__device__ void bvh_closest64(const float4* __restrict__ nodes, const float4* __restrict__ tris, const double o[3], const double d[3],
+                              double tMin, double& closest, int& id) {
+    int stack[48];
+    int sp = 0, cur = 0, best_tri = -1;
+    for (;;) {
+        if (cur >= 0) {
+            const float4 q0 = __ldg(nodes + 4 * cur), q1 = __ldg(nodes + 4 * cur + 1), q2 = __ldg(nodes + 4 * cur + 2), q3 = __ldg(nodes + 4 * cur + 3);
+            const float lo0[3] = {q0.x, q0.y, q0.z}, hi0[3] = {q0.w, q1.x, q1.y}, lo1[3] = {q1.z, q1.w, q2.x}, hi1[3] = {q2.y, q2.z, q2.w};
+            const bool h0 = slab64(lo0, hi0, o, d, tMin, closest), h1 = slab64(lo1, hi1, o, d, tMin, closest);
+            const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
+            if (h0 && h1) { if (sp < 48) stack[sp++] = c1; cur = c0; }
+            else if (h0) cur = c0;
+            else if (h1) cur = c1;
+            else { if (sp == 0) break; cur = stack[--sp]; }
+        } else {
+            const int link = ~cur, first = link >> 2, cnt = (link & 3) + 1;
+            for (int k = 0; k < cnt; ++k) {
+                const float4 a = __ldg(tris + 3 * (first + k)), b = __ldg(tris + 3 * (first + k) + 1), c = __ldg(tris + 3 * (first + k) + 2);
+                const double e1x = b.x, e1y = b.y, e1z = b.z, e2x = c.x, e2y = c.y, e2z = c.z;
+                const double px = d[1] * e2z - d[2] * e2y, py = d[2] * e2x - d[0] * e2z, pz = d[0] * e2y - d[1] * e2x;
+                const double det = e1x * px + e1y * py + e1z * pz;
+                if (det == 0) continue;
+                const double idet = 1.0 / det;
+                const double tx = o[0] - (double)a.x, ty = o[1] - (double)a.y, tz = o[2] - (double)a.z;
+                const double u = (tx * px + ty * py + tz * pz) * idet;
+                if (u < 0 || u > 1) continue;
+                const double qx = ty * e1z - tz * e1y, qy = tz * e1x - tx * e1z, qz = tx * e1y - ty * e1x;
+                const double v = (d[0] * qx + d[1] * qy + d[2] * qz) * idet;
+                if (v < 0 || u + v > 1) continue;
+                const double t = (e2x * qx + e2y * qy + e2z * qz) * idet;
+                if (t < tMin || t > closest) continue;
+                const int tid = __float_as_int(a.w);
+                if (t < closest || (best_tri >= 0 && tid < best_tri)) { closest = t; id = __float_as_int(c.w); best_tri = tid; }
+            }
+            if (sp == 0) break;
+            cur = stack[--sp];
+        }
+    }
+}
+
+__global__ void primary_hits_kernel(const Obj64* __restrict__ world, int n_obj, const float4* __restrict__ bvh_nodes,
+                                    const float4* __restrict__ bvh_tris, Camera64 cam, int W, int H,
                                     double xi_u, double xi_v, int32_t* __restrict__ ids, double* __restrict__ tt) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
     if (x >= W || y >= H) return;
@@ -77,16 +135,17 @@ __global__ void primary_hits_kernel(const Obj64* __restrict__ world, int n_obj, 
     int id = -1;
     for (int i = 0; i < n_obj; i++) {                                 // renderer.go:297-302
         double t;
-        if (hit64(world[i], o, d, 0.001, closest, t)) { closest = t; id = i; }
+        if (hit64(world[i], o, d, 0.001, closest, t)) { closest = t; id = world[i].pad; }   // pad = world index
     }
+    if (bvh_nodes) bvh_closest64(bvh_nodes, bvh_tris, o, d, 0.001, closest, id);
     ids[(size_t)y * W + x] = id;
     tt[(size_t)y * W + x] = id >= 0 ? closest : 0.0;
 }
 
-int launch_primary_hits(const Obj64* d_world, int n_obj, const Camera64& cam, int width, int height, double xi_u,
-                        double xi_v, int32_t* d_ids, double* d_t, void* stream) {
+int launch_primary_hits(const Obj64* d_world, int n_obj, const float4* bvh_nodes, const float4* bvh_tris, const Camera64& cam,
+                        int width, int height, double xi_u, double xi_v, int32_t* d_ids, double* d_t, void* stream) {
     dim3 block(32, 8), grid((width + 31) / 32, (height + 7) / 8);
-    primary_hits_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(d_world, n_obj, cam, width, height, xi_u, xi_v, d_ids, d_t);
+    primary_hits_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(d_world, n_obj, bvh_nodes, bvh_tris, cam, width, height, xi_u, xi_v, d_ids, d_t);
     return (int)cudaGetLastError();
 }
 

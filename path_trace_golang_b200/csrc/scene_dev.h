@@ -52,7 +52,7 @@ struct DevScene {                        // ~43 KB of the 64 KB constant bank
 
 // fp64 world for the primary-hit parity kernel (global memory; N is tiny).
 struct Obj64 {
-    int32_t type, pad;
+    int32_t type, pad;   // pad = world index (meshes interleave with analytic objects in world order)
     double a[3], b[3];   // sphere: a centre, b.x radius | plane: a point, b normal | box: a min, b max
 };
 struct Camera64 {
@@ -72,11 +72,14 @@ struct FrameParams {
     uint8_t* rgba;               // W*H*4 finalised pixels, or nullptr
     unsigned long long* stats;   // kStatsWords counters, or nullptr
     unsigned int* work_counter;  // wavefront kernel: next unassigned pixel index (zeroed before the launch)
+    const float4* bvh_nodes;     // EXTENSION: BVH over the mesh triangles (bvh.h), nullptr when the scene has no mesh
+    const float4* bvh_tris;
 };
 
 enum StatWord {
     ST_SAMPLES = 0, ST_SEGMENTS, ST_EXIT_SCANS, ST_ACC_SPHERE, ST_ACC_PLANE, ST_ACC_BOX, ST_SCATTERS,
     ST_END_SKY, ST_END_EMISSIVE, ST_END_RR, ST_END_DEPTH, ST_END_NOSCATTER, ST_LANE_ACTIVE, ST_LANE_TOTAL,
+    ST_ACC_MESH, ST_BVH_NODES, ST_BVH_TRIS,
     kStatsWords
 };
 
@@ -85,8 +88,8 @@ int upload_scene_constants(const DevScene& host_scene, void* stream);
 int launch_integrator(const FrameParams& fp, bool stats, int n_obj, int n_mat, void* stream);
 int launch_integrator_wf(const FrameParams& fp, bool stats, int n_obj, int n_mat, int sm_count, void* stream);
 int launch_finalize(const float* accum, int width, int height, int spp_total, uint8_t* rgba, void* stream);
-int launch_primary_hits(const Obj64* d_world, int n_obj, const Camera64& cam, int width, int height,
-                        double xi_u, double xi_v, int32_t* d_ids, double* d_t, void* stream);
+int launch_primary_hits(const Obj64* d_world, int n_obj, const float4* bvh_nodes, const float4* bvh_tris, const Camera64& cam,
+                        int width, int height, double xi_u, double xi_v, int32_t* d_ids, double* d_t, void* stream);
 int launch_fma_peak(float* d_out, int blocks, int threads, int iters, void* stream);
 
 }  // namespace ptb

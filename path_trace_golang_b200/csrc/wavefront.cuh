@@ -171,6 +171,13 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
                 if (h) { best[k] = t; bid[k] = i; }
             }
         }
+        if (fp.bvh_nodes) {                  // EXTENSION: triangle meshes, tested after the analytic objects (bvh.cuh)
+#pragma unroll 1
+            for (int k = 0; k < WF_SPT; ++k) {
+                const int j = tid + k * WF_THREADS;
+                if (S.pix[j] >= 0 && S.depth[j] > 0) bvh_closest<STATS>(fp.bvh_nodes, fp.bvh_tris, ray[k], 0.001f, best[k], bid[k], st);
+            }
+        }
         int cls[WF_SPT];
 #pragma unroll
         for (int k = 0; k < WF_SPT; ++k) {
@@ -178,6 +185,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
             if (S.pix[j] < 0) cls[k] = CL_DEAD;
             else if (S.depth[j] <= 0) cls[k] = CL_REGEN;
             else if (bid[k] < 0) cls[k] = CL_TERM;
+            else if (bid[k] & kTriBit) cls[k] = (__float_as_int(__ldg(fp.bvh_tris + 3 * (bid[k] & ~kTriBit) + 1).w) >> 3) & 7;
             else cls[k] = (s_obj[bid[k]].meta >> 3) & 7;
             S.best[j] = best[k]; S.bid[j] = bid[k];
             if (STATS) { st[ST_LANE_TOTAL]++; if (cls[k] != CL_DEAD && cls[k] != CL_REGEN) { st[ST_LANE_ACTIVE]++; st[ST_SEGMENTS]++; } }
@@ -258,12 +266,19 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
             const F3 ro = f3(S.ox[j], S.oy[j], S.oz[j]);
             const F3 rd = f3(S.dx[j], S.dy[j], S.dz[j]);
             const float t_hit = S.best[j];
-            const DevObj ob = s_obj[S.bid[j]];
-            const int type = ob.meta & 3;
-            if (STATS) st[ST_ACC_SPHERE + type]++;
+            const int hid = S.bid[j];
             F3 p, n; bool front;
-            surface(ob, type, ro, rd, t_hit, p, n, front);
-            const DevMat m = s_mat[ob.meta >> 6];
+            int meta;
+            if (hid & kTriBit) {
+                tri_surface(fp.bvh_tris, hid & ~kTriBit, ro, rd, t_hit, p, n, front, meta);
+                if (STATS) st[ST_ACC_MESH]++;
+            } else {
+                const DevObj ob = s_obj[hid];
+                meta = ob.meta;
+                if (STATS) st[ST_ACC_SPHERE + (meta & 3)]++;
+                surface(ob, meta & 3, ro, rd, t_hit, p, n, front);
+            }
+            const DevMat m = s_mat[meta >> 6];
             Rng rng{S.key[j], S.ctr[j]};
             int depth = S.depth[j];
 
@@ -395,10 +410,11 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
                 e = sky_color(f3(S.dx[j], S.dy[j], S.dz[j]));
                 if (STATS) st[ST_END_SKY]++;
             } else {
-                const DevObj& ob = s_obj[hb];
-                const DevMat& m = s_mat[ob.meta >> 6];
+                const bool is_tri = (hb & kTriBit) != 0;
+                const int meta = is_tri ? __float_as_int(__ldg(fp.bvh_tris + 3 * (hb & ~kTriBit) + 1).w) : s_obj[hb].meta;
+                const DevMat& m = s_mat[meta >> 6];
                 e = f3(m.emit[0], m.emit[1], m.emit[2]);
-                if (STATS) { st[ST_END_EMISSIVE]++; st[ST_ACC_SPHERE + (ob.meta & 3)]++; }
+                if (STATS) { st[ST_END_EMISSIVE]++; st[is_tri ? ST_ACC_MESH : ST_ACC_SPHERE + (meta & 3)]++; }
             }
             S.ax[j] += S.bx[j] * e.x; S.ay[j] += S.by[j] * e.y; S.az[j] += S.bz[j] * e.z;
         }

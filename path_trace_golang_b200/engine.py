@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from ._lib import PROGRESS_FN, PtbCfg, PtbDeviceInfo, PtbError, PtbStats, PTB_FLAG_MEGAKERNEL, PTB_FLAG_STATS
+from ._lib import PROGRESS_FN, PtbBvhInfo, PtbCfg, PtbDeviceInfo, PtbError, PtbStats, PTB_FLAG_MEGAKERNEL, PTB_FLAG_STATS
 from .scene import RenderSettings, Scene
 
 BackendCPU, BackendGPU, BackendCUDA = 0, 1, 2      # backend.go:7-10 + the CUDA backend
@@ -131,6 +131,12 @@ class Context:
         s = PtbStats()
         self._check(self._L.ptb_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def bvh_info(self) -> dict:
+        """EXTENSION: the BVH ptb_scene_upload built over the mesh triangles (zeros without meshes)."""
+        b = PtbBvhInfo()
+        self._check(self._L.ptb_get_bvh_info(self._h, C.byref(b)))
+        return b.as_dict()
 
     def fp32_peak_tflops(self) -> float:
         v = C.c_double()

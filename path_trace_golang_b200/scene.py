@@ -54,6 +54,20 @@ class Scene:
             raise PtbError(rc, _lib.lib().ptb_host_last_error().decode())
         return s
 
+    def mesh_triangles(self) -> dict:
+        """EXTENSION: {object index: float32 (n_tri, 9) world-space triangles} of the "mesh" objects, as flattened."""
+        import numpy as np
+        f = self.flat()
+        out = {}
+        for i in range(f.n_obj):
+            m = f.obj_mesh[i] if f.n_mesh > 0 else -1
+            if m < 0:
+                continue
+            t0, t1 = f.mesh_tri_begin[m], f.mesh_tri_begin[m + 1]
+            if t1 > t0:
+                out[i] = np.ctypeslib.as_array(f.tri_vertices, shape=(f.mesh_tri_begin[f.n_mesh] * 9,))[t0 * 9:t1 * 9].reshape(-1, 9).copy()
+        return out
+
     def marshal(self) -> str:
         L = _lib.lib()
         n = L.ptb_host_scene_marshal(self._h, None, 0)

@@ -1,0 +1,171 @@
+"""EXTENSION (BASELINE config C4): triangle meshes + BVH.  The reference has neither, so the
+semantics are this repository's (DESIGN.md "Meshes"); the oracle implements them independently (brute force and its
+own median-split BVH), the product with a binned-SAH BVH traversed on the GPU."""
+import json
+
+import numpy as np
+import pytest
+
+from conftest import SCENE_DEPTH, scene_json
+
+CAM = {"position": {"x": 0, "y": 0, "z": 5}, "target": {"x": 0, "y": 0, "z": 0}, "up": {"x": 0, "y": 1, "z": 0}, "fov": 60}
+SKY = {"type": "solid", "color": {"r": 1, "g": 1, "b": 1}}
+
+
+def mesh_obj(vertices, triangles, pos=(0, 0, 0), size=(0, 0, 0), mat="m"):
+    return {"type": "mesh", "position": dict(zip("xyz", pos)), "size": dict(zip("xyz", size)), "material_id": mat,
+            "mesh": {"vertices": [float(x) for v in vertices for x in v], "triangles": [int(i) for t in triangles for i in t]}}
+
+
+def with_heightfield(name, nx, nz, pos=(0, 0.8, 1), size=(6, 1, 6), mat=None, seed=7):
+    sc = scene_json(name)
+    mat = mat or sc["materials"][0]["id"]
+    sc["objects"].append({"id": "terrain", "type": "mesh", "position": dict(zip("xyz", pos)), "size": dict(zip("xyz", size)),
+                          "material_id": mat,
+                          "mesh": {"heightfield": {"nx": nx, "nz": nz, "seed": seed, "amplitude": 0.4, "frequency": 3, "octaves": 3}}})
+    return sc
+
+
+LAMB = {"id": "m", "type": "lambert", "albedo": {"r": 0.5, "g": 0.5, "b": 0.5}}
+QUAD_V = [(-1, -1, 0), (1, -1, 0), (1, 1, 0), (-1, 1, 0)]
+QUAD_T = [(0, 1, 2), (0, 2, 3)]
+
+
+def test_triangle_hit_kats(oracle_mod):
+    """Moeller-Trumbore, two-sided, geometric normal flipped against the ray."""
+    sc = {"camera": CAM, "sky": SKY, "materials": [LAMB], "objects": [mesh_obj(QUAD_V, QUAD_T)]}
+    o = oracle_mod.OracleScene(sc)
+    ids, t, ff, _ = o.trace_path((0.25, 0.5, 5), (0, 0, -2), 1)
+    assert list(ids) == [0] and t[0] == 2.5 and ff[0] == 1            # CCW seen from +z: front face
+    ids, t, ff, _ = o.trace_path((0.25, 0.5, -4), (0, 0, 1), 1)
+    assert list(ids) == [0] and t[0] == 4.0 and ff[0] == 0            # from behind: back face
+    assert list(o.trace_path((1.5, 0, 5), (0, 0, -1), 1)[0]) == [-1]  # beside the quad
+    assert list(o.trace_path((0, 0, 5), (1, 0, 0), 1)[0]) == [-1]     # parallel: det == 0
+    assert list(o.trace_path((0, 0, 0.0005), (0, 0, -1), 1)[0]) == [-1]   # t < tMin = 0.001
+    w = o.world()
+    assert len(w) == 1 and w[0]["type"] == 3 and w[0]["a"] == [-1, -1, 0] and w[0]["b"] == [1, 1, 0]
+
+
+def test_mesh_tie_rules(oracle_mod):
+    """Meshes are scanned after the analytic objects and must beat them strictly; among triangles of equal t the
+    lowest triangle id wins (here: the diagonal shared by both triangles, and two coincident quads)."""
+    plane = {"type": "plane", "position": {"x": 0, "y": 0, "z": 0}, "size": {"x": 0, "y": 0, "z": 0}, "material_id": "m"}
+    floor = mesh_obj([(-1, 0, -1), (1, 0, -1), (1, 0, 1), (-1, 0, 1)], [(0, 2, 1), (0, 3, 2)])
+    for objs, want in (([floor, plane], 1), ([plane, floor], 0)):          # coplanar with the plane: the plane wins either way
+        sc = {"camera": CAM, "sky": SKY, "materials": [LAMB], "objects": objs}
+        assert list(oracle_mod.OracleScene(sc).trace_path((0.3, 2, 0.1), (0, -1, 0), 1)[0]) == [want]
+    two = {"camera": CAM, "sky": SKY, "materials": [LAMB], "objects": [mesh_obj(QUAD_V, QUAD_T), mesh_obj(QUAD_V, QUAD_T)]}
+    assert list(oracle_mod.OracleScene(two).trace_path((0.3, 0.1, 5), (0, 0, -1), 1)[0]) == [0]   # first mesh = lower triangle ids
+
+
+def test_host_mesh_flatten_generator_and_save(host_scenes):
+    from path_trace_golang_b200 import scene
+    doc = {"camera": CAM, "sky": SKY, "materials": [LAMB],
+           "objects": [mesh_obj(QUAD_V, QUAD_T, pos=(1, 2, 3), size=(2, 0, 0.5)),
+                       {"type": "mesh", "material_id": "m"},                                   # no triangles: dropped
+                       {"type": "mesh", "position": {"x": 0, "y": 0, "z": 0}, "size": {"x": 4, "y": 1, "z": 2}, "material_id": "m",
+                        "mesh": {"heightfield": {"nx": 5, "nz": 3, "seed": 11, "amplitude": 0.25, "frequency": 2, "octaves": 2}}}]}
+    sc = scene.Parse(json.dumps(doc))
+    flat = sc.flat()
+    assert [flat.obj_type[i] for i in range(3)] == [3, -1, 3] and [flat.obj_mesh[i] for i in range(3)] == [0, -1, 1]
+    tris = sc.mesh_triangles()
+    assert tris[0].shape == (2, 9) and tris[2].shape == (5 * 3 * 2, 9)
+    # world vertex = position + size * local (size 0 -> 1)
+    np.testing.assert_array_equal(tris[0][0], [1 - 2, 2 - 1, 3, 1 + 2, 2 - 1, 3, 1 + 2, 2 + 1, 3])
+    hf = tris[2].reshape(-1, 3)
+    assert hf[:, 0].min() == -2 and hf[:, 0].max() == 2 and hf[:, 2].min() == -1 and hf[:, 2].max() == 1
+    assert np.abs(hf[:, 1]).max() <= 0.25 * 1.5 + 1e-6 and hf[:, 1].std() > 0.01
+    # deterministic, and Save keeps the extension (generator parameters, not 30 triangles)
+    again = scene.Parse(sc.marshal())
+    np.testing.assert_array_equal(again.mesh_triangles()[2], tris[2])
+    np.testing.assert_array_equal(again.mesh_triangles()[0], tris[0])
+    assert '"heightfield"' in sc.marshal() and '"vertices"' in sc.marshal()
+    # shipped scenes are untouched by the extension
+    assert host_scenes["example_simple"].flat().n_mesh == 0
+    from path_trace_golang_b200 import PtbError
+    with pytest.raises(PtbError, match="decode scene"):
+        scene.Parse(json.dumps({"objects": [mesh_obj(QUAD_V, [(0, 1, 9)])]}))                  # index out of range
+
+
+def test_oracle_bvh_equals_bruteforce(oracle_mod):
+    from path_trace_golang_b200 import scene
+    doc = with_heightfield("example_simple", 40, 30)
+    tris = scene.Parse(json.dumps(doc)).mesh_triangles()
+    ora = oracle_mod.OracleScene(doc, mesh_triangles=tris)
+    a = ora.primary_hits(200, 112)
+    sa, _ = ora.render_sum(64, 36, 2, 8, seed=3, precision=64)
+    ora.set_mesh_accel(False)
+    b = ora.primary_hits(200, 112)
+    sb, _ = ora.render_sum(64, 36, 2, 8, seed=3, precision=64)
+    assert (a[0] == b[0]).all() and (a[1].view(np.uint64) == b[1].view(np.uint64)).all() and (sa == sb).all()
+    assert (a[0] == len(doc["objects"]) - 1).mean() > 0.05
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,nx,nz,res", [("example_simple", 40, 30, (1280, 720)), ("test_comprehensive", 300, 200, (1920, 1080))])
+def test_gpu_primary_hits_with_mesh_bit_exact(name, nx, nz, res, ctx, oracle_mod):
+    """ids and t of the binary64 kernel (BVH traversal + Moeller-Trumbore) == the oracle's, bit for bit."""
+    from path_trace_golang_b200 import scene
+    doc = with_heightfield(name, nx, nz, pos=(0, 1.0, 0), size=(8, 1, 8))
+    sc = scene.Parse(json.dumps(doc))
+    ctx.upload(sc)
+    info = ctx.bvh_info()
+    assert info["n_triangles"] == nx * nz * 2 and info["node_bytes"] == 64 and info["triangle_bytes"] == 48 and info["max_depth"] < 38
+    ids, t = ctx.primary_hits(*res)
+    oids, ot = oracle_mod.OracleScene(doc, mesh_triangles=sc.mesh_triangles()).primary_hits(*res)
+    assert (ids == oids).all(), f"{(ids != oids).sum()} id mismatches"
+    assert (t.view(np.uint64) == ot.view(np.uint64)).all()
+    mesh_idx = len(ctx.world()) - 1
+    assert ctx.world()[mesh_idx]["type"] == 3 and (ids == mesh_idx).mean() > 0.05
+
+
+@pytest.mark.gpu
+def test_gpu_mesh_render_vs_oracle(ctx, oracle_mod):
+    """fp32 integrator with a mesh in the scene: path-for-path vs the binary32 oracle (>= 99 % of pixels within 1e-3),
+    counters within 1 %, and the BVH counters are alive."""
+    from path_trace_golang_b200 import scene, PtbError
+    doc = with_heightfield("example_simple", 60, 40, pos=(0, 1.0, 1), size=(6, 1, 6), mat="metal-rough")
+    sc = scene.Parse(json.dumps(doc))
+    ctx.upload(sc)
+    ora = oracle_mod.OracleScene(doc, mesh_triangles=sc.mesh_triangles())
+    W, H, depth = 320, 180, 8
+    dev = ctx.render_accum(ctx.cfg(W, H, 1, depth, seed=7)).astype(np.float64)
+    ref, _ = ora.render_sum(W, H, 1, depth, seed=7, precision=32)
+    ok = (np.abs(dev - ref) <= 1e-3 * np.maximum(1.0, np.abs(ref))).all(axis=2).mean()
+    print(f"mesh scene path-for-path match {ok:.5f}")
+    assert ok >= 0.99
+    ctx.render_accum(ctx.cfg(W, H, 4, depth, seed=3, stats=True))
+    d = ctx.stats()
+    _, o = ora.render_sum(W, H, 4, depth, seed=3, precision=32)
+    for k in ["segments", "scatters", "end_sky", "end_emissive"]:
+        assert abs(d[k] - o[k]) <= 0.01 * max(o[k], 1000), (k, d[k], o[k])
+    assert d["accepts_mesh"] > 0.02 * d["segments"] and d["bvh_nodes_visited"] > d["segments"] and d["bvh_tris_tested"] > 0
+    assert sum(d["accepts"]) + d["accepts_mesh"] == d["segments"] - d["end_sky"]
+    with pytest.raises(PtbError, match="megakernel"):
+        ctx.render_accum(ctx.cfg(W, H, 1, depth, megakernel=True))
+
+
+@pytest.mark.gpu
+def test_gpu_c4_million_triangles(ctx, oracle_mod):
+    """C4: test_comprehensive + a 1M-triangle heightfield at 1920x1080.  Full-size properties: BVH stats, determinism,
+    primary ids vs the oracle (its own BVH) on a 480x270 sub-sampled grid of the same camera, bounded traversal work."""
+    from path_trace_golang_b200 import scene
+    doc = with_heightfield("test_comprehensive", 1000, 500, pos=(0, 0.6, 0), size=(16, 1.5, 12), mat="lambert-green")
+    sc = scene.Parse(json.dumps(doc))
+    ctx.upload(sc)
+    info = ctx.bvh_info()
+    print("C4 BVH:", info)
+    assert info["n_triangles"] == 1_000_000 and info["n_nodes"] < 600_000
+    ids, t = ctx.primary_hits(480, 270)
+    oids, ot = oracle_mod.OracleScene(doc, mesh_triangles=sc.mesh_triangles()).primary_hits(480, 270)
+    assert (ids == oids).all() and (t.view(np.uint64) == ot.view(np.uint64)).all()
+    cfg = ctx.cfg(1920, 1080, 4, 10, seed=1, stats=True)
+    a = ctx.render_accum(cfg)
+    st = ctx.stats()
+    b = ctx.render_accum(ctx.cfg(1920, 1080, 4, 10, seed=1))
+    assert np.array_equal(a, b)                                                      # deterministic
+    nodes_per_ray = st["bvh_nodes_visited"] / st["segments"]
+    tris_per_ray = st["bvh_tris_tested"] / st["segments"]
+    print(f"C4: {st['last_render_ms']:.1f} ms (stats variant), {nodes_per_ray:.1f} nodes/ray, {tris_per_ray:.1f} tris/ray, mesh hits {st['accepts_mesh'] / st['segments']:.3f}")
+    assert 1 < nodes_per_ray < 200 and tris_per_ray < 50
