@@ -32,7 +32,39 @@ WORKLOADS = {
     "C2": ("test_scene", 1920, 1080, 64, 10),
     "C3": ("metal_glass_room", 3840, 2160, 256, 16),
     "C5": ("gpu_showcase", 7680, 4320, 1024, 12),
+    # C4: test_comprehensive + a synthetic heightfield mesh (EXTENSION: the reference has no triangles), BVH-traversal bound
+    "C4_1M": ("test_comprehensive", 1920, 1080, 16, 10),
+    "C4_4M": ("test_comprehensive", 1920, 1080, 16, 10),
+    "C4_10M": ("test_comprehensive", 1920, 1080, 16, 10),
 }
+C4_MESH = {"C4_1M": (1000, 500), "C4_4M": (2000, 1000), "C4_10M": (3162, 1581)}   # quads; 2 triangles each
+
+
+def workload_doc(workload):
+    """Scene JSON document of a workload (the shipped scene; for C4 with the generated mesh object appended)."""
+    name = WORKLOADS[workload][0]
+    with open(ROOT / "scenes" / f"{name}.json") as f:
+        doc = json.load(f)
+    if workload in C4_MESH:
+        nx, nz = C4_MESH[workload]
+        doc["objects"].append({"id": "terrain", "type": "mesh", "position": {"x": 0, "y": 1.2, "z": 2},
+                               "size": {"x": 14, "y": 2.5, "z": 10}, "material_id": "lambert-green",
+                               "mesh": {"heightfield": {"nx": nx, "nz": nz, "seed": 1234, "amplitude": 0.4, "frequency": 3, "octaves": 4}}})
+    return doc
+
+
+def load_scene(workload):
+    from path_trace_golang_b200 import scene
+    if workload in C4_MESH:
+        return scene.Parse(json.dumps(workload_doc(workload)))
+    return scene.Load(ROOT / "scenes" / f"{WORKLOADS[workload][0]}.json")
+
+
+def load_oracle(workload):
+    from oracle import pyoracle
+    if workload in C4_MESH:
+        return pyoracle.OracleScene(workload_doc(workload), mesh_triangles=load_scene(workload).mesh_triangles())
+    return pyoracle.OracleScene.load(ROOT / "scenes" / f"{WORKLOADS[workload][0]}.json")
 # algorithmic flop constants, SURVEY.md §8(d): per primitive test / per accepted hit / per scattered bounce
 F_TEST = {0: 24, 1: 16, 2: 27}     # sphere, plane, box
 F_ACCEPT = {0: 25, 1: 9, 2: 23}
@@ -42,7 +74,8 @@ F_SHADE, F_PIXEL = 80, 12
 def world_counts(ctx):
     c = {0: 0, 1: 0, 2: 0}
     for o in ctx.world():
-        c[o["type"]] += 1
+        if o["type"] in c:          # analytic objects only (a mesh is credited through the BVH byte roofline)
+            c[o["type"]] += 1
     return c
 
 
@@ -98,8 +131,7 @@ class ClockSampler:
 
 def cpu_calibrate_spp(name, W, H, depth, threads, target_s, max_spp):
     """Pick the spp of the bounded CPU sample so that one full-resolution step takes about target_s seconds."""
-    from oracle import pyoracle
-    ora = pyoracle.OracleScene.load(ROOT / "scenes" / f"{name}.json")
+    ora = load_oracle(name)
     hh = max(32, H // 8)
     t0 = time.perf_counter()
     ora.render_rgba(W, hh, 1, depth, seed=1, threads=threads)       # also warms the thread pool / caches
@@ -109,8 +141,7 @@ def cpu_calibrate_spp(name, W, H, depth, threads, target_s, max_spp):
 
 def cpu_reference_run(name, W, H, depth, spp_sample, steps, warmup, threads):
     """Times the oracle's renderIntoCPU equivalent (fp64, 32x32 tile queue, `threads` workers)."""
-    from oracle import pyoracle
-    ora = pyoracle.OracleScene.load(ROOT / "scenes" / f"{name}.json")
+    ora = load_oracle(name)
     for _ in range(warmup):
         ora.render_rgba(W, max(2, H // 16), spp_sample, depth, seed=1, threads=threads)
     t0 = time.perf_counter()
@@ -139,7 +170,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     name, W, H, spp, depth = WORKLOADS[args.workload]
-    config = {"workload": f"{args.workload}: scenes/{name}.json {W}x{H}, {spp} spp, max depth {depth}", "scene": name,
+    mesh_note = f" + {C4_MESH[args.workload][0] * C4_MESH[args.workload][1] * 2} triangle heightfield" if args.workload in C4_MESH else ""
+    config = {"workload": f"{args.workload}: scenes/{name}.json{mesh_note} {W}x{H}, {spp} spp, max depth {depth}", "scene": name,
               "width": W, "height": H, "samples_per_px": spp, "max_depth": depth,
               "partition": "sample ranges per rank + NCCL reduce to rank 0" if world > 1 else "single GPU",
               "l2": "flushed between steps (256 MiB write); inputs are a few KB of constants"}
@@ -149,8 +181,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cpu_spp = args.cpu_spp or cpu_calibrate_spp(name, W, H, depth, cores, 6.0, spp)
-        msps, rays_per_sample, dt = cpu_reference_run(name, W, H, depth, cpu_spp, args.steps, min(args.warmup, 1), cores)
+        cpu_spp = args.cpu_spp or cpu_calibrate_spp(args.workload, W, H, depth, cores, 6.0, spp)
+        msps, rays_per_sample, dt = cpu_reference_run(args.workload, W, H, depth, cpu_spp, args.steps, min(args.warmup, 1), cores)
         sample = f"{W}x{H}, {cpu_spp} of {spp} spp per step (samples/s is spp-independent), depth {depth}"
         print(json.dumps({
             "impl": "reference", "metric": "Msamples/s", "value": msps, "unit": "Msamples/s", "n_gpus": 0,
@@ -176,8 +208,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     ctx = engine.Context(local_rank)
-    sc = scene.Load(ROOT / "scenes" / f"{name}.json")
+    sc = load_scene(args.workload)
     ctx.upload(sc)
+    bvh = ctx.bvh_info()
     stream = torch.cuda.current_stream(dev).cuda_stream
     cfg = ctx.cfg(W, H, spp, depth, seed=1)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -298,6 +331,7 @@ def main():
                                         "MEASURED_PEAKS.json has no fp32 entry; nominal 148x128x2x1.965 GHz = 74.5",
                          "note": "algorithmic flops by the reference's linear-scan definition (SURVEY §8d); this path is "
                                  "FP32-issue bound, not HBM or tensor bound: HBM traffic is ~4 B/pixel/frame"},
+            "bvh": bvh if bvh["n_triangles"] else None,
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": W * H * 4, "ms_per_step": e2e_s / args.steps * 1e3,
                     "api": "engine.RenderInto(scene, cfg, host image)" if world == 1 else
@@ -305,9 +339,29 @@ def main():
             "gpu_launches": args.steps * (1 if world == 1 else 2),
             "clocks": clocks,
         }
+        if bvh["n_triangles"]:
+            # C4 is bound by the latency/bandwidth of node + triangle fetches, not by FP32: report that roofline instead.
+            # Algorithmic bytes per launch = nodes visited x 64 B + triangles tested x 48 B (device counters).
+            bytes_per_sample = (st["bvh_nodes_visited"] * bvh["node_bytes"] + st["bvh_tris_tested"] * bvh["triangle_bytes"]) / st["samples"]
+            hbm_peak = None
+            try:
+                hbm_peak = json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"]
+            except Exception:
+                pass
+            ach = bytes_per_sample * (samples / world) / (kernel_ms * 1e-3) / 1e9
+            out["roofline_fp32"] = out["roofline"]
+            out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak or 6650.0, "unit": "GB/s",
+                               "frac": ach / (hbm_peak or 6650.0), "traffic": None, "kernel": "integrate_wf_kernel<false>",
+                               "kernel_ms": kernel_ms, "bytes_per_sample": bytes_per_sample,
+                               "nodes_per_ray": st["bvh_nodes_visited"] / st["segments"], "tris_per_ray": st["bvh_tris_tested"] / st["segments"],
+                               "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else "fallback 6.65 TB/s (of fallback)",
+                               "note": "node/triangle fetches are scattered 64/48-byte reads served mostly by the 126 MB L2 "
+                                       "(BVH + triangles of the 1M case = 67 MB); the bound is fetch latency, not DRAM bandwidth"}
+            h2d += int(bvh["n_triangles"]) * 36
+            out["e2e"]["h2d_bytes_per_step"] = h2d
         if not args.no_cpu and world == 1:
-            cpu_spp = args.cpu_spp or cpu_calibrate_spp(name, W, H, depth, cores, 15.0, spp)
-            msps, _, dt = cpu_reference_run(name, W, H, depth, cpu_spp, 1, 0, cores)
+            cpu_spp = args.cpu_spp or cpu_calibrate_spp(args.workload, W, H, depth, cores, 15.0, spp)
+            msps, _, dt = cpu_reference_run(args.workload, W, H, depth, cpu_spp, 1, 0, cores)
             out["cpu_baseline"] = {"value": msps, "unit": "Msamples/s", "cores": cores, "kind": "port",
                                    "sample": f"{W}x{H}, {cpu_spp} of {spp} spp, depth {depth}, {dt:.1f} s, {cores} worker threads",
                                    "note": "C++ restatement of the Go CPU path (Go toolchain unavailable)"}

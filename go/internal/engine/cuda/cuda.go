@@ -170,6 +170,9 @@ func flatten(sc *scene.Scene) *flatScene {
 	s.camera.up = [3]C.double{C.double(c.Up.X), C.double(c.Up.Y), C.double(c.Up.Z)}
 	s.camera.fov, s.camera.aperture = C.double(c.FOV), C.double(c.Aperture)
 	s.camera.focus_dist, s.camera.aspect_ratio = C.double(c.FocusDist), C.double(c.AspectRatio)
+	// no meshes: scene.Object has no mesh field in the reference (the extension is documented in DESIGN.md §3.7);
+	// a maintainer who adds it fills obj_mesh / mesh_tri_begin / tri_vertices here
+	s.n_mesh, s.obj_mesh, s.mesh_tri_begin, s.tri_vertices = 0, nil, nil, nil
 	// sky selection of renderIntoCPU, renderer.go:56-92
 	if sc.Sky != nil && sc.Sky.Type == "gradient" {
 		s.sky.kind = C.PTB_SKY_GRADIENT

@@ -107,7 +107,7 @@ def test_oracle_bvh_equals_bruteforce(oracle_mod):
 def test_gpu_primary_hits_with_mesh_bit_exact(name, nx, nz, res, ctx, oracle_mod):
     """ids and t of the binary64 kernel (BVH traversal + Moeller-Trumbore) == the oracle's, bit for bit."""
     from path_trace_golang_b200 import scene
-    doc = with_heightfield(name, nx, nz, pos=(0, 1.0, 0), size=(8, 1, 8))
+    doc = with_heightfield(name, nx, nz, pos=(0, 1.2, 2), size=(14, 2.5, 10))
     sc = scene.Parse(json.dumps(doc))
     ctx.upload(sc)
     info = ctx.bvh_info()
@@ -151,7 +151,7 @@ def test_gpu_c4_million_triangles(ctx, oracle_mod):
     """C4: test_comprehensive + a 1M-triangle heightfield at 1920x1080.  Full-size properties: BVH stats, determinism,
     primary ids vs the oracle (its own BVH) on a 480x270 sub-sampled grid of the same camera, bounded traversal work."""
     from path_trace_golang_b200 import scene
-    doc = with_heightfield("test_comprehensive", 1000, 500, pos=(0, 0.6, 0), size=(16, 1.5, 12), mat="lambert-green")
+    doc = with_heightfield("test_comprehensive", 1000, 500, pos=(0, 1.2, 2), size=(14, 2.5, 10), mat="lambert-green")
     sc = scene.Parse(json.dumps(doc))
     ctx.upload(sc)
     info = ctx.bvh_info()

@@ -9,7 +9,7 @@ import time
 
 ROOT = pathlib.Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
-from bench import WORKLOADS  # noqa: E402
+from bench import WORKLOADS, load_scene  # noqa: E402
 from path_trace_golang_b200 import engine, scene  # noqa: E402
 
 wl = sys.argv[1] if len(sys.argv) > 1 else "C3"
@@ -17,7 +17,9 @@ spp = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 name, W, H, _, depth = WORKLOADS[wl]
 ctx = engine.Context(0)
-ctx.upload(scene.Load(ROOT / "scenes" / f"{name}.json"))
+ctx.upload(load_scene(wl))
+if ctx.bvh_info()["n_triangles"]:
+    print("bvh:", ctx.bvh_info())
 import torch  # noqa: E402
 out = torch.empty((H, W, 4), dtype=torch.uint8, device="cuda")
 for i in range(reps):
