@@ -1,0 +1,44 @@
+"""tools/render.py — the headless driver (twin of cmd/render/main.go:46-63)."""
+import importlib.util
+import pathlib
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, scene_path
+
+spec = importlib.util.spec_from_file_location("render_cli", ROOT / "tools" / "render.py")
+render_cli = importlib.util.module_from_spec(spec)
+spec.loader.exec_module(render_cli)
+
+
+def test_flag_names_and_settings_resolution():
+    from path_trace_golang_b200 import engine, scene
+    a = render_cli.parse([])
+    assert (a.scene, a.mode, a.out) == ("scenes/example_simple.json", "preview", "output.png")     # main.go:17-21 defaults
+    sc = scene.Load(scene_path("example_simple"))
+    preview, final = engine.RenderSettingsForMode("preview"), engine.RenderSettingsForMode("final")
+    assert render_cli.resolve_settings(render_cli.parse([]), sc.Settings, preview) == (400, 225, 20, 20)      # headless ignores scene.settings (main.go:52)
+    assert render_cli.resolve_settings(render_cli.parse(["-mode", "final"]), sc.Settings, final) == (1920, 1080, 1000, 80)
+    assert render_cli.resolve_settings(render_cli.parse(["-settings"]), sc.Settings, preview) == (400, 225, 20, 10)   # scene file: depth 10
+    c1 = render_cli.parse(["-width", "640", "-height", "360", "-spp", "16", "-depth", "8"])
+    assert render_cli.resolve_settings(c1, sc.Settings, preview) == (640, 360, 16, 8)               # BASELINE config C1 is reachable
+    zero = scene.Load(scene_path("metal_glass_room")).Settings                                      # all-zero settings block
+    assert render_cli.resolve_settings(render_cli.parse(["-settings"]), zero, preview) == (400, 225, 20, 20)
+
+
+def test_missing_scene_is_an_error(capsys):
+    assert render_cli.main(["-scene", "/nonexistent.json"]) == 1
+    assert "load scene" in capsys.readouterr().err
+
+
+@pytest.mark.gpu
+def test_headless_render_writes_png(tmp_path):
+    from PIL import Image
+    out = tmp_path / "o.png"
+    rc = render_cli.main(["-scene", str(scene_path("example_simple")), "-width", "160", "-height", "90", "-spp", "8", "-depth", "8",
+                          "-out", str(out)])
+    assert rc == 0
+    img = np.array(Image.open(out))
+    assert img.shape == (90, 160, 4) and (img[..., 3] == 255).all() and img[..., :3].std() > 5
