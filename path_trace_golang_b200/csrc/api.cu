@@ -208,7 +208,7 @@ int render_launch(ptb_ctx* c, const ptb_cfg* cfg, int s0, int s1, float* d_accum
 
     const bool stats = (cfg->flags & PTB_FLAG_STATS) != 0;
     const bool dbg_timing = std::getenv("PTB_DEBUG_TIMING") != nullptr;   // only meaningful in -DPTB_WF_TIMING builds
-    if (stats || dbg_timing) CK(c, cudaMemsetAsync(c->d_stats, 0, sizeof(unsigned long long) * (kStatsWords + 8), stream));
+    if (stats || dbg_timing) CK(c, cudaMemsetAsync(c->d_stats, 0, sizeof(unsigned long long) * (kStatsWords + 24), stream));
 
     FrameParams fp{};
     fp.width = W; fp.height = H; fp.s_begin = s0; fp.s_end = s1;
@@ -241,6 +241,10 @@ int fetch_stats(ptb_ctx* c, bool stats, float ms) {
             const double warps_iters = iters * 8.0;            // lane 0 of every warp contributes to t[0..2]
             std::fprintf(stderr, "wf cycles per CTA-iteration: scan %.0f  sort %.0f  shade(mean over warps) %.0f  shade(max over warps) %.0f\n",
                          t[0] / warps_iters, t[1] / warps_iters, t[2] / warps_iters, t[3] / iters);
+            unsigned long long cc[12];
+            cudaMemcpy(cc, c->d_stats + kStatsWords + 8, sizeof cc, cudaMemcpyDeviceToHost);
+            const char* names[6] = {"DIEL", "DIFFUSE", "TERM", "REGEN", "SPEC", "DEAD"};
+            for (int k = 0; k < 6; k++) if (cc[2 * k + 1]) std::fprintf(stderr, "   chunk class %-8s mean %.0f cycles  (%llu chunks)\n", names[k], (double)cc[2 * k] / cc[2 * k + 1], cc[2 * k + 1]);
         }
     }
     if (!stats) return PTB_OK;
@@ -288,7 +292,7 @@ int ptb_create(int device, ptb_ctx** out) {
     if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return bail("cudaEventCreate", e);
     if ((e = cudaMallocHost((void**)&c->h_scene, sizeof(DevScene))) != cudaSuccess) return bail("cudaMallocHost", e);
     std::memset(c->h_scene, 0, sizeof(DevScene));
-    if ((e = cudaMalloc((void**)&c->d_stats, sizeof(unsigned long long) * (kStatsWords + 8))) != cudaSuccess) return bail("cudaMalloc", e);
+    if ((e = cudaMalloc((void**)&c->d_stats, sizeof(unsigned long long) * (kStatsWords + 24))) != cudaSuccess) return bail("cudaMalloc", e);
     if ((e = cudaMalloc((void**)&c->d_work, sizeof(unsigned int))) != cudaSuccess) return bail("cudaMalloc", e);
     *out = c;
     return PTB_OK;
@@ -386,13 +390,13 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
     }
     if (n_analytic > PTB_MAX_OBJECTS) return fail(c, PTB_ERR_LIMIT, "%d analytic objects > PTB_MAX_OBJECTS=%d", n_analytic, PTB_MAX_OBJECTS);
     auto meta_of = [](const World64Entry& w) {
-        // shading class of the wavefront kernel (enum in wavefront.cuh): 0 dielectric, 1 diffuse (lambert, rough metal),
-        // 2 terminate (emissive), 4 specular (mirror, smooth metal)
-        int cls = 1;
-        if (w.mat_type == PTB_MAT_METAL) cls = ((float)w.rough > 1e-6f) ? 1 : 4;
+        // shading class of the wavefront kernel (enum in wavefront.cuh): 0 dielectric, 1 terminate (emissive),
+        // 3 diffuse (lambert, rough metal), 4 specular (mirror, smooth metal)
+        int cls = 3;
+        if (w.mat_type == PTB_MAT_METAL) cls = ((float)w.rough > 1e-6f) ? 3 : 4;
         else if (w.mat_type == PTB_MAT_MIRROR) cls = 4;
         else if (w.mat_type == PTB_MAT_DIELECTRIC) cls = 0;
-        else if (w.mat_type == PTB_MAT_EMISSIVE) cls = 2;
+        else if (w.mat_type == PTB_MAT_EMISSIVE) cls = 1;
         return w.type | ((w.mat_type == PTB_MAT_DIELECTRIC) << 2) | (cls << 3) | (w.mat_slot << 6);
     };
 

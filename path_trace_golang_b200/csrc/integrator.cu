@@ -546,29 +546,30 @@ int launch_integrator(const FrameParams& fp, bool stats, int n_obj, int n_mat, v
     return (int)cudaGetLastError();
 }
 
-int launch_integrator_wf(const FrameParams& fp, bool stats, int n_obj, int n_mat, int sm_count, void* stream) {
-    static int blocks_per_sm[2] = {0, 0};
-    const size_t smem = ((sizeof(WfState) + 15) / 16 + (size_t)(n_obj * 2 + n_mat * 3)) * sizeof(uint4);
-    if (!blocks_per_sm[stats]) {
+template <bool STATS, bool MESH>
+static int launch_wf_variant(const FrameParams& fp, size_t smem, int sm_count, cudaStream_t stream) {
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(integrate_wf_kernel<STATS, MESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         int nb = 0;
-        cudaError_t e;
-        if (stats) {
-            if (smem > 48 * 1024) cudaFuncSetAttribute(integrate_wf_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, integrate_wf_kernel<true>, WF_THREADS, smem);
-        } else {
-            if (smem > 48 * 1024) cudaFuncSetAttribute(integrate_wf_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, integrate_wf_kernel<false>, WF_THREADS, smem);
-        }
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, integrate_wf_kernel<STATS, MESH>, WF_THREADS, smem);
         if (e != cudaSuccess) return (int)e;
-        blocks_per_sm[stats] = nb > 0 ? nb : 1;
+        blocks_per_sm = nb > 0 ? nb : 1;
     }
     const long long n_pix = (long long)fp.width * fp.height;
-    long long grid = (long long)sm_count * blocks_per_sm[stats];
+    long long grid = (long long)sm_count * blocks_per_sm;
     const long long need = (n_pix + WF_SLOTS - 1) / WF_SLOTS;
     if (grid > need) grid = need;
-    if (stats) integrate_wf_kernel<true><<<(unsigned)grid, WF_THREADS, smem, (cudaStream_t)stream>>>(fp);
-    else integrate_wf_kernel<false><<<(unsigned)grid, WF_THREADS, smem, (cudaStream_t)stream>>>(fp);
+    integrate_wf_kernel<STATS, MESH><<<(unsigned)grid, WF_THREADS, smem, stream>>>(fp);
     return (int)cudaGetLastError();
+}
+
+int launch_integrator_wf(const FrameParams& fp, bool stats, int n_obj, int n_mat, int sm_count, void* stream) {
+    const size_t smem = ((sizeof(WfState) + 15) / 16 + (size_t)(n_obj * 2 + n_mat * 3)) * sizeof(uint4);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool mesh = fp.bvh_nodes != nullptr;      // the mesh-free instantiation carries no traversal code (it costs ~10 %)
+    if (stats) return mesh ? launch_wf_variant<true, true>(fp, smem, sm_count, st) : launch_wf_variant<true, false>(fp, smem, sm_count, st);
+    return mesh ? launch_wf_variant<false, true>(fp, smem, sm_count, st) : launch_wf_variant<false, false>(fp, smem, sm_count, st);
 }
 
 int launch_finalize(const float* accum, int width, int height, int spp_total, uint8_t* rgba, void* stream) {

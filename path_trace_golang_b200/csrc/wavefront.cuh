@@ -29,12 +29,18 @@ namespace ptb {
 constexpr int WF_THREADS = PTB_WF_THREADS;
 constexpr int WF_WARPS = WF_THREADS / 32;
 constexpr int WF_SPT = PTB_WF_SPT;
+#ifndef PTB_WF_SCAN_GROUP
+#define PTB_WF_SCAN_GROUP 2           // rays tested together against each object record (register pressure)
+#endif
+constexpr int WF_SG = PTB_WF_SCAN_GROUP;
+static_assert(WF_SPT % WF_SG == 0, "PTB_WF_SPT must be a multiple of PTB_WF_SCAN_GROUP");
 constexpr int WF_SLOTS = WF_THREADS * WF_SPT;
 constexpr int WF_CHUNKS = WF_SLOTS / 32;
 // Classes in sort order = the order in which warps pull 32-slot chunks in the SHADE phase: heaviest first
 // (longest-processing-time-first keeps the phase balanced), TERM and REGEN adjacent (they share the regeneration code).
 // CL_DIEL..CL_SPEC match the class bits the host writes into DevObj::meta (api.cu).
-enum : int { CL_DIEL = 0, CL_DIFFUSE = 1, CL_TERM = 2, CL_REGEN = 3, CL_SPEC = 4, CL_DEAD = 5, CL_COUNT = 6 };
+// Measured chunk costs on C3 (cycles, -DPTB_WF_TIMING): DIEL 5500, TERM 3450, REGEN 2740, DIFFUSE 2210, SPEC 1630.
+enum : int { CL_DIEL = 0, CL_TERM = 1, CL_REGEN = 2, CL_DIFFUSE = 3, CL_SPEC = 4, CL_DEAD = 5, CL_COUNT = 6 };
 
 struct WfState {                       // SoA, one entry per slot
     float ox[WF_SLOTS], oy[WF_SLOTS], oz[WF_SLOTS];
@@ -51,7 +57,7 @@ struct WfState {                       // SoA, one entry per slot
     int cnt[CL_COUNT * WF_WARPS];
 };
 
-template <bool STATS>
+template <bool STATS, bool MESH>
 __global__ void __launch_bounds__(WF_THREADS, PTB_WF_MIN_BLOCKS)
 integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
     extern __shared__ uint4 s_raw[];
@@ -142,53 +148,58 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
 #define PTB_MARK()
 #endif
     for (;;) {
-        // ------------------------------------------------------------ SCAN (thread <-> its own WF_SPT slots)
-        RayK ray[WF_SPT];
-        float best[WF_SPT];
-        int bid[WF_SPT];
-#pragma unroll
-        for (int k = 0; k < WF_SPT; ++k) {
-            const int j = tid + k * WF_THREADS;
-            ray[k] = make_ray(f3(S.ox[j], S.oy[j], S.oz[j]), f3(S.dx[j], S.dy[j], S.dz[j]));
-            best[k] = FLT_MAX; bid[k] = -1;
-        }
-#pragma unroll 2
-        for (int i = 0; i < n_box; ++i) {
-            const float4 lo = obj_lo(i), hi = obj_hi(i);
-#pragma unroll
-            for (int k = 0; k < WF_SPT; ++k) {
-                float t;
-                if (hit_box(lo, hi, ray[k], 0.001f, best[k], t)) { best[k] = t; bid[k] = i; }
-            }
-        }
-        for (int i = n_box; i < n_obj; ++i) {
-            const float4 lo = obj_lo(i), hi = obj_hi(i);
-            const bool is_sphere = (__float_as_int(lo.w) & 3) == PTB_OBJ_SPHERE;
-#pragma unroll
-            for (int k = 0; k < WF_SPT; ++k) {
-                float t;
-                const bool h = is_sphere ? hit_sphere(lo, hi, ray[k], 0.001f, best[k], t) : hit_plane(lo, ray[k], 0.001f, best[k], t);
-                if (h) { best[k] = t; bid[k] = i; }
-            }
-        }
-        if (fp.bvh_nodes) {                  // EXTENSION: triangle meshes, tested after the analytic objects (bvh.cuh)
-#pragma unroll 1
-            for (int k = 0; k < WF_SPT; ++k) {
-                const int j = tid + k * WF_THREADS;
-                if (S.pix[j] >= 0 && S.depth[j] > 0) bvh_closest<STATS>(fp.bvh_nodes, fp.bvh_tris, ray[k], 0.001f, best[k], bid[k], st);
-            }
-        }
+        // ------------------------------------------------------------ SCAN (thread <-> its own WF_SPT slots, WF_SG rays at a time)
         int cls[WF_SPT];
 #pragma unroll
-        for (int k = 0; k < WF_SPT; ++k) {
-            const int j = tid + k * WF_THREADS;
-            if (S.pix[j] < 0) cls[k] = CL_DEAD;
-            else if (S.depth[j] <= 0) cls[k] = CL_REGEN;
-            else if (bid[k] < 0) cls[k] = CL_TERM;
-            else if (bid[k] & kTriBit) cls[k] = (__float_as_int(__ldg(fp.bvh_tris + 3 * (bid[k] & ~kTriBit) + 1).w) >> 3) & 7;
-            else cls[k] = (s_obj[bid[k]].meta >> 3) & 7;
-            S.best[j] = best[k]; S.bid[j] = bid[k];
-            if (STATS) { st[ST_LANE_TOTAL]++; if (cls[k] != CL_DEAD && cls[k] != CL_REGEN) { st[ST_LANE_ACTIVE]++; st[ST_SEGMENTS]++; } }
+        for (int g = 0; g < WF_SPT; g += WF_SG) {
+            RayK ray[WF_SG];
+            float best[WF_SG];
+            int bid[WF_SG];
+#pragma unroll
+            for (int k = 0; k < WF_SG; ++k) {
+                const int j = tid + (g + k) * WF_THREADS;
+                ray[k] = make_ray(f3(S.ox[j], S.oy[j], S.oz[j]), f3(S.dx[j], S.dy[j], S.dz[j]));
+                best[k] = FLT_MAX; bid[k] = -1;
+            }
+#pragma unroll 2
+            for (int i = 0; i < n_box; ++i) {
+                const float4 lo = obj_lo(i), hi = obj_hi(i);
+#pragma unroll
+                for (int k = 0; k < WF_SG; ++k) {
+                    float t;
+                    if (hit_box(lo, hi, ray[k], 0.001f, best[k], t)) { best[k] = t; bid[k] = i; }
+                }
+            }
+            for (int i = n_box; i < n_obj; ++i) {
+                const float4 lo = obj_lo(i), hi = obj_hi(i);
+                const bool is_sphere = (__float_as_int(lo.w) & 3) == PTB_OBJ_SPHERE;
+#pragma unroll
+                for (int k = 0; k < WF_SG; ++k) {
+                    float t;
+                    const bool h = is_sphere ? hit_sphere(lo, hi, ray[k], 0.001f, best[k], t) : hit_plane(lo, ray[k], 0.001f, best[k], t);
+                    if (h) { best[k] = t; bid[k] = i; }
+                }
+            }
+            if (MESH) {                      // EXTENSION: triangle meshes, tested after the analytic objects (bvh.cuh)
+#pragma unroll 1
+                for (int k = 0; k < WF_SG; ++k) {
+                    const int j = tid + (g + k) * WF_THREADS;
+                    if (S.pix[j] >= 0 && S.depth[j] > 0) bvh_closest<STATS>(fp.bvh_nodes, fp.bvh_tris, ray[k], 0.001f, best[k], bid[k], st);
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < WF_SG; ++k) {
+                const int j = tid + (g + k) * WF_THREADS;
+                int c;
+                if (S.pix[j] < 0) c = CL_DEAD;
+                else if (S.depth[j] <= 0) c = CL_REGEN;
+                else if (bid[k] < 0) c = CL_TERM;
+                else if (MESH && (bid[k] & kTriBit)) c = (__float_as_int(__ldg(fp.bvh_tris + 3 * (bid[k] & ~kTriBit) + 1).w) >> 3) & 7;
+                else c = (s_obj[bid[k]].meta >> 3) & 7;
+                cls[g + k] = c;
+                S.best[j] = best[k]; S.bid[j] = bid[k];
+                if (STATS) { st[ST_LANE_TOTAL]++; if (c != CL_DEAD && c != CL_REGEN) { st[ST_LANE_ACTIVE]++; st[ST_SEGMENTS]++; } }
+            }
         }
 
         PTB_TICK(0)
@@ -262,6 +273,10 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
         if (chunk >= live_chunks) continue;
         const unsigned pv = S.perm[chunk * 32 + lane];
         const int j = pv & 0xFFF, c = pv >> 12;
+#ifdef PTB_WF_TIMING
+        const long long tc0 = clock64();
+        const int c_lane0 = __shfl_sync(0xffffffffu, c, 0), c_lane31 = __shfl_sync(0xffffffffu, c, 31);
+#endif
         if (c == CL_DIEL || c == CL_DIFFUSE || c == CL_SPEC) {
             const F3 ro = f3(S.ox[j], S.oy[j], S.oz[j]);
             const F3 rd = f3(S.dx[j], S.dy[j], S.dz[j]);
@@ -269,7 +284,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
             const int hid = S.bid[j];
             F3 p, n; bool front;
             int meta;
-            if (hid & kTriBit) {
+            if (MESH && (hid & kTriBit)) {
                 tri_surface(fp.bvh_tris, hid & ~kTriBit, ro, rd, t_hit, p, n, front, meta);
                 if (STATS) st[ST_ACC_MESH]++;
             } else {
@@ -410,7 +425,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
                 e = sky_color(f3(S.dx[j], S.dy[j], S.dz[j]));
                 if (STATS) st[ST_END_SKY]++;
             } else {
-                const bool is_tri = (hb & kTriBit) != 0;
+                const bool is_tri = MESH && (hb & kTriBit) != 0;
                 const int meta = is_tri ? __float_as_int(__ldg(fp.bvh_tris + 3 * (hb & ~kTriBit) + 1).w) : s_obj[hb].meta;
                 const DevMat& m = s_mat[meta >> 6];
                 e = f3(m.emit[0], m.emit[1], m.emit[2]);
@@ -419,6 +434,12 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
             S.ax[j] += S.bx[j] * e.x; S.ay[j] += S.by[j] * e.y; S.az[j] += S.bz[j] * e.z;
         }
         if (c == CL_TERM || c == CL_REGEN) regen(j, true);
+#ifdef PTB_WF_TIMING
+        if (lane == 0 && fp.stats && c_lane0 == c_lane31) {      // homogeneous chunks only
+            atomicAdd(fp.stats + kStatsWords + 8 + 2 * c_lane0, (unsigned long long)(clock64() - tc0));
+            atomicAdd(fp.stats + kStatsWords + 8 + 2 * c_lane0 + 1, 1ull);
+        }
+#endif
         }   // chunk loop
 #ifdef PTB_WF_TIMING
         { long long now_ = clock64(); int dt_ = (int)(now_ - tq); tm[2] += dt_; if (lane == 0) atomicMax(&s_tmax, dt_); }
