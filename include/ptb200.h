@@ -116,6 +116,8 @@ typedef struct {
 } ptb_cfg;
 
 #define PTB_FLAG_STATS 1u       /* run the counting variant of the integrator (slower); fills ptb_stats */
+#define PTB_FLAG_WAVEQUEUE 4u   /* EXPERIMENTAL, only in builds with -DPTB_ENABLE_WAVEQUEUE (otherwise the render call fails):
+                                   persistent warps + shared-memory work queues instead of barrier phases */
 #define PTB_FLAG_MEGAKERNEL 2u  /* use the pixel-per-lane megakernel instead of the default wavefront-in-shared-memory
                                    kernel (same results up to fp32 rounding; kept for A/B profiling) */
 

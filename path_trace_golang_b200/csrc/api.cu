@@ -52,6 +52,10 @@ struct ptb_ctx {
     int n_world64 = 0;
     BvhNode* d_bvh_nodes = nullptr;      // EXTENSION: mesh BVH
     BvhTri* d_bvh_tris = nullptr;
+    BvhNode* d_bvh_nodes_keep = nullptr; // last built BVH, reused when the same triangles are uploaded again
+    BvhTri* d_bvh_tris_keep = nullptr;
+    ptb_bvh_info bvh_keep{};
+    uint64_t bvh_key = 0;
     ptb_bvh_info bvh{};
 
     // scratch device buffers, grown on demand
@@ -224,7 +228,8 @@ int render_launch(ptb_ctx* c, const ptb_cfg* cfg, int s0, int s1, float* d_accum
     } else {
         fp.work_counter = c->d_work;
         CK(c, cudaMemsetAsync(c->d_work, 0, sizeof(unsigned int), stream));
-        e = launch_integrator_wf(fp, stats, c->h_scene->n_obj, c->h_scene->n_mat, c->prop.multiProcessorCount, stream);
+        if (cfg->flags & PTB_FLAG_WAVEQUEUE) e = launch_integrator_wq(fp, stats, c->h_scene->n_obj, c->h_scene->n_mat, c->prop.multiProcessorCount, stream);
+        else e = launch_integrator_wf(fp, stats, c->h_scene->n_obj, c->h_scene->n_mat, c->prop.multiProcessorCount, stream);
     }
     if (e) return fail(c, PTB_ERR_CUDA, "integrator launch: %s", cudaGetErrorString((cudaError_t)e));
     return PTB_OK;
@@ -236,7 +241,10 @@ int fetch_stats(ptb_ctx* c, bool stats, float ms) {
         unsigned long long t[6];
         cudaMemcpy(t, c->d_stats + kStatsWords, sizeof t, cudaMemcpyDeviceToHost);
         double tot = 0; for (int k = 0; k < 6; k++) tot += (double)t[k];
-        if (tot > 0 && t[4] > 0) {
+        if (std::getenv("PTB_WQ_DEBUG_PRINT"))
+            std::fprintf(stderr, "wq: scan items %llu (%.1f slots/item)  shade items %llu (%.1f slots/item)  idle polls %llu  lock spins %llu\n",
+                         t[0], t[0] ? (double)t[2] / t[0] : 0.0, t[1], t[1] ? (double)t[3] / t[1] : 0.0, t[4], t[5]);
+        else if (tot > 0 && t[4] > 0) {
             const double iters = (double)t[4];                 // CTA-iterations (thread 0 of every CTA)
             const double warps_iters = iters * 8.0;            // lane 0 of every warp contributes to t[0..2]
             std::fprintf(stderr, "wf cycles per CTA-iteration: scan %.0f  sort %.0f  shade(mean over warps) %.0f  shade(max over warps) %.0f\n",
@@ -302,7 +310,7 @@ void ptb_destroy(ptb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_blob); cudaFree(c->d_world64); cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_tris); cudaFree(c->d_accum); cudaFree(c->d_rgba); cudaFree(c->d_stats); cudaFree(c->d_work);
+    cudaFree(c->d_blob); cudaFree(c->d_world64); cudaFree(c->d_bvh_nodes_keep); cudaFree(c->d_bvh_tris_keep); cudaFree(c->d_accum); cudaFree(c->d_rgba); cudaFree(c->d_stats); cudaFree(c->d_work);
     if (c->h_scene) cudaFreeHost(c->h_scene);
     if (c->h_rgba) cudaFreeHost(c->h_rgba);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -440,12 +448,26 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
         if (world[i].type != PTB_OBJ_MESH && world[i].mat_type == PTB_MAT_DIELECTRIC) hs.diel_idx[hs.n_diel++] = dev_of[i];
 
     // EXTENSION: BVH over the mesh triangles
-    cudaFree(c->d_bvh_nodes); c->d_bvh_nodes = nullptr;
-    cudaFree(c->d_bvh_tris); c->d_bvh_tris = nullptr;
+    c->d_bvh_nodes = nullptr; c->d_bvh_tris = nullptr;      // (the kept copy is freed when a different mesh set arrives)
     c->bvh = ptb_bvh_info{};
     if (!tri_world.empty()) {
         std::vector<int32_t> tri_meta(tri_world.size());
         for (size_t q = 0; q < tri_world.size(); q++) tri_meta[q] = meta_of(world[tri_world[q]]);
+        // Re-uploading the same meshes (RenderInto takes the scene on every call, renderer.go:34) must not rebuild the BVH:
+        // key = FNV-1a over the triangle soup and the per-triangle material/world tags.
+        auto fnv = [](uint64_t h, const void* p, size_t n) {
+            const uint64_t* w = (const uint64_t*)p;
+            for (size_t i = 0; i < n / 8; i++) { h ^= w[i]; h *= 0x100000001b3ull; }
+            const unsigned char* b = (const unsigned char*)p + (n / 8) * 8;
+            for (size_t i = 0; i < n % 8; i++) { h ^= b[i]; h *= 0x100000001b3ull; }
+            return h;
+        };
+        uint64_t key = fnv(0xcbf29ce484222325ull, tri_v.data(), tri_v.size() * sizeof(float));
+        key = fnv(key, tri_meta.data(), tri_meta.size() * 4);
+        key = fnv(key, tri_world.data(), tri_world.size() * 4);
+        if (c->d_bvh_nodes_keep && c->bvh_key == key && c->bvh_keep.n_triangles == (int64_t)tri_world.size()) {
+            c->d_bvh_nodes = c->d_bvh_nodes_keep; c->d_bvh_tris = c->d_bvh_tris_keep; c->bvh = c->bvh_keep;
+        } else {
         BvhBuildInput in{tri_v.data(), (int64_t)tri_world.size(), tri_meta.data(), tri_world.data()};
         BvhBuildOutput out;
         unsigned hw = std::thread::hardware_concurrency();
@@ -457,7 +479,13 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
         c->bvh.n_triangles = (int64_t)out.tris.size(); c->bvh.n_nodes = (int64_t)out.nodes.size();
         c->bvh.max_depth = out.max_depth; c->bvh.sah_cost = out.sah_cost; c->bvh.build_ms = out.build_ms;
         c->bvh.node_bytes = sizeof(BvhNode); c->bvh.triangle_bytes = sizeof(BvhTri);
-        if (out.max_depth > 38) return fail(c, PTB_ERR_LIMIT, "BVH depth %d exceeds the traversal stack", out.max_depth);
+        if (out.max_depth > 38) {
+            cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_tris); c->d_bvh_nodes = nullptr; c->d_bvh_tris = nullptr;
+            return fail(c, PTB_ERR_LIMIT, "BVH depth %d exceeds the traversal stack", out.max_depth);
+        }
+        cudaFree(c->d_bvh_nodes_keep); cudaFree(c->d_bvh_tris_keep);
+        c->d_bvh_nodes_keep = c->d_bvh_nodes; c->d_bvh_tris_keep = c->d_bvh_tris; c->bvh_keep = c->bvh; c->bvh_key = key;
+        }
     }
     hs.sky.kind = s->sky.kind == PTB_SKY_GRADIENT ? PTB_SKY_GRADIENT : PTB_SKY_CONST;
     for (int k = 0; k < 3; k++) { hs.sky.color[k] = (float)s->sky.color[k]; hs.sky.horizon[k] = (float)s->sky.horizon[k]; hs.sky.zenith[k] = (float)s->sky.zenith[k]; }

@@ -501,6 +501,9 @@ integrate_kernel(const __grid_constant__ FrameParams fp) {
 }  // namespace ptb
 #include "bvh.cuh"
 #include "wavefront.cuh"
+#ifdef PTB_ENABLE_WAVEQUEUE      // experimental queue-driven variant (slower than the phased kernel so far)
+#include "wavequeue.cuh"
+#endif
 namespace ptb {
 
 __global__ void finalize_kernel(const float* __restrict__ accum, int n_pix, double inv_spp, uchar4* __restrict__ rgba) {
@@ -571,6 +574,37 @@ int launch_integrator_wf(const FrameParams& fp, bool stats, int n_obj, int n_mat
     if (stats) return mesh ? launch_wf_variant<true, true>(fp, smem, sm_count, st) : launch_wf_variant<true, false>(fp, smem, sm_count, st);
     return mesh ? launch_wf_variant<false, true>(fp, smem, sm_count, st) : launch_wf_variant<false, false>(fp, smem, sm_count, st);
 }
+
+#ifdef PTB_ENABLE_WAVEQUEUE
+template <bool STATS, bool MESH>
+static int launch_wq_variant(const FrameParams& fp, size_t smem, int sm_count, cudaStream_t stream) {
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(integrate_wq_kernel<STATS, MESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        int nb = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, integrate_wq_kernel<STATS, MESH>, WQ_THREADS, smem);
+        if (e != cudaSuccess) return (int)e;
+        blocks_per_sm = nb > 0 ? nb : 1;
+    }
+    const long long n_pix = (long long)fp.width * fp.height;
+    long long grid = (long long)sm_count * blocks_per_sm;
+    const long long need = (n_pix + WQ_SLOTS - 1) / WQ_SLOTS;
+    if (grid > need) grid = need;
+    integrate_wq_kernel<STATS, MESH><<<(unsigned)grid, WQ_THREADS, smem, stream>>>(fp);
+    return (int)cudaGetLastError();
+}
+
+int launch_integrator_wq(const FrameParams& fp, bool stats, int n_obj, int n_mat, int sm_count, void* stream) {
+    const size_t smem = ((sizeof(WqState) + 15) / 16 + (size_t)(n_obj * 2 + n_mat * 3)) * sizeof(uint4);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool mesh = fp.bvh_nodes != nullptr;
+    if (stats) return mesh ? launch_wq_variant<true, true>(fp, smem, sm_count, st) : launch_wq_variant<true, false>(fp, smem, sm_count, st);
+    return mesh ? launch_wq_variant<false, true>(fp, smem, sm_count, st) : launch_wq_variant<false, false>(fp, smem, sm_count, st);
+}
+
+#else
+int launch_integrator_wq(const FrameParams&, bool, int, int, int, void*) { return (int)cudaErrorNotSupported; }
+#endif
 
 int launch_finalize(const float* accum, int width, int height, int spp_total, uint8_t* rgba, void* stream) {
     int n = width * height;

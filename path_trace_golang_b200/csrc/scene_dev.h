@@ -87,6 +87,7 @@ enum StatWord {
 int upload_scene_constants(const DevScene& host_scene, void* stream);
 int launch_integrator(const FrameParams& fp, bool stats, int n_obj, int n_mat, void* stream);
 int launch_integrator_wf(const FrameParams& fp, bool stats, int n_obj, int n_mat, int sm_count, void* stream);
+int launch_integrator_wq(const FrameParams& fp, bool stats, int n_obj, int n_mat, int sm_count, void* stream);
 int launch_finalize(const float* accum, int width, int height, int spp_total, uint8_t* rgba, void* stream);
 int launch_primary_hits(const Obj64* d_world, int n_obj, const float4* bvh_nodes, const float4* bvh_tris, const Camera64& cam,
                         int width, int height, double xi_u, double xi_v, int32_t* d_ids, double* d_t, void* stream);

@@ -42,20 +42,238 @@ constexpr int WF_CHUNKS = WF_SLOTS / 32;
 // Measured chunk costs on C3 (cycles, -DPTB_WF_TIMING): DIEL 5500, TERM 3450, REGEN 2740, DIFFUSE 2210, SPEC 1630.
 enum : int { CL_DIEL = 0, CL_TERM = 1, CL_REGEN = 2, CL_DIFFUSE = 3, CL_SPEC = 4, CL_DEAD = 5, CL_COUNT = 6 };
 
-struct WfState {                       // SoA, one entry per slot
-    float ox[WF_SLOTS], oy[WF_SLOTS], oz[WF_SLOTS];
-    float dx[WF_SLOTS], dy[WF_SLOTS], dz[WF_SLOTS];
-    float bx[WF_SLOTS], by[WF_SLOTS], bz[WF_SLOTS];     // throughput beta
-    float ax[WF_SLOTS], ay[WF_SLOTS], az[WF_SLOTS];     // pixel sum
-    float best[WF_SLOTS];
-    int bid[WF_SLOTS];
-    uint32_t key[WF_SLOTS], ctr[WF_SLOTS];
-    int depth[WF_SLOTS];               // remaining depth of the live path; 0 = no live path (needs regeneration)
-    int smp[WF_SLOTS];                 // sample index being traced
-    int pix[WF_SLOTS];                 // pixel index, -1 = slot retired
+template <int N>
+struct SlotState {                     // path state, SoA, one entry per slot
+    float ox[N], oy[N], oz[N];
+    float dx[N], dy[N], dz[N];
+    float bx[N], by[N], bz[N];         // throughput beta
+    float ax[N], ay[N], az[N];         // pixel sum
+    float best[N];
+    int bid[N];
+    uint32_t key[N], ctr[N];
+    int depth[N];                      // remaining depth of the live path; 0 = no live path (needs regeneration)
+    int smp[N];                        // sample index being traced
+    int pix[N];                        // pixel index, -1 = slot retired
+};
+struct WfState : SlotState<WF_SLOTS> {
     unsigned short perm[WF_SLOTS];     // slot | class << 12
     int cnt[CL_COUNT * WF_WARPS];
 };
+
+// Finish the slot's current sample and give it its next camera ray: next sample of the same pixel, or — when the
+// pixel is complete — write the pixel out and take the next pixel from the global counter (renderer.go:171-221).
+template <bool STATS, class SS>
+__device__ __forceinline__ void path_regen(SS& S, const FrameParams& fp, int n_pix, int j, bool sample_done, unsigned long long* st) {
+    int pix = S.pix[j];
+    int s = S.smp[j] + (sample_done ? 1 : 0);
+    if (pix < 0 || s >= fp.s_end) {
+        if (pix >= 0) {                                   // pixel complete: epilogue / accumulation buffer
+            const float sx = S.ax[j], sy = S.ay[j], sz = S.az[j];
+            if (fp.accum) { float* a = fp.accum + (size_t)pix * 3; a[0] = sx; a[1] = sy; a[2] = sz; }
+            if (fp.rgba) {
+                const double inv_spp = 1.0 / (double)fp.spp_total;
+                reinterpret_cast<uchar4*>(fp.rgba)[pix] = make_uchar4(to_u8(sx, inv_spp), to_u8(sy, inv_spp), to_u8(sz, inv_spp), 255);
+            }
+        }
+        pix = (int)atomicAdd(fp.work_counter, 1u);
+        if (pix >= n_pix) { S.pix[j] = -1; S.depth[j] = 0; return; }
+        S.pix[j] = pix;
+        s = fp.s_begin;
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+        if (fp.accum_resume) { const float* a = fp.accum + (size_t)pix * 3; a0 = a[0]; a1 = a[1]; a2 = a[2]; }
+        S.ax[j] = a0; S.ay[j] = a1; S.az[j] = a2;
+    }
+    S.smp[j] = s;
+    const int px = pix % fp.width, py = pix / fp.width;
+    Rng rng;
+    rng.key = fmix(fmix(fp.seed_key ^ (uint32_t)pix) + (uint32_t)s * kGolden);
+    rng.ctr = 0u;
+    const float u = ((float)px + rng.peek(0)) * fp.inv_w;                       // renderer.go:182
+    const float v = ((fp.h_minus_1 - (float)py) + rng.peek(1)) * fp.inv_h;      // renderer.go:174,183
+    rng.ctr = 2u;
+    const DevCamera& cam = c_scene.cam;                                         // camera.go:60-74
+    F3 dir = f3(cam.llc[0] + cam.horizontal[0] * u + cam.vertical[0] * v - cam.origin[0],
+                cam.llc[1] + cam.horizontal[1] * u + cam.vertical[1] * v - cam.origin[1],
+                cam.llc[2] + cam.horizontal[2] * u + cam.vertical[2] * v - cam.origin[2]);
+    F3 org = f3(cam.origin[0], cam.origin[1], cam.origin[2]);
+    if (cam.lens_radius > 0.0f) {
+        F3 rd = in_unit_sphere(rng);
+        float rx = rd.x * cam.lens_radius, ry = rd.y * cam.lens_radius;
+        F3 off = f3(cam.u[0] * rx + cam.v[0] * ry, cam.u[1] * rx + cam.v[1] * ry, cam.u[2] * rx + cam.v[2] * ry);
+        org = f3(org.x + off.x, org.y + off.y, org.z + off.z);
+        dir = f3(dir.x - off.x, dir.y - off.y, dir.z - off.z);
+    }
+    S.ox[j] = org.x; S.oy[j] = org.y; S.oz[j] = org.z;
+    S.dx[j] = dir.x; S.dy[j] = dir.y; S.dz[j] = dir.z;
+    S.bx[j] = 1.0f; S.by[j] = 1.0f; S.bz[j] = 1.0f;
+    S.key[j] = rng.key; S.ctr[j] = rng.ctr;
+    S.depth[j] = fp.max_depth;
+    if (STATS) st[ST_SAMPLES]++;
+}
+
+// One slot's work after a closest-hit scan, given its class c: scatter (+ exit search, Russian roulette), or add the
+// sky / emitted radiance; terminate-class and regenerate-class slots then get their next camera ray.
+template <bool STATS, bool MESH, class SS>
+__device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const DevObj* __restrict__ s_obj, const DevMat* __restrict__ s_mat,
+                                           int n_pix, int j, int c, unsigned long long* st) {
+        if (c == CL_DIEL || c == CL_DIFFUSE || c == CL_SPEC) {
+        const F3 ro = f3(S.ox[j], S.oy[j], S.oz[j]);
+        const F3 rd = f3(S.dx[j], S.dy[j], S.dz[j]);
+        const float t_hit = S.best[j];
+        const int hid = S.bid[j];
+        F3 p, n; bool front;
+        int meta;
+        if (MESH && (hid & kTriBit)) {
+            tri_surface(fp.bvh_tris, hid & ~kTriBit, ro, rd, t_hit, p, n, front, meta);
+            if (STATS) st[ST_ACC_MESH]++;
+        } else {
+            const DevObj ob = s_obj[hid];
+            meta = ob.meta;
+            if (STATS) st[ST_ACC_SPHERE + (meta & 3)]++;
+            surface(ob, meta & 3, ro, rd, t_hit, p, n, front);
+        }
+        const DevMat m = s_mat[meta >> 6];
+        Rng rng{S.key[j], S.ctr[j]};
+        int depth = S.depth[j];
+
+        uint32_t used = 0u;                               // draws consumed by this bounce (classes are warp-coherent: draw lazily)
+        const float a = rd.x * rd.x + rd.y * rd.y + rd.z * rd.z;
+        const float len = sqrt_(a);
+        const float il = rcp_(len);
+        const F3 ud = f3(rd.x * il, rd.y * il, rd.z * il);
+        const float udn = ud.x * n.x + ud.y * n.y + ud.z * n.z;
+        const F3 refl = f3(ud.x - n.x * 2.0f * udn, ud.y - n.y * 2.0f * udn, ud.z - n.z * 2.0f * udn);   // math.go:39-46
+
+        F3 att = f3(m.albedo[0], m.albedo[1], m.albedo[2]), sd = refl, so = p;
+        bool ok = true;
+        if (m.type != PTB_MAT_LAMBERT && len == 0.0f) {   // materials.go:103-105, 178-180, 208-210
+            ok = false;
+            if (STATS) st[ST_END_NOSCATTER]++;
+        } else if (c == CL_DIFFUSE) {                     // lambert (materials.go:76-97) / rough metal (:114-147)
+            const F3 cd = cosine_direction(m.type == PTB_MAT_LAMBERT ? n : refl, rng.peek(0), rng.peek(1));
+            used = 2u;
+            if (m.type == PTB_MAT_LAMBERT) {
+                sd = cd;
+                if (m.rough > 1e-6f) {                    // rejection loop: consumes its draws itself (rare path)
+                    rng.ctr += 2u;
+                    F3 off = in_unit_sphere(rng);
+                    used = 0u;
+                    sd.x += off.x * m.rough * 0.1f; sd.y += off.y * m.rough * 0.1f; sd.z += off.z * m.rough * 0.1f;
+                    sd = unit3(sd);
+                }
+            } else {
+                const float alpha = m.rough * m.rough;
+                float sx = refl.x * (1.0f - alpha) + cd.x * alpha;
+                float sy = refl.y * (1.0f - alpha) + cd.y * alpha;
+                float sz = refl.z * (1.0f - alpha) + cd.z * alpha;
+                const float l2 = sx * sx + sy * sy + sz * sz;
+                if (l2 < 1e-8f) { sx = refl.x; sy = refl.y; sz = refl.z; }
+                else { const float i2 = rcp_(sqrt_(l2)); sx *= i2; sy *= i2; sz *= i2; }
+                if (sx * n.x + sy * n.y + sz * n.z <= 0.0f) { sx = refl.x; sy = refl.y; sz = refl.z; }
+                sd = f3(sx, sy, sz);
+            }
+        } else if (c == CL_DIEL) {                        // materials.go:162-200
+            att = f3(1.0f, 1.0f, 1.0f);
+            const float ratio = front ? rcp_(m.ior) : m.ior;
+            const float cos_t = fminf(-udn, 1.0f);
+            const float sin_t = sqrt_(1.0f - cos_t * cos_t);
+            const bool cannot = ratio * sin_t > 1.0f;
+            float r0 = (1.0f - ratio) * rcp_(1.0f + ratio);
+            r0 = r0 * r0;
+            const float om = 1.0f - cos_t;
+            const float om2 = om * om;
+            const float refl_prob = r0 + (1.0f - r0) * (om2 * om2 * om);   // Schlick, materials.go:226-231
+            bool reflect = cannot;
+            if (!cannot) { reflect = refl_prob > rng.peek(0); used = 1u; }  // `||` short-circuit: no draw when cannot
+            if (!reflect) {                               // refractVec, math.go:48-64
+                const float c2 = fminf(-ud.x * n.x - ud.y * n.y - ud.z * n.z, 1.0f);
+                float qx = (ud.x + n.x * c2) * ratio, qy = (ud.y + n.y * c2) * ratio, qz = (ud.z + n.z * c2) * ratio;
+                const float par = -sqrt_(fabsf(1.0f - (qx * qx + qy * qy + qz * qz)));
+                sd = f3(qx + n.x * par, qy + n.y * par, qz + n.z * par);
+            }
+            if (front) {                                  // exit search, renderer.go:316-371
+                if (STATS) st[ST_EXIT_SCANS]++;
+                const RayK er = make_ray(p, sd);
+                float exit_t = FLT_MAX;
+                bool hit_exit = false;
+                F3 ep = p;
+                const int n_diel = c_scene.n_diel;
+                for (int k = 0; k < n_diel; ++k) {        // only dielectric objects can be accepted (:335)
+                    const int ei = c_scene.diel_idx[k];
+                    const DevObj& eo = c_scene.obj[ei];
+                    const int et = eo.meta & 3;
+                    float t;
+                    if (!hit_any(obj_lo(ei), obj_hi(ei), et, er, 0.0001f, exit_t, t)) continue;
+                    F3 q, qn; bool qf;
+                    surface(eo, et, p, sd, t, q, qn, qf);
+                    if (!qf && t < exit_t) {
+                        float ex = q.x - p.x, ey = q.y - p.y, ez = q.z - p.z;
+                        float d2 = ex * ex + ey * ey + ez * ez;
+                        if (d2 > 1e-8f && d2 < 1000.0f) { hit_exit = true; exit_t = t; ep = q; }
+                    }
+                }
+                if (hit_exit) {                           // renderer.go:352-369
+                    float ex = ep.x - p.x, ey = ep.y - p.y, ez = ep.z - p.z;
+                    float dist = sqrt_(ex * ex + ey * ey + ez * ez);
+                    if (m.absorption[0] > 0.0f || m.absorption[1] > 0.0f || m.absorption[2] > 0.0f) {
+                        att = f3(exp_(-m.absorption[0] * dist), exp_(-m.absorption[1] * dist), exp_(-m.absorption[2] * dist));
+                    }
+                    so = ep;
+                }
+            }
+        }
+        // (CL_SPEC — mirror and smooth metal: sd = refl, att = albedo, the defaults; materials.go:148-158, 205-221)
+
+        bool done = !ok;
+        if (ok) {
+            if (STATS) st[ST_SCATTERS]++;
+            if (depth <= 3) {                             // Russian roulette, renderer.go:374-393
+                const float mx = fmaxf(att.x, fmaxf(att.y, att.z));
+                if (mx < 1e-6f) {
+                    done = true;
+                } else {
+                    const float pr = fminf(mx, 0.95f);
+                    const float ur = rng.peek(used);
+                    used += 1u;
+                    if (ur > pr) done = true;
+                    else { const float ip = rcp_(pr); att.x *= ip; att.y *= ip; att.z *= ip; }
+                }
+                if (STATS && done) st[ST_END_RR]++;
+            }
+            rng.ctr += used;
+            if (!done) {                                  // renderer.go:398-403
+                if (--depth <= 0) {                       // renderer.go:287-289
+                    done = true;
+                    if (STATS) st[ST_END_DEPTH]++;
+                }
+            }
+        }
+        if (done) {
+            S.depth[j] = 0;                               // regenerated next iteration, together with the other finished slots
+        } else {
+            S.bx[j] *= att.x; S.by[j] *= att.y; S.bz[j] *= att.z;
+            S.ox[j] = so.x; S.oy[j] = so.y; S.oz[j] = so.z;
+            S.dx[j] = sd.x; S.dy[j] = sd.y; S.dz[j] = sd.z;
+            S.ctr[j] = rng.ctr;
+            S.depth[j] = depth;
+        }
+    } else if (c == CL_TERM) {                            // sky (renderer.go:304-306) or emissive hit (:308-312)
+        F3 e;
+        const int hb = S.bid[j];
+        if (hb < 0) {
+            e = sky_color(f3(S.dx[j], S.dy[j], S.dz[j]));
+            if (STATS) st[ST_END_SKY]++;
+        } else {
+            const bool is_tri = MESH && (hb & kTriBit) != 0;
+            const int meta = is_tri ? __float_as_int(__ldg(fp.bvh_tris + 3 * (hb & ~kTriBit) + 1).w) : s_obj[hb].meta;
+            const DevMat& m = s_mat[meta >> 6];
+            e = f3(m.emit[0], m.emit[1], m.emit[2]);
+            if (STATS) { st[ST_END_EMISSIVE]++; st[is_tri ? ST_ACC_MESH : ST_ACC_SPHERE + (meta & 3)]++; }
+        }
+        S.ax[j] += S.bx[j] * e.x; S.ay[j] += S.by[j] * e.y; S.az[j] += S.bz[j] * e.z;
+    }
+    if (c == CL_TERM || c == CL_REGEN) path_regen<STATS>(S, fp, n_pix, j, true, st);
+}
 
 template <bool STATS, bool MESH>
 __global__ void __launch_bounds__(WF_THREADS, PTB_WF_MIN_BLOCKS)
@@ -76,62 +294,12 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
     const int n_box = c_scene.n_box;
     unsigned long long st[STATS ? kStatsWords : 1] = {0};
 
-    // Finish the slot's current sample and give it its next camera ray: next sample of the same pixel, or — when the
-    // pixel is complete — write the pixel out and take the next pixel from the global counter (renderer.go:171-221).
-    auto regen = [&](int j, bool sample_done) {
-        int pix = S.pix[j];
-        int s = S.smp[j] + (sample_done ? 1 : 0);
-        if (pix < 0 || s >= fp.s_end) {
-            if (pix >= 0) {                                   // pixel complete: epilogue / accumulation buffer
-                const float sx = S.ax[j], sy = S.ay[j], sz = S.az[j];
-                if (fp.accum) { float* a = fp.accum + (size_t)pix * 3; a[0] = sx; a[1] = sy; a[2] = sz; }
-                if (fp.rgba) {
-                    const double inv_spp = 1.0 / (double)fp.spp_total;
-                    reinterpret_cast<uchar4*>(fp.rgba)[pix] = make_uchar4(to_u8(sx, inv_spp), to_u8(sy, inv_spp), to_u8(sz, inv_spp), 255);
-                }
-            }
-            pix = (int)atomicAdd(fp.work_counter, 1u);
-            if (pix >= n_pix) { S.pix[j] = -1; S.depth[j] = 0; return; }
-            S.pix[j] = pix;
-            s = fp.s_begin;
-            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
-            if (fp.accum_resume) { const float* a = fp.accum + (size_t)pix * 3; a0 = a[0]; a1 = a[1]; a2 = a[2]; }
-            S.ax[j] = a0; S.ay[j] = a1; S.az[j] = a2;
-        }
-        S.smp[j] = s;
-        const int px = pix % fp.width, py = pix / fp.width;
-        Rng rng;
-        rng.key = fmix(fmix(fp.seed_key ^ (uint32_t)pix) + (uint32_t)s * kGolden);
-        rng.ctr = 0u;
-        const float u = ((float)px + rng.peek(0)) * fp.inv_w;                       // renderer.go:182
-        const float v = ((fp.h_minus_1 - (float)py) + rng.peek(1)) * fp.inv_h;      // renderer.go:174,183
-        rng.ctr = 2u;
-        const DevCamera& cam = c_scene.cam;                                         // camera.go:60-74
-        F3 dir = f3(cam.llc[0] + cam.horizontal[0] * u + cam.vertical[0] * v - cam.origin[0],
-                    cam.llc[1] + cam.horizontal[1] * u + cam.vertical[1] * v - cam.origin[1],
-                    cam.llc[2] + cam.horizontal[2] * u + cam.vertical[2] * v - cam.origin[2]);
-        F3 org = f3(cam.origin[0], cam.origin[1], cam.origin[2]);
-        if (cam.lens_radius > 0.0f) {
-            F3 rd = in_unit_sphere(rng);
-            float rx = rd.x * cam.lens_radius, ry = rd.y * cam.lens_radius;
-            F3 off = f3(cam.u[0] * rx + cam.v[0] * ry, cam.u[1] * rx + cam.v[1] * ry, cam.u[2] * rx + cam.v[2] * ry);
-            org = f3(org.x + off.x, org.y + off.y, org.z + off.z);
-            dir = f3(dir.x - off.x, dir.y - off.y, dir.z - off.z);
-        }
-        S.ox[j] = org.x; S.oy[j] = org.y; S.oz[j] = org.z;
-        S.dx[j] = dir.x; S.dy[j] = dir.y; S.dz[j] = dir.z;
-        S.bx[j] = 1.0f; S.by[j] = 1.0f; S.bz[j] = 1.0f;
-        S.key[j] = rng.key; S.ctr[j] = rng.ctr;
-        S.depth[j] = fp.max_depth;
-        if (STATS) st[ST_SAMPLES]++;
-    };
-
 #pragma unroll
     for (int k = 0; k < WF_SPT; ++k) {
         const int j = tid + k * WF_THREADS;
         S.pix[j] = -1; S.smp[j] = 0; S.depth[j] = 0;
         S.ox[j] = 0.f; S.oy[j] = 0.f; S.oz[j] = 0.f; S.dx[j] = 0.f; S.dy[j] = 0.f; S.dz[j] = 1.f;
-        if (fp.max_depth > 0) regen(j, false);
+        if (fp.max_depth > 0) path_regen<STATS>(S, fp, n_pix, j, false, st);
     }
     __syncthreads();
 
@@ -277,163 +445,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
         const long long tc0 = clock64();
         const int c_lane0 = __shfl_sync(0xffffffffu, c, 0), c_lane31 = __shfl_sync(0xffffffffu, c, 31);
 #endif
-        if (c == CL_DIEL || c == CL_DIFFUSE || c == CL_SPEC) {
-            const F3 ro = f3(S.ox[j], S.oy[j], S.oz[j]);
-            const F3 rd = f3(S.dx[j], S.dy[j], S.dz[j]);
-            const float t_hit = S.best[j];
-            const int hid = S.bid[j];
-            F3 p, n; bool front;
-            int meta;
-            if (MESH && (hid & kTriBit)) {
-                tri_surface(fp.bvh_tris, hid & ~kTriBit, ro, rd, t_hit, p, n, front, meta);
-                if (STATS) st[ST_ACC_MESH]++;
-            } else {
-                const DevObj ob = s_obj[hid];
-                meta = ob.meta;
-                if (STATS) st[ST_ACC_SPHERE + (meta & 3)]++;
-                surface(ob, meta & 3, ro, rd, t_hit, p, n, front);
-            }
-            const DevMat m = s_mat[meta >> 6];
-            Rng rng{S.key[j], S.ctr[j]};
-            int depth = S.depth[j];
-
-            uint32_t used = 0u;                               // draws consumed by this bounce (classes are warp-coherent: draw lazily)
-            const float a = rd.x * rd.x + rd.y * rd.y + rd.z * rd.z;
-            const float len = sqrt_(a);
-            const float il = rcp_(len);
-            const F3 ud = f3(rd.x * il, rd.y * il, rd.z * il);
-            const float udn = ud.x * n.x + ud.y * n.y + ud.z * n.z;
-            const F3 refl = f3(ud.x - n.x * 2.0f * udn, ud.y - n.y * 2.0f * udn, ud.z - n.z * 2.0f * udn);   // math.go:39-46
-
-            F3 att = f3(m.albedo[0], m.albedo[1], m.albedo[2]), sd = refl, so = p;
-            bool ok = true;
-            if (m.type != PTB_MAT_LAMBERT && len == 0.0f) {   // materials.go:103-105, 178-180, 208-210
-                ok = false;
-                if (STATS) st[ST_END_NOSCATTER]++;
-            } else if (c == CL_DIFFUSE) {                     // lambert (materials.go:76-97) / rough metal (:114-147)
-                const F3 cd = cosine_direction(m.type == PTB_MAT_LAMBERT ? n : refl, rng.peek(0), rng.peek(1));
-                used = 2u;
-                if (m.type == PTB_MAT_LAMBERT) {
-                    sd = cd;
-                    if (m.rough > 1e-6f) {                    // rejection loop: consumes its draws itself (rare path)
-                        rng.ctr += 2u;
-                        F3 off = in_unit_sphere(rng);
-                        used = 0u;
-                        sd.x += off.x * m.rough * 0.1f; sd.y += off.y * m.rough * 0.1f; sd.z += off.z * m.rough * 0.1f;
-                        sd = unit3(sd);
-                    }
-                } else {
-                    const float alpha = m.rough * m.rough;
-                    float sx = refl.x * (1.0f - alpha) + cd.x * alpha;
-                    float sy = refl.y * (1.0f - alpha) + cd.y * alpha;
-                    float sz = refl.z * (1.0f - alpha) + cd.z * alpha;
-                    const float l2 = sx * sx + sy * sy + sz * sz;
-                    if (l2 < 1e-8f) { sx = refl.x; sy = refl.y; sz = refl.z; }
-                    else { const float i2 = rcp_(sqrt_(l2)); sx *= i2; sy *= i2; sz *= i2; }
-                    if (sx * n.x + sy * n.y + sz * n.z <= 0.0f) { sx = refl.x; sy = refl.y; sz = refl.z; }
-                    sd = f3(sx, sy, sz);
-                }
-            } else if (c == CL_DIEL) {                        // materials.go:162-200
-                att = f3(1.0f, 1.0f, 1.0f);
-                const float ratio = front ? rcp_(m.ior) : m.ior;
-                const float cos_t = fminf(-udn, 1.0f);
-                const float sin_t = sqrt_(1.0f - cos_t * cos_t);
-                const bool cannot = ratio * sin_t > 1.0f;
-                float r0 = (1.0f - ratio) * rcp_(1.0f + ratio);
-                r0 = r0 * r0;
-                const float om = 1.0f - cos_t;
-                const float om2 = om * om;
-                const float refl_prob = r0 + (1.0f - r0) * (om2 * om2 * om);   // Schlick, materials.go:226-231
-                bool reflect = cannot;
-                if (!cannot) { reflect = refl_prob > rng.peek(0); used = 1u; }  // `||` short-circuit: no draw when cannot
-                if (!reflect) {                               // refractVec, math.go:48-64
-                    const float c2 = fminf(-ud.x * n.x - ud.y * n.y - ud.z * n.z, 1.0f);
-                    float qx = (ud.x + n.x * c2) * ratio, qy = (ud.y + n.y * c2) * ratio, qz = (ud.z + n.z * c2) * ratio;
-                    const float par = -sqrt_(fabsf(1.0f - (qx * qx + qy * qy + qz * qz)));
-                    sd = f3(qx + n.x * par, qy + n.y * par, qz + n.z * par);
-                }
-                if (front) {                                  // exit search, renderer.go:316-371
-                    if (STATS) st[ST_EXIT_SCANS]++;
-                    const RayK er = make_ray(p, sd);
-                    float exit_t = FLT_MAX;
-                    bool hit_exit = false;
-                    F3 ep = p;
-                    const int n_diel = c_scene.n_diel;
-                    for (int k = 0; k < n_diel; ++k) {        // only dielectric objects can be accepted (:335)
-                        const int ei = c_scene.diel_idx[k];
-                        const DevObj& eo = c_scene.obj[ei];
-                        const int et = eo.meta & 3;
-                        float t;
-                        if (!hit_any(obj_lo(ei), obj_hi(ei), et, er, 0.0001f, exit_t, t)) continue;
-                        F3 q, qn; bool qf;
-                        surface(eo, et, p, sd, t, q, qn, qf);
-                        if (!qf && t < exit_t) {
-                            float ex = q.x - p.x, ey = q.y - p.y, ez = q.z - p.z;
-                            float d2 = ex * ex + ey * ey + ez * ez;
-                            if (d2 > 1e-8f && d2 < 1000.0f) { hit_exit = true; exit_t = t; ep = q; }
-                        }
-                    }
-                    if (hit_exit) {                           // renderer.go:352-369
-                        float ex = ep.x - p.x, ey = ep.y - p.y, ez = ep.z - p.z;
-                        float dist = sqrt_(ex * ex + ey * ey + ez * ez);
-                        if (m.absorption[0] > 0.0f || m.absorption[1] > 0.0f || m.absorption[2] > 0.0f) {
-                            att = f3(exp_(-m.absorption[0] * dist), exp_(-m.absorption[1] * dist), exp_(-m.absorption[2] * dist));
-                        }
-                        so = ep;
-                    }
-                }
-            }
-            // (CL_SPEC — mirror and smooth metal: sd = refl, att = albedo, the defaults; materials.go:148-158, 205-221)
-
-            bool done = !ok;
-            if (ok) {
-                if (STATS) st[ST_SCATTERS]++;
-                if (depth <= 3) {                             // Russian roulette, renderer.go:374-393
-                    const float mx = fmaxf(att.x, fmaxf(att.y, att.z));
-                    if (mx < 1e-6f) {
-                        done = true;
-                    } else {
-                        const float pr = fminf(mx, 0.95f);
-                        const float ur = rng.peek(used);
-                        used += 1u;
-                        if (ur > pr) done = true;
-                        else { const float ip = rcp_(pr); att.x *= ip; att.y *= ip; att.z *= ip; }
-                    }
-                    if (STATS && done) st[ST_END_RR]++;
-                }
-                rng.ctr += used;
-                if (!done) {                                  // renderer.go:398-403
-                    if (--depth <= 0) {                       // renderer.go:287-289
-                        done = true;
-                        if (STATS) st[ST_END_DEPTH]++;
-                    }
-                }
-            }
-            if (done) {
-                S.depth[j] = 0;                               // regenerated next iteration, together with the other finished slots
-            } else {
-                S.bx[j] *= att.x; S.by[j] *= att.y; S.bz[j] *= att.z;
-                S.ox[j] = so.x; S.oy[j] = so.y; S.oz[j] = so.z;
-                S.dx[j] = sd.x; S.dy[j] = sd.y; S.dz[j] = sd.z;
-                S.ctr[j] = rng.ctr;
-                S.depth[j] = depth;
-            }
-        } else if (c == CL_TERM) {                            // sky (renderer.go:304-306) or emissive hit (:308-312)
-            F3 e;
-            const int hb = S.bid[j];
-            if (hb < 0) {
-                e = sky_color(f3(S.dx[j], S.dy[j], S.dz[j]));
-                if (STATS) st[ST_END_SKY]++;
-            } else {
-                const bool is_tri = MESH && (hb & kTriBit) != 0;
-                const int meta = is_tri ? __float_as_int(__ldg(fp.bvh_tris + 3 * (hb & ~kTriBit) + 1).w) : s_obj[hb].meta;
-                const DevMat& m = s_mat[meta >> 6];
-                e = f3(m.emit[0], m.emit[1], m.emit[2]);
-                if (STATS) { st[ST_END_EMISSIVE]++; st[is_tri ? ST_ACC_MESH : ST_ACC_SPHERE + (meta & 3)]++; }
-            }
-            S.ax[j] += S.bx[j] * e.x; S.ay[j] += S.by[j] * e.y; S.az[j] += S.bz[j] * e.z;
-        }
-        if (c == CL_TERM || c == CL_REGEN) regen(j, true);
+        path_shade<STATS, MESH>(S, fp, s_obj, s_mat, n_pix, j, c, st);
 #ifdef PTB_WF_TIMING
         if (lane == 0 && fp.stats && c_lane0 == c_lane31) {      // homogeneous chunks only
             atomicAdd(fp.stats + kStatsWords + 8 + 2 * c_lane0, (unsigned long long)(clock64() - tc0));

@@ -89,8 +89,12 @@ class Context:
         return out
 
     @staticmethod
-    def cfg(width, height, spp, max_depth, seed=1, sample_begin=0, sample_count=0, stats=False, megakernel=False) -> PtbCfg:
-        flags = (PTB_FLAG_STATS if stats else 0) | (PTB_FLAG_MEGAKERNEL if megakernel else 0)
+    def cfg(width, height, spp, max_depth, seed=1, sample_begin=0, sample_count=0, stats=False, megakernel=False,
+            wavequeue=None) -> PtbCfg:
+        import os
+        if wavequeue is None:
+            wavequeue = bool(os.environ.get("PTB_WAVEQUEUE"))
+        flags = (PTB_FLAG_STATS if stats else 0) | (PTB_FLAG_MEGAKERNEL if megakernel else 0) | (4 if wavequeue and not megakernel else 0)
         return PtbCfg(int(width), int(height), int(spp), int(max_depth), int(seed) & 0xFFFFFFFF, int(sample_begin),
                       int(sample_count), flags)
 

@@ -2,6 +2,6 @@
 # On the GPU box: time every build/variants/*.so on a few workloads.
 for so in build/variants/*.so; do
   echo "== $(basename $so .so)"
-  PTB200_LIB=$PWD/$so python tools/profile_kernel.py C3 64 3 | tail -1
-  PTB200_LIB=$PWD/$so python tools/profile_kernel.py C2 64 3 | tail -1
+  PTB200_LIB=$PWD/$so timeout 60 python tools/profile_kernel.py C3 64 3 | tail -1
+  PTB200_LIB=$PWD/$so timeout 60 python tools/profile_kernel.py C2 64 3 | tail -1
 done
