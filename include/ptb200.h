@@ -17,6 +17,9 @@
  * an internal mutex); any OS thread may call (cudaSetDevice is done per call), which is what
  * a goroutine-per-render caller such as internal/ui/app.go:135 needs.
  * Ownership: the library never keeps a host pointer after a call returns.
+ * One device, one frame at a time: the scene of the frame being rendered lives in the device's constant bank, so
+ * renders issued through DIFFERENT contexts (or streams) of the SAME device must be ordered by the caller; the
+ * host-buffer calls (ptb_render, ptb_render_accum, ptb_primary_hits) synchronise before they return.
  */
 #ifndef PTB200_H
 #define PTB200_H

@@ -215,6 +215,25 @@ __device__ __forceinline__ void surface(const DevObj& ob, int type, F3 o, F3 d, 
     n = front ? on : f3(-on.x, -on.y, -on.z);
 }
 
+// frontFace (and the hit point) of object `ob` at parameter t WITHOUT building the normal — all the dielectric exit
+// search needs (renderer.go:335: it only keeps back-face hits).  Same decisions as surface(): the sphere's outward
+// normal is (p - c) / r with r > 0, so its sign test can skip the scaling.
+__device__ __forceinline__ bool front_face_only(const DevObj& ob, int type, F3 o, F3 d, float t, F3& p) {
+    p = f3(o.x + d.x * t, o.y + d.y * t, o.z + d.z * t);
+    if (type == PTB_OBJ_SPHERE) return d.x * (p.x - ob.ax) + d.y * (p.y - ob.ay) + d.z * (p.z - ob.az) < 0.0f;
+    if (type == PTB_OBJ_PLANE) return d.y < 0.0f;
+    // box: nearest face in the reference's order -x,+x,-y,+y,-z,+z with strict '<' (objects.go:188-217); the face
+    // normal is +-e_axis, so d.n = +-d[axis]
+    float md = p.x - ob.ax, dn = -d.x;
+    float q;
+    q = ob.bx - p.x; if (q < md) { md = q; dn = d.x; }
+    q = p.y - ob.ay; if (q < md) { md = q; dn = -d.y; }
+    q = ob.by - p.y; if (q < md) { md = q; dn = d.y; }
+    q = p.z - ob.az; if (q < md) { md = q; dn = -d.z; }
+    q = ob.bz - p.z; if (q < md) { dn = d.z; }
+    return dn < 0.0f;
+}
+
 __device__ __forceinline__ F3 sky_color(F3 d) {                                                   // renderer.go:56-92
     if (c_scene.sky.kind == PTB_SKY_GRADIENT) {
         float len = sqrt_(d.x * d.x + d.y * d.y + d.z * d.z);
@@ -420,8 +439,8 @@ integrate_kernel(const __grid_constant__ FrameParams fp) {
                             const int et = eo.meta & 3;
                             float t;
                             if (!hit_any(obj_lo(ei), obj_hi(ei), et, er, 0.0001f, exit_t, t)) continue;
-                            F3 q, qn; bool qf;
-                            surface(eo, et, p, sd, t, q, qn, qf);
+                            F3 q;
+                            const bool qf = front_face_only(eo, et, p, sd, t, q);
                             if (!qf && t < exit_t) {
                                 float ex = q.x - p.x, ey = q.y - p.y, ez = q.z - p.z;
                                 float d2 = ex * ex + ey * ey + ez * ez;

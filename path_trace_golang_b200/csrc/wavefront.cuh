@@ -2,13 +2,15 @@
 //
 // Why: in the pixel-per-lane megakernel (integrate_kernel) every lane of a warp executes the same closest-hit scan,
 // but after it the lanes want different code (sky / emissive / lambert / mirror / glass + exit search / new
-// camera ray), and ncu shows that part running with ~8 of 32 lanes active (profiles/r01_*).  Here the path state
-// lives in shared memory and, after every scan, the CTA's 256 path slots are counting-sorted by the class of
-// work they need, so that a warp shades 32 slots of the SAME class:
+// camera ray), and ncu shows that part running with ~8 of 32 lanes active (profiles/r01b_*).  Here the path state
+// lives in shared memory (WF_SLOTS = 512 slots per 256-thread CTA) and, after every scan, the CTA's slots are
+// counting-sorted by the class of work they need, so that a warp shades 32 slots of the SAME class:
 //
-//   loop:  SCAN   thread i <-> slot i      closest hit over the world (warp-uniform, constant-bank operands)
-//          SORT   ballot/popc per class -> per-warp counts -> exclusive scan -> stable permutation (2 barriers)
-//          SHADE  thread i <-> slot perm[i]  scatter / terminate / regenerate, one class per warp (mostly)
+//   loop:  SCAN   thread i <-> slots i, i+256   closest hit over the world, two rays per object record
+//                                               (warp-uniform loop, operands from the constant bank via LDCU)
+//          SORT   ballot/popc per class -> per-warp counts -> shuffle prefix scan -> stable permutation (2 barriers)
+//          SHADE  warp w <-> 32-slot chunks w and 15-w of perm[]   scatter / terminate / regenerate, one class per
+//                                               chunk; perm[] is sorted heaviest class first (serpentine pairing)
 //
 // A slot is bound to one pixel at a time and walks that pixel's samples in order with its fp32 sum in shared
 // memory (deterministic per-pixel sum order, no atomics on radiance); when the pixel is done the slot writes it
@@ -16,6 +18,8 @@
 // cheap sky pixels and expensive glass pixels balance across the whole chip.
 //
 // Semantics are those of integrate_kernel (same helpers, same counter-RNG draw order), hence of the reference.
+// MESH = true adds the BVH traversal of bvh.cuh to the scan (separate instantiation: the traversal code costs the
+// mesh-free path 10 % if it is merely present).
 #pragma once
 
 namespace ptb {
@@ -204,8 +208,8 @@ __device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const D
                     const int et = eo.meta & 3;
                     float t;
                     if (!hit_any(obj_lo(ei), obj_hi(ei), et, er, 0.0001f, exit_t, t)) continue;
-                    F3 q, qn; bool qf;
-                    surface(eo, et, p, sd, t, q, qn, qf);
+                    F3 q;
+                    const bool qf = front_face_only(eo, et, p, sd, t, q);
                     if (!qf && t < exit_t) {
                         float ex = q.x - p.x, ey = q.y - p.y, ez = q.z - p.z;
                         float d2 = ex * ex + ey * ey + ez * ez;

@@ -169,3 +169,23 @@ def test_gpu_c4_million_triangles(ctx, oracle_mod):
     tris_per_ray = st["bvh_tris_tested"] / st["segments"]
     print(f"C4: {st['last_render_ms']:.1f} ms (stats variant), {nodes_per_ray:.1f} nodes/ray, {tris_per_ray:.1f} tris/ray, mesh hits {st['accepts_mesh'] / st['segments']:.3f}")
     assert 1 < nodes_per_ray < 200 and tris_per_ray < 50
+
+
+@pytest.mark.gpu
+def test_gpu_bvh_is_reused_for_identical_meshes(ctx):
+    """RenderInto hands the scene over on every call (renderer.go:34): uploading the same triangles again must not
+    rebuild the BVH (same build_ms = the kept build), a different mesh must, and results are unchanged."""
+    from path_trace_golang_b200 import scene
+    doc = with_heightfield("example_simple", 64, 48)
+    sc = scene.Parse(json.dumps(doc))
+    ctx.upload(sc)
+    first = ctx.bvh_info()
+    a = ctx.render_accum(ctx.cfg(160, 90, 2, 8, seed=1))
+    ctx.upload(scene.Parse(json.dumps(doc)))                       # a fresh Scene object with identical content
+    second = ctx.bvh_info()
+    assert second == first                                          # build_ms identical: nothing was rebuilt
+    assert np.array_equal(a, ctx.render_accum(ctx.cfg(160, 90, 2, 8, seed=1)))
+    ctx.upload(scene.Parse(json.dumps(with_heightfield("example_simple", 64, 48, seed=8))))
+    assert ctx.bvh_info()["build_ms"] != first["build_ms"] and ctx.bvh_info()["n_triangles"] == first["n_triangles"]
+    ctx.upload(scene.Parse(json.dumps(scene_json("example_simple"))))
+    assert ctx.bvh_info()["n_triangles"] == 0
