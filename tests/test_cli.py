@@ -42,3 +42,31 @@ def test_headless_render_writes_png(tmp_path):
     assert rc == 0
     img = np.array(Image.open(out))
     assert img.shape == (90, 160, 4) and (img[..., 3] == 255).all() and img[..., :3].std() > 5
+
+
+def test_cpp_driver_flags_and_errors():
+    """ptb_render = cmd/render in C++ over the host mirror: Go-style flags, loud failure (exit 1) without a GPU or scene."""
+    import subprocess
+    exe = ROOT / "path_trace_golang_b200" / "ptb_render"
+    assert exe.exists(), "build with __graft_entry__.build()"
+    r = subprocess.run([str(exe), "-bogus"], capture_output=True, text=True)
+    assert r.returncode == 2 and "flag provided but not defined: -bogus" in r.stderr
+    r = subprocess.run([str(exe), "-scene", "/nonexistent.json", "-headless"], capture_output=True, text=True)
+    assert r.returncode == 1 and "open scene" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_driver_renders_png(tmp_path):
+    import subprocess
+    from PIL import Image
+    exe = ROOT / "path_trace_golang_b200" / "ptb_render"
+    out = tmp_path / "c.png"
+    r = subprocess.run([str(exe), "-headless", "-scene", str(scene_path("metal_glass_room")), "-width=192", "-height", "108", "-spp", "8",
+                        "-depth", "16", "-seed", "3", "-out", str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    img = np.array(Image.open(out))
+    assert img.shape == (108, 192, 4) and (img[..., 3] == 255).all() and img[..., :3].std() > 3
+    # same seed through the Python veneer gives the same bytes (both go through engine.RenderInto of the C++ host mirror)
+    from path_trace_golang_b200 import engine, scene
+    ref = engine.Render(scene.Load(scene_path("metal_glass_room")), engine.RenderConfig(192, 108, 8, 16), seed=3)
+    assert (img == ref).all()
