@@ -52,3 +52,31 @@ def test_product_does_not_import_oracle():
         text = p.read_text().lower()
         for needle in ("import oracle", "from oracle", "liboracle", "oracle/", "pyoracle"):
             assert needle not in text, (p, needle)
+
+
+def test_headers_are_plain_c():
+    """include/*.h must be consumable by cgo: they compile as C11 (no C++ in the signatures)."""
+    import subprocess
+    for h in sorted((ROOT / "include").glob("*.h")):
+        r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", str(h)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+def test_bench_reference_arm_schema():
+    """bench.py --impl reference (the CPU arm the driver runs first): one JSON line with the contract's keys; only rank 0 prints."""
+    import json
+    import os
+    import subprocess
+    import sys
+    cmd = [sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", "C1", "--steps", "1", "--warmup", "0", "--cpu-spp", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ["impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "cpu_baseline", "e2e"]:
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "Msamples/s" and line["value"] > 0 and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "workload" in line["config"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
+    assert r.returncode == 0 and r.stdout.strip() == ""
