@@ -66,88 +66,6 @@ __device__ __forceinline__ void bvh_closest(const float4* __restrict__ nodes, co
     }
 }
 
-// BVH phase of the wavefront kernel: the CTA's slots hold the analytic closest hit (S.best / S.bid); every warp
-// traverses rays it FETCHES from a shared counter (persistent "while-while" with dynamic fetch, Aila & Laine): a lane
-// whose ray is finished picks up the next slot as soon as fewer than kRefill lanes of its warp are still traversing,
-// so short rays (most miss the mesh's box after one node) do not leave the warp idle behind a long one.
-template <bool STATS, class SS>
-__device__ __forceinline__ void bvh_phase_dynamic(SS& S, int n_slots, int* next_ray, const float4* __restrict__ nodes,
-                                                  const float4* __restrict__ tris, unsigned long long* st) {
-    constexpr int kRefill = 20;
-    int stack[40];
-    int sp = 0, cur = 0, best_tri = -1, j = -1, bid = -1;
-    float best = 0.0f;
-    RayK r = make_ray(f3(0.f, 0.f, 0.f), f3(0.f, 0.f, 1.f));
-    bool exhausted = false;
-    for (;;) {
-        if (j < 0 && !exhausted) {                    // fetch the next slot that carries a live ray
-            for (;;) {
-                const int k = atomicAdd(next_ray, 1);
-                if (k >= n_slots) { exhausted = true; break; }
-                if (S.pix[k] >= 0 && S.depth[k] > 0) { j = k; break; }
-            }
-            if (j >= 0) {
-                r = make_ray(f3(S.ox[j], S.oy[j], S.oz[j]), f3(S.dx[j], S.dy[j], S.dz[j]));
-                best = S.best[j]; bid = S.bid[j];
-                best_tri = -1; sp = 0; cur = 0;
-            }
-        }
-        if (__ballot_sync(0xffffffffu, j >= 0) == 0u) break;      // no lane has a ray and the counter is exhausted
-        while (j >= 0) {
-            if (cur >= 0) {
-                const float4 q0 = __ldg(nodes + 4 * cur), q1 = __ldg(nodes + 4 * cur + 1), q2 = __ldg(nodes + 4 * cur + 2),
-                             q3 = __ldg(nodes + 4 * cur + 3);
-                if (STATS) st[ST_BVH_NODES]++;
-                float ax = fmaf(q0.x, r.inv.x, -r.oi.x), bx = fmaf(q0.w, r.inv.x, -r.oi.x);
-                float ay = fmaf(q0.y, r.inv.y, -r.oi.y), by = fmaf(q1.x, r.inv.y, -r.oi.y);
-                float az = fmaf(q0.z, r.inv.z, -r.oi.z), bz = fmaf(q1.y, r.inv.z, -r.oi.z);
-                const float n0 = fmaxf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)), 0.001f);
-                const float f0 = fminf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), best);
-                ax = fmaf(q1.z, r.inv.x, -r.oi.x); bx = fmaf(q2.y, r.inv.x, -r.oi.x);
-                ay = fmaf(q1.w, r.inv.y, -r.oi.y); by = fmaf(q2.z, r.inv.y, -r.oi.y);
-                az = fmaf(q2.x, r.inv.z, -r.oi.z); bz = fmaf(q2.w, r.inv.z, -r.oi.z);
-                const float n1 = fmaxf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)), 0.001f);
-                const float f1 = fminf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), best);
-                const bool h0 = f0 >= n0, h1 = f1 >= n1;
-                const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-                if (h0 && h1) {
-                    const bool first0 = n0 <= n1;
-                    if (sp < 40) stack[sp++] = first0 ? c1 : c0;
-                    cur = first0 ? c0 : c1;
-                    continue;
-                }
-                if (h0) { cur = c0; continue; }
-                if (h1) { cur = c1; continue; }
-            } else {
-                const int link = ~cur, first = link >> 2, cnt = (link & 3) + 1;
-                for (int k = 0; k < cnt; ++k) {
-                    const float4 a = __ldg(tris + 3 * (first + k)), b = __ldg(tris + 3 * (first + k) + 1), c = __ldg(tris + 3 * (first + k) + 2);
-                    if (STATS) st[ST_BVH_TRIS]++;
-                    const float px = r.d.y * c.z - r.d.z * c.y, py = r.d.z * c.x - r.d.x * c.z, pz = r.d.x * c.y - r.d.y * c.x;
-                    const float det = b.x * px + b.y * py + b.z * pz;
-                    if (det == 0.0f) continue;
-                    const float idet = rcp_(det);
-                    const float tx = r.o.x - a.x, ty = r.o.y - a.y, tz = r.o.z - a.z;
-                    const float u = (tx * px + ty * py + tz * pz) * idet;
-                    if (u < 0.0f || u > 1.0f) continue;
-                    const float qx = ty * b.z - tz * b.y, qy = tz * b.x - tx * b.z, qz = tx * b.y - ty * b.x;
-                    const float v = (r.d.x * qx + r.d.y * qy + r.d.z * qz) * idet;
-                    if (v < 0.0f || u + v > 1.0f) continue;
-                    const float t = (c.x * qx + c.y * qy + c.z * qz) * idet;
-                    if (t < 0.001f || t > best) continue;
-                    const int id = __float_as_int(a.w);
-                    if (t < best || (best_tri >= 0 && id < best_tri)) { best = t; bid = kTriBit | (first + k); best_tri = id; }
-                }
-            }
-            // pop, or finish this ray
-            if (sp > 0) { cur = stack[--sp]; }
-            else { S.best[j] = best; S.bid[j] = bid; j = -1; }
-            // too few lanes still traversing: go back and refill the idle ones (only worth it while rays remain)
-            if (!exhausted && __popc(__activemask()) < kRefill) break;
-        }
-    }
-}
-
 // Surface of a triangle hit: point, geometric normal flipped against the ray (setFaceNormal, objects.go:17-24), frontFace.
 __device__ __forceinline__ void tri_surface(const float4* __restrict__ tris, int slot, F3 o, F3 d, float t, F3& p, F3& n, bool& front, int& meta) {
     const float4 b = __ldg(tris + 3 * slot + 1), c = __ldg(tris + 3 * slot + 2);

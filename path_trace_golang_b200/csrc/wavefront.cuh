@@ -62,7 +62,6 @@ struct SlotState {                     // path state, SoA, one entry per slot
 struct WfState : SlotState<WF_SLOTS> {
     unsigned short perm[WF_SLOTS];     // slot | class << 12
     int cnt[CL_COUNT * WF_WARPS];
-    int next_ray;                      // MESH: next slot to traverse in the BVH phase
 };
 
 // Finish the slot's current sample and give it its next camera ray: next sample of the same pixel, or — when the
@@ -306,7 +305,6 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
         S.ox[j] = 0.f; S.oy[j] = 0.f; S.oz[j] = 0.f; S.dx[j] = 0.f; S.dy[j] = 0.f; S.dz[j] = 1.f;
         if (fp.max_depth > 0) path_regen<STATS>(S, fp, n_pix, j, false, st);
     }
-    if (tid == 0) S.next_ray = 0;
     __syncthreads();
 
 #ifdef PTB_WF_TIMING
@@ -354,39 +352,24 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
                     if (h) { best[k] = t; bid[k] = i; }
                 }
             }
+            if (MESH) {                      // EXTENSION: triangle meshes, tested after the analytic objects (bvh.cuh)
+#pragma unroll 1
+                for (int k = 0; k < WF_SG; ++k) {
+                    const int j = tid + (g + k) * WF_THREADS;
+                    if (S.pix[j] >= 0 && S.depth[j] > 0) bvh_closest<STATS>(fp.bvh_nodes, fp.bvh_tris, ray[k], 0.001f, best[k], bid[k], st);
+                }
+            }
 #pragma unroll
             for (int k = 0; k < WF_SG; ++k) {
                 const int j = tid + (g + k) * WF_THREADS;
-                S.best[j] = best[k]; S.bid[j] = bid[k];
-                if (!MESH) {                 // (with meshes the class is known only after the BVH phase below)
-                    int c;
-                    if (S.pix[j] < 0) c = CL_DEAD;
-                    else if (S.depth[j] <= 0) c = CL_REGEN;
-                    else if (bid[k] < 0) c = CL_TERM;
-                    else c = (s_obj[bid[k]].meta >> 3) & 7;
-                    cls[g + k] = c;
-                    if (STATS) { st[ST_LANE_TOTAL]++; if (c != CL_DEAD && c != CL_REGEN) { st[ST_LANE_ACTIVE]++; st[ST_SEGMENTS]++; } }
-                }
-            }
-        }
-        if (MESH) {
-            // EXTENSION: triangle meshes, tested after the analytic objects.  Own phase between two barriers: warps
-            // fetch rays dynamically (bvh.cuh) because traversal lengths vary by 50x between rays.
-            __syncthreads();
-            bvh_phase_dynamic<STATS>(S, WF_SLOTS, &S.next_ray, fp.bvh_nodes, fp.bvh_tris, st);
-            __syncthreads();
-            if (tid == 0) S.next_ray = 0;    // ordered before the next BVH phase by the barriers in between
-#pragma unroll
-            for (int k = 0; k < WF_SPT; ++k) {
-                const int j = tid + k * WF_THREADS;
-                const int b = S.bid[j];
                 int c;
                 if (S.pix[j] < 0) c = CL_DEAD;
                 else if (S.depth[j] <= 0) c = CL_REGEN;
-                else if (b < 0) c = CL_TERM;
-                else if (b & kTriBit) c = (__float_as_int(__ldg(fp.bvh_tris + 3 * (b & ~kTriBit) + 1).w) >> 3) & 7;
-                else c = (s_obj[b].meta >> 3) & 7;
-                cls[k] = c;
+                else if (bid[k] < 0) c = CL_TERM;
+                else if (MESH && (bid[k] & kTriBit)) c = (__float_as_int(__ldg(fp.bvh_tris + 3 * (bid[k] & ~kTriBit) + 1).w) >> 3) & 7;
+                else c = (s_obj[bid[k]].meta >> 3) & 7;
+                cls[g + k] = c;
+                S.best[j] = best[k]; S.bid[j] = bid[k];
                 if (STATS) { st[ST_LANE_TOTAL]++; if (c != CL_DEAD && c != CL_REGEN) { st[ST_LANE_ACTIVE]++; st[ST_SEGMENTS]++; } }
             }
         }
