@@ -185,7 +185,7 @@ def main():
         msps, rays_per_sample, dt = cpu_reference_run(args.workload, W, H, depth, cpu_spp, args.steps, min(args.warmup, 1), cores)
         sample = f"{W}x{H}, {cpu_spp} of {spp} spp per step (samples/s is spp-independent), depth {depth}"
         print(json.dumps({
-            "impl": "reference", "metric": "Msamples/s", "value": msps, "unit": "Msamples/s", "n_gpus": 0,
+            "impl": "reference", "metric": "Msamples/s", "value": msps, "unit": "Msamples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "mrays_per_s": msps * rays_per_sample,
