@@ -127,7 +127,8 @@ typedef struct {
 typedef struct ptb_ctx ptb_ctx;
 
 /* progress callback, same role as `progress func()` of RenderInto (renderer.go:34):
- * invoked on the calling thread after rgba has been refreshed with the samples so far. */
+ * invoked on the calling thread after rgba has been refreshed with the samples so far.  The context is locked
+ * while it runs: it must not call back into the library with the same context. */
 typedef void (*ptb_progress_fn)(void* user);
 
 typedef struct {
