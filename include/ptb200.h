@@ -207,6 +207,20 @@ int ptb_primary_hits(ptb_ctx* ctx, const ptb_cfg* cfg, double xi_u, double xi_v,
 int ptb_get_stats(ptb_ctx* ctx, ptb_stats* out);
 int ptb_get_bvh_info(ptb_ctx* ctx, ptb_bvh_info* out);
 
+/* ---- single-process multi-GPU (what a Go host that owns every GPU of the box calls; one process per GPU + NCCL is the
+ * other supported arrangement).  Device k traces samples [k*spp/n, (k+1)*spp/n) of every pixel
+ * into its own fp32 buffer; device 0 then runs ONE kernel that reads all n buffers — its own and, through NVLink
+ * peer access, the others' — sums them and applies the pixel epilogue (reduce + finalise fused, no staging copy).
+ * Same image as one device up to fp32 re-association of the n partial sums. */
+typedef struct ptb_multi ptb_multi;
+int ptb_multi_create(const int* devices, int n_devices, ptb_multi** out);   /* devices == NULL: devices 0..n-1 */
+void ptb_multi_destroy(ptb_multi* m);
+const char* ptb_multi_last_error(const ptb_multi* m);                       /* m may be NULL (failed create) */
+int ptb_multi_scene_upload(ptb_multi* m, const ptb_scene* scene);
+int ptb_multi_render(ptb_multi* m, const ptb_cfg* cfg, uint8_t* rgba, size_t stride);
+/* device time of the last ptb_multi_render: slowest device's integrator, and the fused reduce+epilogue on device 0 */
+int ptb_multi_last_timing(ptb_multi* m, double* render_ms, double* reduce_ms);
+
 /* Measurement helper: FP32 FMA throughput of the device (2 flop per FMA), the roofline
  * denominator MEASURED_PEAKS.json does not carry. */
 int ptb_measure_fp32_peak(ptb_ctx* ctx, double* tflops);

@@ -99,6 +99,12 @@ SYMBOLS = {
     "ptb_get_stats": (C.c_int, [C.c_void_p, C.POINTER(PtbStats)]),
     "ptb_get_bvh_info": (C.c_int, [C.c_void_p, C.POINTER(PtbBvhInfo)]),
     "ptb_measure_fp32_peak": (C.c_int, [C.c_void_p, _dp]),
+    "ptb_multi_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    "ptb_multi_destroy": (None, [C.c_void_p]),
+    "ptb_multi_last_error": (C.c_char_p, [C.c_void_p]),
+    "ptb_multi_scene_upload": (C.c_int, [C.c_void_p, C.POINTER(PtbScene)]),
+    "ptb_multi_render": (C.c_int, [C.c_void_p, C.POINTER(PtbCfg), C.c_void_p, C.c_size_t]),
+    "ptb_multi_last_timing": (C.c_int, [C.c_void_p, _dp, _dp]),
     # host mirror
     "ptb_host_last_error": (C.c_char_p, []),
     "ptb_host_scene_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),

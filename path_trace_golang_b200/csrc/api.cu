@@ -677,6 +677,152 @@ int ptb_get_stats(ptb_ctx* c, ptb_stats* out) {
     return PTB_OK;
 }
 
+// ------------------------------------------------------------------ single-process multi-GPU
+}  // extern "C"
+
+struct ptb_multi {
+    std::vector<ptb_ctx*> ctx;
+    std::string err;
+    std::mutex mu;
+    std::vector<float*> d_accum;         // per device, W*H*3 floats
+    size_t accum_cap = 0;
+    const float** d_ptrs = nullptr;      // device-0 array of the n buffer pointers
+    std::vector<cudaEvent_t> done, begin;
+    double render_ms = 0, reduce_ms = 0;
+};
+namespace {
+thread_local std::string g_multi_error;
+int mfail(ptb_multi* m, int code, const std::string& msg) { if (m) m->err = msg; else g_multi_error = msg; return code; }
+}  // namespace
+
+extern "C" {
+
+int ptb_multi_create(const int* devices, int n, ptb_multi** out) {
+    if (!out || n < 1) return mfail(nullptr, PTB_ERR_INVALID, "bad argument");
+    *out = nullptr;
+    ptb_multi* m = new ptb_multi();
+    for (int k = 0; k < n; k++) {
+        ptb_ctx* c = nullptr;
+        int rc = ptb_create(devices ? devices[k] : k, &c);
+        if (rc != PTB_OK) { std::string e = ptb_last_error(nullptr); ptb_multi_destroy(m); return mfail(nullptr, rc, e); }
+        m->ctx.push_back(c);
+    }
+    // peer access: device 0 reads every other device's accumulation buffer
+    cudaSetDevice(m->ctx[0]->device);
+    for (int k = 1; k < n; k++) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, m->ctx[0]->device, m->ctx[k]->device);
+        if (!can) { ptb_multi_destroy(m); return mfail(nullptr, PTB_ERR_CUDA, "device " + std::to_string(m->ctx[0]->device) + " cannot access device " + std::to_string(m->ctx[k]->device) + " as a peer"); }
+        cudaError_t e = cudaDeviceEnablePeerAccess(m->ctx[k]->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ptb_multi_destroy(m); return mfail(nullptr, PTB_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); }
+        cudaGetLastError();
+    }
+    m->d_accum.assign(n, nullptr);
+    m->done.assign(n, nullptr); m->begin.assign(n, nullptr);
+    for (int k = 0; k < n; k++) { cudaSetDevice(m->ctx[k]->device); cudaEventCreate(&m->done[k]); cudaEventCreate(&m->begin[k]); }
+    *out = m;
+    return PTB_OK;
+}
+
+void ptb_multi_destroy(ptb_multi* m) {
+    if (!m) return;
+    for (size_t k = 0; k < m->ctx.size(); k++) {
+        cudaSetDevice(m->ctx[k]->device);
+        if (k < m->d_accum.size()) cudaFree(m->d_accum[k]);
+        if (k < m->done.size() && m->done[k]) cudaEventDestroy(m->done[k]);
+        if (k < m->begin.size() && m->begin[k]) cudaEventDestroy(m->begin[k]);
+    }
+    if (!m->ctx.empty()) { cudaSetDevice(m->ctx[0]->device); cudaFree((void*)m->d_ptrs); }
+    for (ptb_ctx* c : m->ctx) ptb_destroy(c);
+    delete m;
+}
+
+const char* ptb_multi_last_error(const ptb_multi* m) { return m ? m->err.c_str() : g_multi_error.c_str(); }
+
+int ptb_multi_scene_upload(ptb_multi* m, const ptb_scene* s) {
+    if (!m) return PTB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(m->mu);
+    for (ptb_ctx* c : m->ctx) { int rc = ptb_scene_upload(c, s); if (rc != PTB_OK) return mfail(m, rc, ptb_last_error(c)); }
+    return PTB_OK;
+}
+
+int ptb_multi_render(ptb_multi* m, const ptb_cfg* cfg, uint8_t* rgba, size_t stride) {
+    if (!m || !cfg || !rgba) return mfail(m, PTB_ERR_INVALID, "NULL argument");
+    std::lock_guard<std::mutex> lk(m->mu);
+    const int n = (int)m->ctx.size(), W = cfg->width, H = cfg->height, spp = cfg->samples_per_px;
+    if (W < 2 || H < 2 || spp < 1) return mfail(m, PTB_ERR_INVALID, "bad frame configuration");
+    if (stride < (size_t)W * 4) return mfail(m, PTB_ERR_INVALID, "stride < 4*width");
+    const size_t bytes = (size_t)W * H * 3 * sizeof(float);
+    if (m->accum_cap < bytes) {
+        for (int k = 0; k < n; k++) {
+            cudaSetDevice(m->ctx[k]->device);
+            cudaFree(m->d_accum[k]); m->d_accum[k] = nullptr;
+            cudaError_t e = cudaMalloc((void**)&m->d_accum[k], bytes);
+            if (e != cudaSuccess) return mfail(m, PTB_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        }
+        cudaSetDevice(m->ctx[0]->device);
+        if (!m->d_ptrs) { cudaError_t e = cudaMalloc((void**)&m->d_ptrs, sizeof(float*) * n); if (e != cudaSuccess) return mfail(m, PTB_ERR_CUDA, "cudaMalloc failed"); }
+        cudaError_t e = cudaMemcpy((void*)m->d_ptrs, m->d_accum.data(), sizeof(float*) * n, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return mfail(m, PTB_ERR_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e));
+        m->accum_cap = bytes;
+    }
+    // every device traces its sample range (asynchronous launches: the devices run concurrently)
+    int active = 0;
+    for (int k = 0; k < n; k++) {
+        const int base = spp / n, rem = spp % n;
+        const int b = k * base + (k < rem ? k : rem), cnt = base + (k < rem ? 1 : 0);
+        ptb_ctx* c = m->ctx[k];
+        cudaSetDevice(c->device);
+        cudaEventRecord(m->begin[k], c->stream);
+        if (cnt > 0) {
+            ptb_cfg sub = *cfg;
+            sub.sample_begin = b; sub.sample_count = cnt;
+            sub.flags &= ~PTB_FLAG_STATS;
+            int rc = ptb_render_accum_device(c, &sub, m->d_accum[k], c->stream);
+            if (rc != PTB_OK) return mfail(m, rc, ptb_last_error(c));
+            active++;
+        } else {
+            cudaMemsetAsync(m->d_accum[k], 0, bytes, c->stream);
+        }
+        cudaEventRecord(m->done[k], c->stream);
+    }
+    // device 0: wait for everybody, then the fused reduce + epilogue over peer memory, then read back
+    ptb_ctx* c0 = m->ctx[0];
+    cudaSetDevice(c0->device);
+    const size_t img_bytes = (size_t)W * H * 4;
+    int rc;
+    if ((rc = ensure(c0, (void**)&c0->d_rgba, &c0->rgba_cap, img_bytes))) return mfail(m, rc, ptb_last_error(c0));
+    if ((rc = ensure(c0, (void**)&c0->h_rgba, &c0->h_rgba_cap, img_bytes, true))) return mfail(m, rc, ptb_last_error(c0));
+    for (int k = 1; k < n; k++) cudaStreamWaitEvent(c0->stream, m->done[k], 0);
+    cudaEventRecord(c0->ev0, c0->stream);
+    int e = launch_finalize_peers((const float* const*)m->d_ptrs, n, W, H, spp, c0->d_rgba, c0->stream);
+    if (e) return mfail(m, PTB_ERR_CUDA, std::string("finalize_peers launch: ") + cudaGetErrorString((cudaError_t)e));
+    cudaEventRecord(c0->ev1, c0->stream);
+    cudaError_t ce = cudaMemcpyAsync(c0->h_rgba, c0->d_rgba, img_bytes, cudaMemcpyDeviceToHost, c0->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(c0->stream);
+    if (ce != cudaSuccess) return mfail(m, PTB_ERR_CUDA, std::string("multi render: ") + cudaGetErrorString(ce));
+    if (stride == (size_t)W * 4) std::memcpy(rgba, c0->h_rgba, img_bytes);
+    else for (int y = 0; y < H; y++) std::memcpy(rgba + (size_t)y * stride, c0->h_rgba + (size_t)y * W * 4, (size_t)W * 4);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c0->ev0, c0->ev1);
+    m->reduce_ms = ms;
+    m->render_ms = 0;
+    for (int k = 0; k < n; k++) {
+        cudaSetDevice(m->ctx[k]->device);
+        float t = 0;
+        if (cudaEventElapsedTime(&t, m->begin[k], m->done[k]) == cudaSuccess && t > m->render_ms) m->render_ms = t;
+    }
+    (void)active;
+    return PTB_OK;
+}
+
+int ptb_multi_last_timing(ptb_multi* m, double* render_ms, double* reduce_ms) {
+    if (!m) return PTB_ERR_INVALID;
+    if (render_ms) *render_ms = m->render_ms;
+    if (reduce_ms) *reduce_ms = m->reduce_ms;
+    return PTB_OK;
+}
+
 int ptb_measure_fp32_peak(ptb_ctx* c, double* tflops) {
     if (!c || !tflops) return PTB_ERR_INVALID;
     std::lock_guard<std::mutex> lk(c->mu);

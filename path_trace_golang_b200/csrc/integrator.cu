@@ -532,6 +532,35 @@ __global__ void finalize_kernel(const float* __restrict__ accum, int n_pix, doub
     rgba[i] = make_uchar4(to_u8(a[0], inv_spp), to_u8(a[1], inv_spp), to_u8(a[2], inv_spp), 255);
 }
 
+// Multi-GPU reduce fused with the pixel epilogue: bufs[k] is device k's fp32 sum buffer; bufs[1..] are PEER pointers, read
+// over NVLink with 16-byte loads.  Sum order is device 0, 1, 2, ... (deterministic).
+__global__ void finalize_peers_kernel(const float* const* __restrict__ bufs, int n_bufs, int n_pix, double inv_spp, uchar4* __restrict__ rgba) {
+    // 4 pixels = 12 floats = 3 float4 per thread
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    const int p0 = g * 4;
+    if (p0 >= n_pix) return;
+    if (p0 + 4 <= n_pix) {
+        float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
+        for (int k = 0; k < n_bufs; ++k) {
+            const float4* src = reinterpret_cast<const float4*>(bufs[k]) + (size_t)g * 3;
+            const float4 x = src[0], y = src[1], z = src[2];
+            a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+            b.x += y.x; b.y += y.y; b.z += y.z; b.w += y.w;
+            c.x += z.x; c.y += z.y; c.z += z.z; c.w += z.w;
+        }
+        rgba[p0 + 0] = make_uchar4(to_u8(a.x, inv_spp), to_u8(a.y, inv_spp), to_u8(a.z, inv_spp), 255);
+        rgba[p0 + 1] = make_uchar4(to_u8(a.w, inv_spp), to_u8(b.x, inv_spp), to_u8(b.y, inv_spp), 255);
+        rgba[p0 + 2] = make_uchar4(to_u8(b.z, inv_spp), to_u8(b.w, inv_spp), to_u8(c.x, inv_spp), 255);
+        rgba[p0 + 3] = make_uchar4(to_u8(c.y, inv_spp), to_u8(c.z, inv_spp), to_u8(c.w, inv_spp), 255);
+    } else {
+        for (int p = p0; p < n_pix; ++p) {
+            float r = 0, gg = 0, bb = 0;
+            for (int k = 0; k < n_bufs; ++k) { const float* s = bufs[k] + (size_t)p * 3; r += s[0]; gg += s[1]; bb += s[2]; }
+            rgba[p] = make_uchar4(to_u8(r, inv_spp), to_u8(gg, inv_spp), to_u8(bb, inv_spp), 255);
+        }
+    }
+}
+
 // FP32 FMA throughput probe: 8 independent chains per thread, 2 flop per FMA.
 __global__ void fma_peak_kernel(float* out, int iters) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
@@ -629,6 +658,13 @@ int launch_finalize(const float* accum, int width, int height, int spp_total, ui
     int n = width * height;
     finalize_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(accum, n, 1.0 / (double)spp_total,
                                                                       reinterpret_cast<uchar4*>(rgba));
+    return (int)cudaGetLastError();
+}
+
+int launch_finalize_peers(const float* const* d_bufs_on_dev0, int n_bufs, int width, int height, int spp_total, uint8_t* rgba, void* stream) {
+    const int n = width * height, threads = 256, groups = (n + 3) / 4;
+    finalize_peers_kernel<<<(groups + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(d_bufs_on_dev0, n_bufs, n, 1.0 / (double)spp_total,
+                                                                                              reinterpret_cast<uchar4*>(rgba));
     return (int)cudaGetLastError();
 }
 

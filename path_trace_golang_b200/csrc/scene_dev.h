@@ -91,6 +91,7 @@ int launch_integrator_wq(const FrameParams& fp, bool stats, int n_obj, int n_mat
 int launch_finalize(const float* accum, int width, int height, int spp_total, uint8_t* rgba, void* stream);
 int launch_primary_hits(const Obj64* d_world, int n_obj, const float4* bvh_nodes, const float4* bvh_tris, const Camera64& cam,
                         int width, int height, double xi_u, double xi_v, int32_t* d_ids, double* d_t, void* stream);
+int launch_finalize_peers(const float* const* d_bufs_on_dev0, int n_bufs, int width, int height, int spp_total, uint8_t* rgba, void* stream);
 int launch_fma_peak(float* d_out, int blocks, int threads, int iters, void* stream);
 
 }  // namespace ptb

@@ -148,6 +148,54 @@ class Context:
         return v.value
 
 
+class MultiContext:
+    """ptb_multi: every listed CUDA device driven from ONE process (what a Go host owning the whole box would do).
+    Device k traces its slice of the samples; device 0 sums all slices over NVLink peer loads inside the epilogue kernel."""
+
+    def __init__(self, devices):
+        self._L = _lib.lib()
+        devs = list(range(devices)) if isinstance(devices, int) else [int(d) for d in devices]
+        arr = (C.c_int * len(devs))(*devs)
+        h = C.c_void_p()
+        rc = self._L.ptb_multi_create(arr, len(devs), C.byref(h))
+        if rc:
+            raise PtbError(rc, self._L.ptb_multi_last_error(None).decode())
+        self._h = h
+        self.devices = devs
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._L.ptb_multi_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc:
+            raise PtbError(rc, self._L.ptb_multi_last_error(self._h).decode())
+
+    def upload(self, sc: Scene):
+        flat = sc.flat()
+        self._check(self._L.ptb_multi_scene_upload(self._h, C.byref(flat)))
+        self._scene = sc
+
+    def render(self, cfg: PtbCfg, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.zeros((cfg.height, cfg.width, 4), dtype=np.uint8)
+        assert out.dtype == np.uint8 and out.ndim == 3 and out.shape[2] == 4 and out.strides[1] == 4 and out.strides[2] == 1
+        self._check(self._L.ptb_multi_render(self._h, C.byref(cfg), out.ctypes.data, out.strides[0]))
+        return out
+
+    def last_timing(self) -> dict:
+        a, b = C.c_double(), C.c_double()
+        self._check(self._L.ptb_multi_last_timing(self._h, C.byref(a), C.byref(b)))
+        return dict(render_ms=a.value, reduce_ms=b.value)
+
+
 def default_context() -> Context:
     global _default_ctx
     if _default_ctx is None:

@@ -43,6 +43,12 @@ def test_create_fails_loudly_without_gpu():
         assert e.code == -2 and "no CPU fallback" in e.message
     else:
         raise AssertionError("ptb_create succeeded without a GPU")
+    try:
+        engine.MultiContext([0, 1])
+    except PtbError as e:
+        assert e.code == -2 and "no CPU fallback" in e.message
+    else:
+        raise AssertionError("ptb_multi_create succeeded without a GPU")
 
 
 def test_product_does_not_import_oracle():

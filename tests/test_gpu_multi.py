@@ -1,0 +1,66 @@
+"""ptb_multi_*: every device of the box from ONE process (the arrangement a Go host would use).
+The sample set is the same as on one device (samples are keyed by index), only the fp32 summation order of the
+per-device partial sums differs, so the 8-bit image may differ by one level in a few pixels."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from path_trace_golang_b200 import engine
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_devices():
+    import torch
+    return torch.cuda.device_count()
+
+
+def test_multi_single_device_is_bit_identical(ctx, host_scenes):
+    """n = 1: the fused reduce+epilogue kernel must produce exactly ptb_render's image."""
+    sc = host_scenes["metal_glass_room"]
+    ctx.upload(sc)
+    cfg = ctx.cfg(320, 180, 16, 8, seed=5)
+    one = ctx.render(cfg)
+    m = engine.MultiContext([0])
+    m.upload(sc)
+    img = m.render(cfg)
+    assert np.array_equal(img, one)
+    # ragged pixel count (not a multiple of 4) goes through the scalar tail
+    cfg = ctx.cfg(37, 23, 4, 6, seed=5)
+    assert np.array_equal(m.render(cfg), ctx.render(cfg))
+    t = m.last_timing()
+    assert t["render_ms"] > 0 and t["reduce_ms"] > 0
+    m.close()
+
+
+def test_multi_rejects_bad_arguments(ctx, host_scenes):
+    m = engine.MultiContext([0])
+    with pytest.raises(engine.PtbError):
+        m.render(ctx.cfg(64, 64, 4, 4))                     # no scene yet
+    m.upload(host_scenes["test_scene"])
+    with pytest.raises(engine.PtbError):
+        m.render(ctx.cfg(64, 64, 0, 4))
+    m.close()
+    with pytest.raises(engine.PtbError):
+        engine.MultiContext([9999])
+
+
+def test_multi_two_devices_match_one(ctx, host_scenes):
+    if _n_devices() < 2:
+        pytest.skip("needs at least 2 CUDA devices")
+    sc = host_scenes["metal_glass_room"]
+    ctx.upload(sc)
+    m = engine.MultiContext(_n_devices())
+    m.upload(sc)
+    for (w, h, spp, depth) in [(640, 360, 64, 16), (101, 67, 5, 8), (64, 64, 1, 4)]:   # spp=1: idle devices contribute zeros
+        cfg = ctx.cfg(w, h, spp, depth, seed=9)
+        one = ctx.render(cfg).astype(np.int16)
+        img = m.render(cfg).astype(np.int16)
+        diff = np.abs(one - img)
+        assert diff.max() <= 1, (w, h, spp, diff.max())
+        assert (diff > 0).mean() < 1e-3
+    # repeated renders are deterministic
+    cfg = ctx.cfg(640, 360, 64, 16, seed=9)
+    assert np.array_equal(m.render(cfg), m.render(cfg))
+    m.close()
