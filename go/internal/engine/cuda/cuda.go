@@ -45,9 +45,14 @@ var Seed uint32 = 1
 // Device is the CUDA device ordinal used by the process-wide context.
 var Device = 0
 
+// Devices > 1 renders every frame on devices 0..Devices-1 of the box (ptb_multi_*: sample ranges per device, reduced on
+// device 0).  The progress callback then fires only once, when the frame is complete.
+var Devices = 1
+
 var (
 	mu      sync.Mutex // one render at a time per context (the GL path serialises on its worker, gpu.go:266-297)
 	ctx     *C.ptb_ctx
+	multi   *C.ptb_multi
 	initErr error
 	once    sync.Once
 )
@@ -56,6 +61,12 @@ func lastError(c *C.ptb_ctx) error { return errors.New(C.GoString(C.ptb_last_err
 
 func ensureContext() error {
 	once.Do(func() {
+		if Devices > 1 {
+			if rc := C.ptb_multi_create(nil, C.int(Devices), &multi); rc != C.PTB_OK {
+				initErr = fmt.Errorf("CUDA initialization failed: %s", C.GoString(C.ptb_multi_last_error(nil)))
+			}
+			return
+		}
 		if rc := C.ptb_create(C.int(Device), &ctx); rc != C.PTB_OK {
 			initErr = fmt.Errorf("CUDA initialization failed: %w", lastError(nil))
 		}
@@ -205,11 +216,24 @@ func Render(sc *scene.Scene, cfg RenderConfig, img *image.RGBA, progress func())
 
 	f := flatten(sc)
 	defer f.release()
+	c := C.ptb_cfg{width: C.int32_t(cfg.Width), height: C.int32_t(cfg.Height), samples_per_px: C.int32_t(cfg.SamplesPerPx),
+		max_depth: C.int32_t(cfg.MaxDepth), seed: C.uint32_t(Seed)}
+	if multi != nil {
+		if rc := C.ptb_multi_scene_upload(multi, &f.s); rc != C.PTB_OK {
+			return fmt.Errorf("ptb_multi_scene_upload: %s", C.GoString(C.ptb_multi_last_error(multi)))
+		}
+		off := img.PixOffset(b.Min.X, b.Min.Y)
+		if rc := C.ptb_multi_render(multi, &c, (*C.uint8_t)(unsafe.Pointer(&img.Pix[off])), C.size_t(img.Stride)); rc != C.PTB_OK {
+			return fmt.Errorf("ptb_multi_render: %s", C.GoString(C.ptb_multi_last_error(multi)))
+		}
+		if progress != nil {
+			progress()
+		}
+		return nil
+	}
 	if rc := C.ptb_scene_upload(ctx, &f.s); rc != C.PTB_OK {
 		return fmt.Errorf("ptb_scene_upload: %w", lastError(ctx))
 	}
-	c := C.ptb_cfg{width: C.int32_t(cfg.Width), height: C.int32_t(cfg.Height), samples_per_px: C.int32_t(cfg.SamplesPerPx),
-		max_depth: C.int32_t(cfg.MaxDepth), seed: C.uint32_t(Seed)}
 	var cb C.ptb_progress_fn
 	var user unsafe.Pointer
 	if progress != nil {
