@@ -16,6 +16,9 @@ uint32_t g_seed = 1;
 int g_device = 0;
 ptb_ctx* g_ctx = nullptr;
 int g_ctx_device = -1;
+int g_devices = 1;
+ptb_multi* g_multi = nullptr;
+int g_multi_n = 0;
 std::mutex g_mu;
 std::string g_err;
 
@@ -32,6 +35,7 @@ void SetBackend(Backend b) { g_backend = (b == BackendCPU || b == BackendGPU || 
 Backend GetBackend() { return g_backend; }
 void SetSeed(uint32_t s) { g_seed = s; }
 void SetDevice(int d) { g_device = d; }
+void SetDevices(int n) { g_devices = n < 1 ? 1 : n; }
 const std::string& LastError() { return g_err; }
 
 int RenderIntoCtx(ptb_ctx* ctx, const scene::Scene& sc, RenderConfig cfg, uint32_t seed, uint8_t* pix, size_t stride,
@@ -53,6 +57,33 @@ int RenderInto(const scene::Scene& sc, RenderConfig cfg, RGBA& img, const std::f
         g_err = "backend not available in this build: only BackendCUDA exists (no CPU fallback)";
         std::fprintf(stderr, "render error: %s\n", g_err.c_str());
         return PTB_ERR_INVALID;
+    }
+    if (g_devices > 1) {
+        if (img.W != cfg.Width || img.H != cfg.Height) return PTB_OK;
+        if (g_multi && g_multi_n != g_devices) { ptb_multi_destroy(g_multi); g_multi = nullptr; }
+        if (!g_multi) {
+            if (ptb_multi_create(nullptr, g_devices, &g_multi) != PTB_OK) {
+                g_err = std::string("CUDA initialization failed: ") + ptb_multi_last_error(nullptr);
+                g_multi = nullptr;
+                std::fprintf(stderr, "%s\n", g_err.c_str());
+                return PTB_ERR_CUDA;
+            }
+            g_multi_n = g_devices;
+        }
+        scene::Flat flat = scene::Flatten(sc);
+        ptb_scene view = flat.view();
+        ptb_cfg c{};
+        c.width = cfg.Width; c.height = cfg.Height; c.samples_per_px = cfg.SamplesPerPx; c.max_depth = cfg.MaxDepth;
+        c.seed = g_seed;
+        int rc = ptb_multi_scene_upload(g_multi, &view);
+        if (rc == PTB_OK) rc = ptb_multi_render(g_multi, &c, img.Pix.data(), (size_t)img.Stride);
+        if (rc != PTB_OK) {
+            g_err = ptb_multi_last_error(g_multi);
+            std::fprintf(stderr, "CUDA render error: %s\n", g_err.c_str());
+        } else if (progress) {
+            progress();
+        }
+        return rc;
     }
     ptb_ctx* ctx = default_ctx();
     if (!ctx) { std::fprintf(stderr, "%s\n", g_err.c_str()); return PTB_ERR_CUDA; }

@@ -28,6 +28,7 @@ Backend GetBackend();
 // Counter-RNG key and device for subsequent renders (the reference seeds from the clock, random.go:14-16).
 void SetSeed(uint32_t seed);
 void SetDevice(int device);
+void SetDevices(int n);          // n > 1: render every frame on devices 0..n-1 of the box (ptb_multi_*); progress fires once at the end
 const std::string& LastError();
 
 RGBA Render(const scene::Scene& sc, RenderConfig cfg);                                               // renderer.go:25-29

@@ -1,7 +1,7 @@
 // render_main.cpp — `ptb_render`: the reference's cmd/render (main.go:14-63) in C++ on the CUDA backend.
 //
 // Same flags and defaults as the reference (-scene, -mode, -gpu, -headless, -out; Go-style single-dash flags, `-flag value`
-// or `-flag=value`), plus what SURVEY §8f rank 2 asks for: -width -height -spp -depth -seed -settings -device.
+// or `-flag=value`), plus what SURVEY §8f rank 2 asks for: -width -height -spp -depth -seed -settings -device -devices.
 // The UI path (internal/ui) is out of scope: without -headless this driver still renders headless and says so.
 #include <chrono>
 #include <cstdio>
@@ -15,7 +15,7 @@ namespace {
 struct Flags {
     std::string scene = "scenes/example_simple.json", mode = "preview", out = "output.png";   // main.go:17-21
     bool gpu = false, headless = false, settings = false;
-    int width = 0, height = 0, spp = 0, depth = -1, device = 0;
+    int width = 0, height = 0, spp = 0, depth = -1, device = 0, devices = 1;
     unsigned seed = 1;
 };
 bool parse(int argc, char** argv, Flags& f) {
@@ -44,6 +44,7 @@ bool parse(int argc, char** argv, Flags& f) {
         else if (a == "-spp") { if (!(v = next())) return false; f.spp = std::atoi(v); }
         else if (a == "-depth") { if (!(v = next())) return false; f.depth = std::atoi(v); }
         else if (a == "-seed") { if (!(v = next())) return false; f.seed = (unsigned)std::strtoul(v, nullptr, 10); }
+        else if (a == "-devices") { if (!(v = next())) return false; f.devices = std::atoi(v); }
         else if (a == "-device") { if (!(v = next())) return false; f.device = std::atoi(v); }
         else { std::fprintf(stderr, "flag provided but not defined: %s\n", a.c_str()); return false; }
     }
@@ -59,6 +60,7 @@ int main(int argc, char** argv) {
     if (!f.headless) std::fprintf(stderr, "note: the desktop UI is out of scope of this backend; rendering headless\n");
     engine::SetBackend(engine::BackendCUDA);                                  // main.go:26-30 selects CPU/GPU; here: CUDA only
     engine::SetDevice(f.device);
+    engine::SetDevices(f.devices);
     engine::SetSeed(f.seed);
     try {
         std::unique_ptr<scene::Scene> sc = scene::Load(f.scene);              // main.go:47

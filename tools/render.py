@@ -35,6 +35,7 @@ def parse(argv=None):
     ap.add_argument("-depth", type=int, default=-1)
     ap.add_argument("-seed", type=int, default=1, help="key of the counter RNG (the reference seeds from the clock)")
     ap.add_argument("-device", type=int, default=0)
+    ap.add_argument("-devices", type=int, default=1, help="render on devices 0..N-1 of the box from this one process")
     return ap.parse_args(argv)
 
 
@@ -66,9 +67,15 @@ def main(argv=None) -> int:
         return 1
     w, h, spp, depth = resolve_settings(args, sc.Settings, engine.RenderSettingsForMode(args.mode))
     try:
-        ctx = engine.Context(args.device)
         t0 = time.perf_counter()
-        img = engine.Render(sc, engine.RenderConfig(w, h, spp, depth), ctx=ctx, seed=args.seed)   # main.go:54
+        if args.devices > 1:
+            m = engine.MultiContext(args.devices)
+            m.upload(sc)
+            img = m.render(engine.Context.cfg(w, h, spp, depth, seed=args.seed))
+        else:
+            ctx = engine.Context(args.device)
+            t0 = time.perf_counter()
+            img = engine.Render(sc, engine.RenderConfig(w, h, spp, depth), ctx=ctx, seed=args.seed)   # main.go:54
         dt = time.perf_counter() - t0
         engine.SavePNG(args.out, img)                                     # main.go:59
     except PtbError as e:
