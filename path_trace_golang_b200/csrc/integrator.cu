@@ -130,13 +130,14 @@ __device__ __forceinline__ F3 cosine_direction(F3 n, float r1, float r2) {
 // Per-ray constants of the closest-hit tests: a = d.d (objects.go:43), inv = 1/d (objects.go:149-161),
 // oi = o*inv (so a slab distance (b - o)*inv is one FFMA: b*inv - oi), inv_a = 1/a (the divisions of
 // objects.go:55,57 become multiplications).
-struct RayK { F3 o, d, inv, oi; float a, inv_a; };
+struct RayK { F3 o, d, inv, oi, ainv; float a, inv_a; };
 __device__ __forceinline__ RayK make_ray(F3 o, F3 d) {
     RayK r;
     r.o = o; r.d = d;
     r.a = d.x * d.x + d.y * d.y + d.z * d.z;
     r.inv = f3(rcp_(d.x), rcp_(d.y), rcp_(d.z));
     r.oi = f3(o.x * r.inv.x, o.y * r.inv.y, o.z * r.inv.z);
+    r.ainv = f3(fabsf(r.inv.x), fabsf(r.inv.y), fabsf(r.inv.z));
     r.inv_a = rcp_(r.a);
     return r;
 }
@@ -148,17 +149,38 @@ __device__ __forceinline__ RayK make_ray(F3 o, F3 d) {
 // direction component exactly 0) is dropped by min/max instead of poisoning the comparison; the binary64
 // parity kernel keeps the reference's exact form.]
 __device__ __forceinline__ bool hit_box(float4 lo, float4 hi, const RayK& r, float tmin, float tmax, float& t_out) {
-#if PTB_FAST_MATH
-    const float ax = fmaf(lo.x, r.inv.x, -r.oi.x), bx = fmaf(hi.x, r.inv.x, -r.oi.x);
-    const float ay = fmaf(lo.y, r.inv.y, -r.oi.y), by = fmaf(hi.y, r.inv.y, -r.oi.y);
-    const float az = fmaf(lo.z, r.inv.z, -r.oi.z), bz = fmaf(hi.z, r.inv.z, -r.oi.z);
+#if PTB_FAST_MATH && PTB_BOX_CH
+    // record = (centre c, half extent h >= 0): the slab interval of an axis is (c - o)/d -+ h/|d|, so near and far come
+    // out ordered and the per-axis min/max pair (half-rate ALU pipe) disappears: 9 FMA-pipe ops + 4 three-input min/max.
+    const float cx = fmaf(lo.x, r.inv.x, -r.oi.x), cy = fmaf(lo.y, r.inv.y, -r.oi.y), cz = fmaf(lo.z, r.inv.z, -r.oi.z);
+#if PTB_BOX_CH == 1
+    const float nx = fmaf(-hi.x, r.ainv.x, cx), ny = fmaf(-hi.y, r.ainv.y, cy), nz = fmaf(-hi.z, r.ainv.z, cz);
+    const float fx = fmaf(hi.x, r.ainv.x, cx), fy = fmaf(hi.y, r.ainv.y, cy), fz = fmaf(hi.z, r.ainv.z, cz);
 #else
-    const float ax = (lo.x - r.o.x) * r.inv.x, bx = (hi.x - r.o.x) * r.inv.x;
-    const float ay = (lo.y - r.o.y) * r.inv.y, by = (hi.y - r.o.y) * r.inv.y;
-    const float az = (lo.z - r.o.z) * r.inv.z, bz = (hi.z - r.o.z) * r.inv.z;
+    const float hx = hi.x * r.inv.x, hy = hi.y * r.inv.y, hz = hi.z * r.inv.z;
+    const float nx = cx - fabsf(hx), ny = cy - fabsf(hy), nz = cz - fabsf(hz);
+    const float fx = cx + fabsf(hx), fy = cy + fabsf(hy), fz = cz + fabsf(hz);
+#endif
+    const float t0 = fmaxf(fmaxf(fmaxf(nx, ny), nz), tmin);
+    const float t1 = fminf(fminf(fminf(fx, fy), fz), tmax);
+#else
+#if PTB_BOX_CH
+    const float lx = lo.x - hi.x, ly = lo.y - hi.y, lz = lo.z - hi.z, ux = lo.x + hi.x, uy = lo.y + hi.y, uz = lo.z + hi.z;
+#else
+    const float lx = lo.x, ly = lo.y, lz = lo.z, ux = hi.x, uy = hi.y, uz = hi.z;
+#endif
+#if PTB_FAST_MATH
+    const float ax = fmaf(lx, r.inv.x, -r.oi.x), bx = fmaf(ux, r.inv.x, -r.oi.x);
+    const float ay = fmaf(ly, r.inv.y, -r.oi.y), by = fmaf(uy, r.inv.y, -r.oi.y);
+    const float az = fmaf(lz, r.inv.z, -r.oi.z), bz = fmaf(uz, r.inv.z, -r.oi.z);
+#else
+    const float ax = (lx - r.o.x) * r.inv.x, bx = (ux - r.o.x) * r.inv.x;
+    const float ay = (ly - r.o.y) * r.inv.y, by = (uy - r.o.y) * r.inv.y;
+    const float az = (lz - r.o.z) * r.inv.z, bz = (uz - r.o.z) * r.inv.z;
 #endif
     const float t0 = fmaxf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)), tmin);
     const float t1 = fminf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), tmax);
+#endif
     t_out = t0;
     return t1 > t0;
 }
@@ -200,9 +222,16 @@ __device__ __forceinline__ void surface(const DevObj& ob, int type, F3 o, F3 d, 
     } else if (type == PTB_OBJ_PLANE) {
         on = f3(0.0f, 1.0f, 0.0f);
     } else {
+#if PTB_BOX_CH
+        const float qx = p.x - ob.ax, qy = p.y - ob.ay, qz = p.z - ob.az;     // record = (centre, half extent)
+        float dxMin = qx + ob.bx, dxMax = ob.bx - qx;
+        float dyMin = qy + ob.by, dyMax = ob.by - qy;
+        float dzMin = qz + ob.bz, dzMax = ob.bz - qz;
+#else
         float dxMin = p.x - ob.ax, dxMax = ob.bx - p.x;
         float dyMin = p.y - ob.ay, dyMax = ob.by - p.y;
         float dzMin = p.z - ob.az, dzMax = ob.bz - p.z;
+#endif
         float md = dxMin;
         on = f3(-1.0f, 0.0f, 0.0f);
         if (dxMax < md) { md = dxMax; on = f3(1.0f, 0.0f, 0.0f); }
@@ -224,6 +253,16 @@ __device__ __forceinline__ bool front_face_only(const DevObj& ob, int type, F3 o
     if (type == PTB_OBJ_PLANE) return d.y < 0.0f;
     // box: nearest face in the reference's order -x,+x,-y,+y,-z,+z with strict '<' (objects.go:188-217); the face
     // normal is +-e_axis, so d.n = +-d[axis]
+#if PTB_BOX_CH
+    const float qx = p.x - ob.ax, qy = p.y - ob.ay, qz = p.z - ob.az;
+    float md = qx + ob.bx, dn = -d.x;
+    float q;
+    q = ob.bx - qx; if (q < md) { md = q; dn = d.x; }
+    q = qy + ob.by; if (q < md) { md = q; dn = -d.y; }
+    q = ob.by - qy; if (q < md) { md = q; dn = d.y; }
+    q = qz + ob.bz; if (q < md) { md = q; dn = -d.z; }
+    q = ob.bz - qz; if (q < md) { dn = d.z; }
+#else
     float md = p.x - ob.ax, dn = -d.x;
     float q;
     q = ob.bx - p.x; if (q < md) { md = q; dn = d.x; }
@@ -231,6 +270,7 @@ __device__ __forceinline__ bool front_face_only(const DevObj& ob, int type, F3 o
     q = ob.by - p.y; if (q < md) { md = q; dn = d.y; }
     q = p.z - ob.az; if (q < md) { md = q; dn = -d.z; }
     q = ob.bz - p.z; if (q < md) { dn = d.z; }
+#endif
     return dn < 0.0f;
 }
 

@@ -13,6 +13,12 @@
 
 namespace ptb {
 
+// PTB_BOX_CH: 0 = box records hold (min, max); 1/2 = (centre, half extent) so the slab test needs no per-axis min/max
+// (1: |1/d| kept in registers, 2: |h/d| through the FADD abs modifier).
+#ifndef PTB_BOX_CH
+#define PTB_BOX_CH 1
+#endif
+
 // 32-byte records, two 16-byte vector loads each.
 struct alignas(16) DevObj {
     float ax, ay, az;   // sphere centre | plane point | box min            (objects.go:31-35, 92-96, 136-139)
