@@ -422,7 +422,17 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
     std::vector<int> order, dev_of(world.size(), -1);
     for (int i = 0; i < (int)world.size(); i++) if (world[i].type == PTB_OBJ_BOX) order.push_back(i);
     hs.n_box = (int)order.size();
-    for (int i = 0; i < (int)world.size(); i++) if (world[i].type == PTB_OBJ_SPHERE || world[i].type == PTB_OBJ_PLANE) order.push_back(i);
+    {   // non-box objects keep their world order; the leading planes and the spheres right after them get typed tables
+        std::vector<int> rest;
+        for (int i = 0; i < (int)world.size(); i++) if (world[i].type == PTB_OBJ_SPHERE || world[i].type == PTB_OBJ_PLANE) rest.push_back(i);
+        size_t k = 0;
+        while (k < rest.size() && world[rest[k]].type == PTB_OBJ_PLANE) k++;
+        hs.n_plane_run = (int)k;
+        while (k < rest.size() && world[rest[k]].type == PTB_OBJ_SPHERE) k++;
+        hs.n_sphere_run = (int)k - hs.n_plane_run;
+        order.insert(order.end(), rest.begin(), rest.end());
+        hs.n_typed = hs.n_box + hs.n_plane_run + hs.n_sphere_run;
+    }
     std::vector<Obj64> w64;
     for (int i = 0; i < (int)world.size(); i++) {
         if (world[i].type == PTB_OBJ_MESH) continue;
@@ -446,6 +456,27 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
         } else { o.bx = (float)w.b[0]; o.by = (float)w.b[1]; o.bz = (float)w.b[2]; }
         o.meta = meta_of(w);
         o.world_idx = i;
+    }
+    {   // scan tables (scene_dev.h)
+        hs.n_box_groups = (hs.n_box + kBoxGroup - 1) / kBoxGroup;
+        float* tab = hs.scan_tab;
+        int f = 0;
+        for (int k = 0; k < hs.n_box_groups * kBoxGroup; k++, f += 6) {
+            float* b = tab + f;
+            if (k < hs.n_box) { const DevObj& o = hs.obj[k]; b[0] = o.ax; b[1] = o.ay; b[2] = o.az; b[3] = o.bx; b[4] = o.by; b[5] = o.bz; }
+            else { b[0] = b[1] = b[2] = 0.0f; b[3] = b[4] = b[5] = -1.0f; }      // far < near on every axis: never hit
+        }
+        f = (f + 3) / 4 * 4;
+        hs.plane_off4 = f / 4;
+        for (int k = 0; k < hs.n_plane_run; k++) tab[f++] = hs.obj[hs.n_box + k].ay;
+        f = (f + 3) / 4 * 4;
+        hs.sphere_off4 = f / 4;
+        hs.n_sphere_groups = (hs.n_sphere_run + kSphereGroup - 1) / kSphereGroup;
+        for (int k = 0; k < hs.n_sphere_groups * kSphereGroup; k++, f += 4) {
+            float* b = tab + f;
+            if (k < hs.n_sphere_run) { const DevObj& o = hs.obj[hs.n_box + hs.n_plane_run + k]; b[0] = o.ax; b[1] = o.ay; b[2] = o.az; b[3] = o.by; }
+            else { b[0] = b[1] = b[2] = 0.0f; b[3] = -1.0f; }                    // radius^2 = -1: discriminant < 0 for every ray
+        }
     }
     for (int i = 0; i < (int)world.size(); i++)      // exit-search candidates: analytic dielectric objects (meshes are not searched)
         if (world[i].type != PTB_OBJ_MESH && world[i].mat_type == PTB_MAT_DIELECTRIC) hs.diel_idx[hs.n_diel++] = dev_of[i];

@@ -197,6 +197,27 @@ __device__ __forceinline__ bool hit_sphere(float4 lo, float4 hi, const RayK& r, 
     t_out = root;
     return !(disc < 0.0f) && !(root < tmin || root > tmax);
 }
+// Same decisions as hit_sphere from the scan table record (centre, radius^2), fewer ALU-pipe ops: r1 <= r2 always (sq >= 0,
+// inv_a > 0), so "r1 if it is in [tmin, tmax] else r2, then range-check" == "root = r1 >= tmin ? r1 : r2; root in range";
+// a negative discriminant makes sq, r1, r2 and root NaN and every ordered comparison false.
+__device__ __forceinline__ bool hit_sphere4(float cx, float cy, float cz, float r2, const RayK& r, float tmin, float tmax, float& t_out) {
+    const float ocx = r.o.x - cx, ocy = r.o.y - cy, ocz = r.o.z - cz;
+    const float hb = ocx * r.d.x + ocy * r.d.y + ocz * r.d.z;
+    const float c = fmaf(ocz, ocz, fmaf(ocy, ocy, fmaf(ocx, ocx, -r2)));
+    const float disc = fmaf(hb, hb, -(r.a * c));
+    const float sq = sqrt_(disc);
+    const float q1 = (-hb - sq) * r.inv_a;
+    const float q2 = (sq - hb) * r.inv_a;
+    const float root = (q1 >= tmin) ? q1 : q2;
+    t_out = root;
+    return root >= tmin && root <= tmax;
+}
+// plane.hit from the scan table (p.y only; normal (0,1,0)): t = p.y/d.y - o.y/d.y.
+__device__ __forceinline__ bool hit_plane1(float py, const RayK& r, float tmin, float tmax, float& t_out) {
+    const float t = fmaf(py, r.inv.y, -r.oi.y);
+    t_out = t;
+    return !(fabsf(r.d.y) < 1e-6f) && t >= tmin && t <= tmax;
+}
 // plane.hit with normal (0,1,0): denom = d.y, t = (p.y - o.y)/d.y (objects.go:100-110, 251-257).
 __device__ __forceinline__ bool hit_plane(float4 lo, const RayK& r, float tmin, float tmax, float& t_out) {
     float t = (lo.y - r.o.y) * r.inv.y;

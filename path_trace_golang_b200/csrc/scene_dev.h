@@ -47,14 +47,26 @@ struct DevSky {      // renderer.go:56-92
     float color[3], horizon[3], zenith[3];
 };
 
-struct DevScene {                        // ~43 KB of the 64 KB constant bank
+struct DevScene {                        // ~55 KB of the 64 KB constant bank
     int32_t n_obj, n_mat, n_diel, n_box;   // n_mat counts the appended zero material (index n_mat-1); boxes are obj[0..n_box)
+    // ---- the closest-hit scan's own tables (wavefront kernel).  Device order of the analytic objects:
+    //   [0, n_box) boxes | [n_box, n_box + n_plane_run) planes | [.., + n_sphere_run) spheres | rest (generic loop),
+    // where the plane run / sphere run / rest split the non-box objects WITHOUT reordering them (world order kept, so the
+    // reference's "later object wins a tie" rule for spheres and planes survives).  scan_tab holds, 16-byte aligned:
+    //   boxes   6 floats each (centre, half extent), padded to whole groups of kBoxGroup with never-hit boxes (h = -1);
+    //   planes  1 float each (p.y), padded to a multiple of 4;
+    //   spheres 4 floats each (centre, radius^2), padded to whole groups of kSphereGroup with never-hit spheres (r^2 = -1).
+    int32_t n_box_groups, n_plane_run, n_sphere_run, n_sphere_groups;
+    int32_t plane_off4, sphere_off4, n_typed, pad_;                       // offsets in float4 units; n_typed = first "rest" index
+    alignas(16) float scan_tab[PTB_MAX_OBJECTS * 6 + 16];
     DevSky sky;
     DevCamera cam;
     int32_t diel_idx[PTB_MAX_OBJECTS];   // DEVICE indices of objects with a dielectric material, in ascending world order
     DevObj obj[PTB_MAX_OBJECTS];
     DevMat mat[PTB_MAX_MATERIALS + 1];   // slot n_mat-1 = the zero material (missing material_id, objects.go:234)
 };
+constexpr int kBoxGroup = 4;
+constexpr int kSphereGroup = 2;
 
 // fp64 world for the primary-hit parity kernel (global memory; N is tiny).
 struct Obj64 {

@@ -296,6 +296,8 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_pix = fp.width * fp.height;
     const int n_box = c_scene.n_box;
+    const int n_box_groups = c_scene.n_box_groups, n_plane_run = c_scene.n_plane_run, n_sphere_groups = c_scene.n_sphere_groups;
+    const int plane_off4 = c_scene.plane_off4, sphere_off4 = c_scene.sphere_off4, n_typed = c_scene.n_typed, sphere_base = n_box + n_plane_run;
     unsigned long long st[STATS ? kStatsWords : 1] = {0};
 
 #pragma unroll
@@ -333,16 +335,43 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
                 ray[k] = make_ray(f3(S.ox[j], S.oy[j], S.oz[j]), f3(S.dx[j], S.dy[j], S.dz[j]));
                 best[k] = FLT_MAX; bid[k] = -1;
             }
-#pragma unroll 2
-            for (int i = 0; i < n_box; ++i) {
-                const float4 lo = obj_lo(i), hi = obj_hi(i);
+            const float4* tab4 = reinterpret_cast<const float4*>(c_scene.scan_tab);
+            for (int gi = 0; gi < n_box_groups; ++gi) {              // kBoxGroup boxes per trip, 6 floats each (scene_dev.h)
+                const float4* q = tab4 + gi * (kBoxGroup * 6 / 4);
+                float bx[kBoxGroup * 6];
+#pragma unroll
+                for (int v = 0; v < kBoxGroup * 6 / 4; ++v) { const float4 w = q[v]; bx[4 * v] = w.x; bx[4 * v + 1] = w.y; bx[4 * v + 2] = w.z; bx[4 * v + 3] = w.w; }
+#pragma unroll
+                for (int u = 0; u < kBoxGroup; ++u) {
+                    const float4 lo = make_float4(bx[6 * u], bx[6 * u + 1], bx[6 * u + 2], 0.0f);
+                    const float4 hi = make_float4(bx[6 * u + 3], bx[6 * u + 4], bx[6 * u + 5], 0.0f);
+#pragma unroll
+                    for (int k = 0; k < WF_SG; ++k) {
+                        float t;
+                        if (hit_box(lo, hi, ray[k], 0.001f, best[k], t)) { best[k] = t; bid[k] = gi * kBoxGroup + u; }
+                    }
+                }
+            }
+            for (int i = 0; i < n_plane_run; ++i) {
+                const float py = c_scene.scan_tab[plane_off4 * 4 + i];
 #pragma unroll
                 for (int k = 0; k < WF_SG; ++k) {
                     float t;
-                    if (hit_box(lo, hi, ray[k], 0.001f, best[k], t)) { best[k] = t; bid[k] = i; }
+                    if (hit_plane1(py, ray[k], 0.001f, best[k], t)) { best[k] = t; bid[k] = n_box + i; }
                 }
             }
-            for (int i = n_box; i < n_obj; ++i) {
+            for (int gi = 0; gi < n_sphere_groups; ++gi) {
+#pragma unroll
+                for (int u = 0; u < kSphereGroup; ++u) {
+                    const float4 sp = tab4[sphere_off4 + gi * kSphereGroup + u];
+#pragma unroll
+                    for (int k = 0; k < WF_SG; ++k) {
+                        float t;
+                        if (hit_sphere4(sp.x, sp.y, sp.z, sp.w, ray[k], 0.001f, best[k], t)) { best[k] = t; bid[k] = sphere_base + gi * kSphereGroup + u; }
+                    }
+                }
+            }
+            for (int i = n_typed; i < n_obj; ++i) {                  // whatever follows the typed runs in world order
                 const float4 lo = obj_lo(i), hi = obj_hi(i);
                 const bool is_sphere = (__float_as_int(lo.w) & 3) == PTB_OBJ_SPHERE;
 #pragma unroll

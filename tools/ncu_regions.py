@@ -7,9 +7,9 @@ def find(src,pat,start=0): return next(i for i,l in enumerate(src) if i>=start a
 mi=[("rng",find(srcI,"struct Rng")-8),("vec helpers",find(srcI,"struct F3")),("in_unit_sphere",find(srcI,"F3 in_unit_sphere")),("cosine_direction",find(srcI,"F3 cosine_direction")-1),
 ("make_ray",find(srcI,"struct RayK")-3),("hit box",find(srcI,"bool hit_box")-7),("hit sphere",find(srcI,"bool hit_sphere")-1),("hit plane",find(srcI,"bool hit_plane")-1),("obj load/hit_any",find(srcI,"float4 obj_lo")-1),
 ("surface",find(srcI,"void surface")-1),("sky",find(srcI,"F3 sky_color")),("to_u8",find(srcI,"uint8_t to_u8")-1),("megakernel",find(srcI,"integrate_kernel(const __grid_constant__")-2)]
-mw=[("wf prologue",1),("wf regen",find(srcW,"auto regen")),("wf init",find(srcW,"S.pix[j] = -1; S.smp")),("wf scan",find(srcW,"SCAN (thread")),("wf sort",find(srcW,"SORT (stable")),
-("wf shade: load+surface",find(srcW,"SHADE (one class per")),("wf shade: common",find(srcW,"draws consumed by this bounce")),("wf shade: diffuse",find(srcW,"} else if (c == CL_DIFFUSE)")),("wf shade: dielectric",find(srcW,"} else if (c == CL_DIEL)")),
-("wf exit search",find(srcW,"if (front) {")),("wf RR/update",find(srcW,"bool done = !ok;")),("wf term",find(srcW,"} else if (c == CL_TERM)")),("wf regen call+barrier",find(srcW,"if (c == CL_TERM || c == CL_REGEN) regen")),("wf epilogue",find(srcW,"if (c == CL_TERM || c == CL_REGEN) regen")+3)]
+mw=[("wf prologue",1),("wf regen",find(srcW,"void path_regen")-1),("wf shade: load+surface",find(srcW,"void path_shade")-1),("wf shade: common",find(srcW,"draws consumed by this bounce")),
+("wf shade: diffuse",find(srcW,"} else if (c == CL_DIFFUSE)")),("wf shade: dielectric",find(srcW,"} else if (c == CL_DIEL)")),("wf exit search",find(srcW,"if (front) {")),
+("wf RR/update",find(srcW,"bool done = !ok;")),("wf term",find(srcW,"} else if (c == CL_TERM)")),("wf kernel prologue",find(srcW,"integrate_wf_kernel(const __grid_constant__")-2),("wf scan",find(srcW,"SCAN (thread")),("wf sort",find(srcW,"SORT (stable")),("wf shade loop+barrier",find(srcW,"SHADE (one class per")),("wf epilogue",find(srcW,"if (STATS) {",find(srcW,"SHADE (one class per")))]
 def region(f,line):
     marks = mi if f=="integrator.cu" else mw if f=="wavefront.cuh" else None
     if marks is None: return "other:"+f
