@@ -450,7 +450,7 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
         if (w.type == PTB_OBJ_SPHERE) {
             float r = (float)w.b[0];
             o.bx = r; o.by = r * r; o.bz = 1.0f / r;    // radiusSq (objects.go:46), invRadius (objects.go:68)
-        } else if (w.type == PTB_OBJ_BOX && PTB_BOX_CH) {      // (centre, half extent), see hit_box
+        } else if (w.type == PTB_OBJ_BOX) {      // (centre, half extent), see hit_box
             o.ax = (float)((w.a[0] + w.b[0]) * 0.5); o.ay = (float)((w.a[1] + w.b[1]) * 0.5); o.az = (float)((w.a[2] + w.b[2]) * 0.5);
             o.bx = (float)((w.b[0] - w.a[0]) * 0.5); o.by = (float)((w.b[1] - w.a[1]) * 0.5); o.bz = (float)((w.b[2] - w.a[2]) * 0.5);
         } else { o.bx = (float)w.b[0]; o.by = (float)w.b[1]; o.bz = (float)w.b[2]; }

@@ -149,35 +149,19 @@ __device__ __forceinline__ RayK make_ray(F3 o, F3 d) {
 // direction component exactly 0) is dropped by min/max instead of poisoning the comparison; the binary64
 // parity kernel keeps the reference's exact form.]
 __device__ __forceinline__ bool hit_box(float4 lo, float4 hi, const RayK& r, float tmin, float tmax, float& t_out) {
-#if PTB_FAST_MATH && PTB_BOX_CH
+#if PTB_FAST_MATH
     // record = (centre c, half extent h >= 0): the slab interval of an axis is (c - o)/d -+ h/|d|, so near and far come
-    // out ordered and the per-axis min/max pair (half-rate ALU pipe) disappears: 9 FMA-pipe ops + 4 three-input min/max.
+    // out ordered and the per-axis min/max pair (half-rate ALU pipe) disappears: 9 FFMA (|1/d| is an operand modifier)
+    // + 2 three-input and 2 two-input min/max.
     const float cx = fmaf(lo.x, r.inv.x, -r.oi.x), cy = fmaf(lo.y, r.inv.y, -r.oi.y), cz = fmaf(lo.z, r.inv.z, -r.oi.z);
-#if PTB_BOX_CH == 1
     const float nx = fmaf(-hi.x, r.ainv.x, cx), ny = fmaf(-hi.y, r.ainv.y, cy), nz = fmaf(-hi.z, r.ainv.z, cz);
     const float fx = fmaf(hi.x, r.ainv.x, cx), fy = fmaf(hi.y, r.ainv.y, cy), fz = fmaf(hi.z, r.ainv.z, cz);
-#else
-    const float hx = hi.x * r.inv.x, hy = hi.y * r.inv.y, hz = hi.z * r.inv.z;
-    const float nx = cx - fabsf(hx), ny = cy - fabsf(hy), nz = cz - fabsf(hz);
-    const float fx = cx + fabsf(hx), fy = cy + fabsf(hy), fz = cz + fabsf(hz);
-#endif
     const float t0 = fmaxf(fmaxf(fmaxf(nx, ny), nz), tmin);
     const float t1 = fminf(fminf(fminf(fx, fy), fz), tmax);
 #else
-#if PTB_BOX_CH
-    const float lx = lo.x - hi.x, ly = lo.y - hi.y, lz = lo.z - hi.z, ux = lo.x + hi.x, uy = lo.y + hi.y, uz = lo.z + hi.z;
-#else
-    const float lx = lo.x, ly = lo.y, lz = lo.z, ux = hi.x, uy = hi.y, uz = hi.z;
-#endif
-#if PTB_FAST_MATH
-    const float ax = fmaf(lx, r.inv.x, -r.oi.x), bx = fmaf(ux, r.inv.x, -r.oi.x);
-    const float ay = fmaf(ly, r.inv.y, -r.oi.y), by = fmaf(uy, r.inv.y, -r.oi.y);
-    const float az = fmaf(lz, r.inv.z, -r.oi.z), bz = fmaf(uz, r.inv.z, -r.oi.z);
-#else
-    const float ax = (lx - r.o.x) * r.inv.x, bx = (ux - r.o.x) * r.inv.x;
-    const float ay = (ly - r.o.y) * r.inv.y, by = (uy - r.o.y) * r.inv.y;
-    const float az = (lz - r.o.z) * r.inv.z, bz = (uz - r.o.z) * r.inv.z;
-#endif
+    const float ax = (lo.x - hi.x - r.o.x) * r.inv.x, bx = (lo.x + hi.x - r.o.x) * r.inv.x;
+    const float ay = (lo.y - hi.y - r.o.y) * r.inv.y, by = (lo.y + hi.y - r.o.y) * r.inv.y;
+    const float az = (lo.z - hi.z - r.o.z) * r.inv.z, bz = (lo.z + hi.z - r.o.z) * r.inv.z;
     const float t0 = fmaxf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)), tmin);
     const float t1 = fminf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), tmax);
 #endif
@@ -243,23 +227,21 @@ __device__ __forceinline__ void surface(const DevObj& ob, int type, F3 o, F3 d, 
     } else if (type == PTB_OBJ_PLANE) {
         on = f3(0.0f, 1.0f, 0.0f);
     } else {
-#if PTB_BOX_CH
-        const float qx = p.x - ob.ax, qy = p.y - ob.ay, qz = p.z - ob.az;     // record = (centre, half extent)
-        float dxMin = qx + ob.bx, dxMax = ob.bx - qx;
-        float dyMin = qy + ob.by, dyMax = ob.by - qy;
-        float dzMin = qz + ob.bz, dzMax = ob.bz - qz;
-#else
-        float dxMin = p.x - ob.ax, dxMax = ob.bx - p.x;
-        float dyMin = p.y - ob.ay, dyMax = ob.by - p.y;
-        float dzMin = p.z - ob.az, dzMax = ob.bz - p.z;
-#endif
-        float md = dxMin;
-        on = f3(-1.0f, 0.0f, 0.0f);
-        if (dxMax < md) { md = dxMax; on = f3(1.0f, 0.0f, 0.0f); }
-        if (dyMin < md) { md = dyMin; on = f3(0.0f, -1.0f, 0.0f); }
-        if (dyMax < md) { md = dyMax; on = f3(0.0f, 1.0f, 0.0f); }
-        if (dzMin < md) { md = dzMin; on = f3(0.0f, 0.0f, -1.0f); }
-        if (dzMax < md) { on = f3(0.0f, 0.0f, 1.0f); }
+        // Nearest face in the reference's order -x,+x,-y,+y,-z,+z with strict '<' (objects.go:188-217).  With the record
+        // (centre c, half extent h) and q = p - c the two face distances of an axis are h + q and h - q: their minimum is
+        // h - |q| and it is the + face iff q > 0; across axes the earlier axis keeps a tie.  (Differs from the sequential
+        // form only if |q| < ulp(h) on the chosen axis, i.e. never for a point on a face.)
+        const float qx = p.x - ob.ax, qy = p.y - ob.ay, qz = p.z - ob.az;
+        const float mx = ob.bx - fabsf(qx), my = ob.by - fabsf(qy), mz = ob.bz - fabsf(qz);
+        const bool py = my < mx;
+        const float mxy = py ? my : mx;
+        const bool pz = mz < mxy;
+        const float qa = pz ? qz : (py ? qy : qx), da = pz ? d.z : (py ? d.y : d.x);
+        const float sgn = qa > 0.0f ? 1.0f : -1.0f;
+        front = da * sgn < 0.0f;
+        const float v = front ? sgn : -sgn;
+        n = f3((py || pz) ? 0.0f : v, (py && !pz) ? v : 0.0f, pz ? v : 0.0f);
+        return;
     }
     front = dot3(d, on) < 0.0f;
     n = front ? on : f3(-on.x, -on.y, -on.z);
@@ -274,25 +256,12 @@ __device__ __forceinline__ bool front_face_only(const DevObj& ob, int type, F3 o
     if (type == PTB_OBJ_PLANE) return d.y < 0.0f;
     // box: nearest face in the reference's order -x,+x,-y,+y,-z,+z with strict '<' (objects.go:188-217); the face
     // normal is +-e_axis, so d.n = +-d[axis]
-#if PTB_BOX_CH
-    const float qx = p.x - ob.ax, qy = p.y - ob.ay, qz = p.z - ob.az;
-    float md = qx + ob.bx, dn = -d.x;
-    float q;
-    q = ob.bx - qx; if (q < md) { md = q; dn = d.x; }
-    q = qy + ob.by; if (q < md) { md = q; dn = -d.y; }
-    q = ob.by - qy; if (q < md) { md = q; dn = d.y; }
-    q = qz + ob.bz; if (q < md) { md = q; dn = -d.z; }
-    q = ob.bz - qz; if (q < md) { dn = d.z; }
-#else
-    float md = p.x - ob.ax, dn = -d.x;
-    float q;
-    q = ob.bx - p.x; if (q < md) { md = q; dn = d.x; }
-    q = p.y - ob.ay; if (q < md) { md = q; dn = -d.y; }
-    q = ob.by - p.y; if (q < md) { md = q; dn = d.y; }
-    q = p.z - ob.az; if (q < md) { md = q; dn = -d.z; }
-    q = ob.bz - p.z; if (q < md) { dn = d.z; }
-#endif
-    return dn < 0.0f;
+    const float qx = p.x - ob.ax, qy = p.y - ob.ay, qz = p.z - ob.az;      // see surface()
+    const float mx = ob.bx - fabsf(qx), my = ob.by - fabsf(qy), mz = ob.bz - fabsf(qz);
+    const bool py = my < mx;
+    const bool pz = mz < (py ? my : mx);
+    const float qa = pz ? qz : (py ? qy : qx), da = pz ? d.z : (py ? d.y : d.x);
+    return (qa > 0.0f ? da : -da) < 0.0f;
 }
 
 __device__ __forceinline__ F3 sky_color(F3 d) {                                                   // renderer.go:56-92

@@ -13,17 +13,11 @@
 
 namespace ptb {
 
-// PTB_BOX_CH: 0 = box records hold (min, max); 1/2 = (centre, half extent) so the slab test needs no per-axis min/max
-// (1: |1/d| kept in registers, 2: |h/d| through the FADD abs modifier).
-#ifndef PTB_BOX_CH
-#define PTB_BOX_CH 1
-#endif
-
 // 32-byte records, two 16-byte vector loads each.
 struct alignas(16) DevObj {
-    float ax, ay, az;   // sphere centre | plane point | box min            (objects.go:31-35, 92-96, 136-139)
+    float ax, ay, az;   // sphere centre | plane point | box CENTRE         (objects.go:31-35, 92-96, 136-139)
     int32_t meta;       // bits 0..1 type, bit 2 dielectric material, bits 3..5 shading class (wavefront.cuh), bits 6.. material index
-    float bx, by, bz;   // sphere (radius, radius^2, 1/radius) | plane unused | box max
+    float bx, by, bz;   // sphere (radius, radius^2, 1/radius) | plane unused | box HALF EXTENT (see hit_box)
     int32_t world_idx;  // index in the reference's world order (device order groups boxes first)
 };
 

@@ -61,7 +61,7 @@ struct SlotState {                     // path state, SoA, one entry per slot
 };
 struct WfState : SlotState<WF_SLOTS> {
     unsigned short perm[WF_SLOTS];     // slot | class << 12
-    int cnt[CL_COUNT * WF_WARPS];
+    alignas(4) unsigned short cnt[CL_COUNT * WF_WARPS];
 };
 
 // Finish the slot's current sample and give it its next camera ray: next sample of the same pixel, or — when the
@@ -405,55 +405,58 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
 
         PTB_TICK(0)
         // ------------------------------------------------------------ SORT (stable counting sort of the CTA's slots by class)
-        unsigned mine = 0u;                 // lane c < CL_COUNT: this warp's number of class-c slots
+        // In-warp ranks from ballots of the three class BITS (not one ballot per class): the lanes whose row-r class
+        // equals class c are AND_b (B[r][b] ^ nmask_b(c)), nmask_b(c) = 0 if bit b of c is set, else ~0.
         unsigned before[WF_SPT];            // slots of the same class that precede mine inside this warp
+        unsigned mine = 0u;                 // lane c < CL_COUNT: this warp's number of class-c slots
         {
-            unsigned run_c[WF_SPT];
+            unsigned B[WF_SPT][3];
 #pragma unroll
-            for (int k = 0; k < WF_SPT; ++k) { before[k] = 0u; run_c[k] = 0u; }
+            for (int k = 0; k < WF_SPT; ++k)
 #pragma unroll
-            for (int c = 0; c < CL_COUNT; ++c) {
-                unsigned tot = 0u;
+                for (int b = 0; b < 3; ++b) B[k][b] = __ballot_sync(0xffffffffu, (cls[k] >> b) & 1);
+            const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
-                for (int k = 0; k < WF_SPT; ++k) {
-                    const unsigned m = __ballot_sync(0xffffffffu, cls[k] == c);
-                    if (cls[k] == c) before[k] = tot + __popc(m & ((1u << lane) - 1u));
-                    tot += __popc(m);
-                }
-                if (lane == c) mine = tot;
+            for (int k = 0; k < WF_SPT; ++k) {
+                const unsigned n0 = (cls[k] & 1) ? 0u : ~0u, n1 = (cls[k] & 2) ? 0u : ~0u, n2 = (cls[k] & 4) ? 0u : ~0u;
+                unsigned acc = 0u;
+#pragma unroll
+                for (int r = 0; r < k; ++r) acc += __popc((B[r][0] ^ n0) & (B[r][1] ^ n1) & (B[r][2] ^ n2));
+                before[k] = acc + __popc((B[k][0] ^ n0) & (B[k][1] ^ n1) & (B[k][2] ^ n2) & lt);
             }
+            const unsigned l0 = (lane & 1) ? 0u : ~0u, l1 = (lane & 2) ? 0u : ~0u, l2 = (lane & 4) ? 0u : ~0u;
+#pragma unroll
+            for (int r = 0; r < WF_SPT; ++r) mine += __popc((B[r][0] ^ l0) & (B[r][1] ^ l1) & (B[r][2] ^ l2));
         }
-        if (lane < CL_COUNT) S.cnt[lane * WF_WARPS + warp] = (int)mine;
+        if (lane < CL_COUNT) S.cnt[lane * WF_WARPS + warp] = (unsigned short)mine;
         PTB_TICK(1)
         __syncthreads();
         PTB_MARK()
-        // exclusive prefix over the CL_COUNT x WF_WARPS (class-major, warp-minor) counts, redundantly in every warp
-        constexpr int kEntries = CL_COUNT * WF_WARPS, kChunks = (kEntries + 31) / 32;
-        int run = 0, n_dead = 0;
+        // exclusive prefix over the CL_COUNT x WF_WARPS (class-major, warp-minor) counts, redundantly in every warp: lane l
+        // owns entries 2l and 2l+1 (one 32-bit load of two 16-bit counts), one 5-step scan of the pair sums
+        static_assert(CL_COUNT * WF_WARPS <= 64 && WF_WARPS % 2 == 0 && WF_SLOTS < 65536, "pair-packed prefix");
         int base[WF_SPT];
-#pragma unroll
-        for (int k = 0; k < WF_SPT; ++k) base[k] = 0;
-#pragma unroll
-        for (int q = 0; q < kChunks; ++q) {
-            const int e = (q * 32 + lane < kEntries) ? S.cnt[q * 32 + lane] : 0;
-            int inc = e;
+        int n_dead;
+        {
+            constexpr int kPairs = CL_COUNT * WF_WARPS / 2;
+            const unsigned pr = lane < kPairs ? reinterpret_cast<const unsigned*>(S.cnt)[lane] : 0u;
+            const unsigned e0 = pr & 0xFFFFu, e1 = pr >> 16;
+            unsigned inc = e0 + e1;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
-                const int a = __shfl_up_sync(0xffffffffu, inc, off);
+                const unsigned a = __shfl_up_sync(0xffffffffu, inc, off);
                 if (lane >= off) inc += a;
             }
-            const int ex = inc - e + run;
+            const unsigned ex0 = inc - e0 - e1;
+            const unsigned packed = ex0 | ((ex0 + e0) << 16);      // exclusive prefixes of entries 2l (low) and 2l+1 (high)
+            const int sh = (warp & 1) * 16;                           // entry index = class * WF_WARPS + warp: its parity is the warp's
 #pragma unroll
             for (int k = 0; k < WF_SPT; ++k) {
                 const int idx = cls[k] * WF_WARPS + warp;
-                const int b = __shfl_sync(0xffffffffu, ex, idx & 31);
-                if ((idx >> 5) == q) base[k] = b;
+                base[k] = (int)((__shfl_sync(0xffffffffu, packed, idx >> 1) >> sh) & 0xFFFFu);
             }
-            // retired slots = sum of the CL_DEAD row
-            const int lo_i = CL_DEAD * WF_WARPS - q * 32, hi_i = lo_i + WF_WARPS;
-            const int mine_dead = (lane >= lo_i && lane < hi_i) ? e : 0;
-            n_dead += __reduce_add_sync(0xffffffffu, mine_dead);
-            run += __shfl_sync(0xffffffffu, inc, 31);
+            // live slots = everything sorted before the CL_DEAD row
+            n_dead = WF_SLOTS - (int)(__shfl_sync(0xffffffffu, packed, CL_DEAD * WF_WARPS / 2) & 0xFFFFu);
         }
 #pragma unroll
         for (int k = 0; k < WF_SPT; ++k)
