@@ -321,9 +321,9 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "mrays_per_s": value * rays_per_sample, "rays_per_sample": rays_per_sample,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp32_peak if fp32_peak else None, "traffic": 41472,
+                         "frac": achieved / fp32_peak if fp32_peak else None, "traffic": 51200,
                          "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one integrate_wf_kernel launch from the ncu "
-                                         "--set full capture profiles/r01e_ncu_details.txt (40 KB read, 1.5 KB written: the scene is "
+                                         "--set full capture profiles/r01j_ncu_details.txt (44 KB read, 7 KB written: the scene is "
                                          "constant/shared-memory resident and the 33 MB image stays in the 126 MB L2 for the kernel's lifetime)",
                          "kernel": "integrate_wf_kernel<false>", "kernel_ms": kernel_ms,
                          "flops_per_sample": fps, "simt_lane_utilisation": simt_util,
