@@ -52,6 +52,7 @@ struct ptb_ctx {
     int n_world64 = 0;
     BvhNode* d_bvh_nodes = nullptr;      // EXTENSION: mesh BVH
     BvhTri* d_bvh_tris = nullptr;
+    int* d_trav = nullptr; size_t trav_cap = 0;   // suspended-traversal scratch (wavefront kernel, mesh scenes)
     BvhNode* d_bvh_nodes_keep = nullptr; // last built BVH, reused when the same triangles are uploaded again
     BvhTri* d_bvh_tris_keep = nullptr;
     ptb_bvh_info bvh_keep{};
@@ -221,6 +222,11 @@ int render_launch(ptb_ctx* c, const ptb_cfg* cfg, int s0, int s1, float* d_accum
     fp.inv_w = 1.0f / (float)(W - 1); fp.inv_h = 1.0f / (float)(H - 1); fp.h_minus_1 = (float)(H - 1);
     fp.scene_blob = c->d_blob; fp.accum = d_accum; fp.accum_resume = resume ? 1 : 0; fp.rgba = d_rgba; fp.stats = (stats || dbg_timing) ? c->d_stats : nullptr;
     fp.bvh_nodes = (const float4*)c->d_bvh_nodes; fp.bvh_tris = (const float4*)c->d_bvh_tris;
+    if (c->d_bvh_nodes) {
+        int rc = ensure(c, (void**)&c->d_trav, &c->trav_cap, wf_trav_scratch_bytes(c->prop.multiProcessorCount));
+        if (rc) return rc;
+        fp.trav_scratch = c->d_trav;
+    }
     const bool mega = (cfg->flags & PTB_FLAG_MEGAKERNEL) != 0 || cfg->max_depth <= 0;
     if (mega && cfg->max_depth > 0 && c->d_bvh_nodes) return fail(c, PTB_ERR_INVALID, "the megakernel integrator does not support meshes");
     if (mega) {
@@ -310,7 +316,7 @@ void ptb_destroy(ptb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_blob); cudaFree(c->d_world64); cudaFree(c->d_bvh_nodes_keep); cudaFree(c->d_bvh_tris_keep); cudaFree(c->d_accum); cudaFree(c->d_rgba); cudaFree(c->d_stats); cudaFree(c->d_work);
+    cudaFree(c->d_trav); cudaFree(c->d_blob); cudaFree(c->d_world64); cudaFree(c->d_bvh_nodes_keep); cudaFree(c->d_bvh_tris_keep); cudaFree(c->d_accum); cudaFree(c->d_rgba); cudaFree(c->d_stats); cudaFree(c->d_work);
     if (c->h_scene) cudaFreeHost(c->h_scene);
     if (c->h_rgba) cudaFreeHost(c->h_rgba);
     if (c->ev0) cudaEventDestroy(c->ev0);

@@ -627,6 +627,9 @@ int launch_integrator(const FrameParams& fp, bool stats, int n_obj, int n_mat, v
     return (int)cudaGetLastError();
 }
 
+constexpr int kMeshBlocksPerSm = PTB_WF_MIN_BLOCKS;
+size_t wf_trav_scratch_bytes(int sm_count) { return (size_t)sm_count * kMeshBlocksPerSm * WF_SLOTS * kTravStride * sizeof(int); }
+
 template <bool STATS, bool MESH>
 static int launch_wf_variant(const FrameParams& fp, size_t smem, int sm_count, cudaStream_t stream) {
     static int blocks_per_sm = 0;
@@ -638,7 +641,7 @@ static int launch_wf_variant(const FrameParams& fp, size_t smem, int sm_count, c
         blocks_per_sm = nb > 0 ? nb : 1;
     }
     const long long n_pix = (long long)fp.width * fp.height;
-    long long grid = (long long)sm_count * blocks_per_sm;
+    long long grid = (long long)sm_count * (MESH && blocks_per_sm > kMeshBlocksPerSm ? kMeshBlocksPerSm : blocks_per_sm);   // trav_scratch is sized for kMeshBlocksPerSm
     const long long need = (n_pix + WF_SLOTS - 1) / WF_SLOTS;
     if (grid > need) grid = need;
     integrate_wf_kernel<STATS, MESH><<<(unsigned)grid, WF_THREADS, smem, stream>>>(fp);

@@ -86,6 +86,7 @@ struct FrameParams {
     unsigned int* work_counter;  // wavefront kernel: next unassigned pixel index (zeroed before the launch)
     const float4* bvh_nodes;     // EXTENSION: BVH over the mesh triangles (bvh.h), nullptr when the scene has no mesh
     const float4* bvh_tris;
+    int* trav_scratch;           // kTravStride ints per path slot of the launch (suspended traversals), mesh scenes only
 };
 
 enum StatWord {
@@ -99,6 +100,7 @@ enum StatWord {
 int upload_scene_constants(const DevScene& host_scene, void* stream);
 int launch_integrator(const FrameParams& fp, bool stats, int n_obj, int n_mat, void* stream);
 int launch_integrator_wf(const FrameParams& fp, bool stats, int n_obj, int n_mat, int sm_count, void* stream);
+size_t wf_trav_scratch_bytes(int sm_count);      // size of FrameParams::trav_scratch the mesh instantiation needs
 int launch_integrator_wq(const FrameParams& fp, bool stats, int n_obj, int n_mat, int sm_count, void* stream);
 int launch_finalize(const float* accum, int width, int height, int spp_total, uint8_t* rgba, void* stream);
 int launch_primary_hits(const Obj64* d_world, int n_obj, const float4* bvh_nodes, const float4* bvh_tris, const Camera64& cam,

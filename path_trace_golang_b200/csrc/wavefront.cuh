@@ -44,7 +44,8 @@ constexpr int WF_CHUNKS = WF_SLOTS / 32;
 // (longest-processing-time-first keeps the phase balanced), TERM and REGEN adjacent (they share the regeneration code).
 // CL_DIEL..CL_SPEC match the class bits the host writes into DevObj::meta (api.cu).
 // Measured chunk costs on C3 (cycles, -DPTB_WF_TIMING): DIEL 5500, TERM 3450, REGEN 2740, DIFFUSE 2210, SPEC 1630.
-enum : int { CL_DIEL = 0, CL_TERM = 1, CL_REGEN = 2, CL_DIFFUSE = 3, CL_SPEC = 4, CL_DEAD = 5, CL_COUNT = 6 };
+// CL_CONT (MESH only): the slot's BVH traversal ran out of its per-iteration step budget and continues next iteration.
+enum : int { CL_DIEL = 0, CL_TERM = 1, CL_REGEN = 2, CL_DIFFUSE = 3, CL_SPEC = 4, CL_CONT = 5, CL_DEAD = 6, CL_COUNT = 7 };
 
 template <int N>
 struct SlotState {                     // path state, SoA, one entry per slot
@@ -62,6 +63,7 @@ struct SlotState {                     // path state, SoA, one entry per slot
 struct WfState : SlotState<WF_SLOTS> {
     unsigned short perm[WF_SLOTS];     // slot | class << 12
     alignas(4) unsigned short cnt[CL_COUNT * WF_WARPS];
+    unsigned char trav[WF_SLOTS];      // MESH: 1 = the slot's traversal is suspended (state in FrameParams::trav_scratch)
 };
 
 // Finish the slot's current sample and give it its next camera ray: next sample of the same pixel, or — when the
@@ -303,7 +305,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
 #pragma unroll
     for (int k = 0; k < WF_SPT; ++k) {
         const int j = tid + k * WF_THREADS;
-        S.pix[j] = -1; S.smp[j] = 0; S.depth[j] = 0;
+        S.pix[j] = -1; S.smp[j] = 0; S.depth[j] = 0; S.trav[j] = 0;
         S.ox[j] = 0.f; S.oy[j] = 0.f; S.oz[j] = 0.f; S.dx[j] = 0.f; S.dy[j] = 0.f; S.dz[j] = 1.f;
         if (fp.max_depth > 0) path_regen<STATS>(S, fp, n_pix, j, false, st);
     }
@@ -381,11 +383,21 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
                     if (h) { best[k] = t; bid[k] = i; }
                 }
             }
+            bool susp[WF_SG];
+#pragma unroll
+            for (int k = 0; k < WF_SG; ++k) susp[k] = false;
             if (MESH) {                      // EXTENSION: triangle meshes, tested after the analytic objects (bvh.cuh)
 #pragma unroll 1
                 for (int k = 0; k < WF_SG; ++k) {
                     const int j = tid + (g + k) * WF_THREADS;
-                    if (S.pix[j] >= 0 && S.depth[j] > 0) bvh_closest<STATS>(fp.bvh_nodes, fp.bvh_tris, ray[k], 0.001f, best[k], bid[k], st);
+                    if (S.pix[j] >= 0 && S.depth[j] > 0) {
+                        const bool resume = S.trav[j] != 0;
+                        if (resume) { best[k] = S.best[j]; bid[k] = S.bid[j]; }      // the analytic result is already folded in
+                        int* save = fp.trav_scratch + ((size_t)blockIdx.x * WF_SLOTS + j) * kTravStride;
+                        const bool fin = bvh_closest<STATS>(fp.bvh_nodes, fp.bvh_tris, ray[k], 0.001f, best[k], bid[k], st, save, resume, PTB_BVH_STEP_BUDGET);
+                        S.trav[j] = fin ? 0 : 1;
+                        susp[k] = !fin;
+                    }
                 }
             }
 #pragma unroll
@@ -394,12 +406,13 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
                 int c;
                 if (S.pix[j] < 0) c = CL_DEAD;
                 else if (S.depth[j] <= 0) c = CL_REGEN;
+                else if (MESH && susp[k]) c = CL_CONT;
                 else if (bid[k] < 0) c = CL_TERM;
                 else if (MESH && (bid[k] & kTriBit)) c = (__float_as_int(__ldg(fp.bvh_tris + 3 * (bid[k] & ~kTriBit) + 1).w) >> 3) & 7;
                 else c = (s_obj[bid[k]].meta >> 3) & 7;
                 cls[g + k] = c;
                 S.best[j] = best[k]; S.bid[j] = bid[k];
-                if (STATS) { st[ST_LANE_TOTAL]++; if (c != CL_DEAD && c != CL_REGEN) { st[ST_LANE_ACTIVE]++; st[ST_SEGMENTS]++; } }
+                if (STATS) { st[ST_LANE_TOTAL]++; if (c != CL_DEAD && c != CL_REGEN) { st[ST_LANE_ACTIVE]++; if (c != CL_CONT) st[ST_SEGMENTS]++; } }
             }
         }
 
