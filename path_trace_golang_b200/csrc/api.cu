@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cfloat>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -490,7 +491,14 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
     // EXTENSION: BVH over the mesh triangles
     c->d_bvh_nodes = nullptr; c->d_bvh_tris = nullptr;      // (the kept copy is freed when a different mesh set arrives)
     c->bvh = ptb_bvh_info{};
+    for (int k = 0; k < 4; k++) { hs.mesh_c[k] = 0.0f; hs.mesh_h[k] = -1.0f; }
     if (!tri_world.empty()) {
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        for (size_t q = 0; q < tri_v.size(); q++) { const float v = tri_v[q]; const int a = (int)(q % 3); lo[a] = std::min(lo[a], v); hi[a] = std::max(hi[a], v); }
+        for (int k = 0; k < 3; k++) {        // padded like the BVH boxes so that the prefilter never rejects what the root would accept
+            const float pad = 1e-5f * std::max(1.0f, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
+            hs.mesh_c[k] = 0.5f * (lo[k] + hi[k]); hs.mesh_h[k] = 0.5f * (hi[k] - lo[k]) + 2.0f * pad;
+        }
         std::vector<int32_t> tri_meta(tri_world.size());
         for (size_t q = 0; q < tri_world.size(); q++) tri_meta[q] = meta_of(world[tri_world[q]]);
         // Re-uploading the same meshes (RenderInto takes the scene on every call, renderer.go:34) must not rebuild the BVH:

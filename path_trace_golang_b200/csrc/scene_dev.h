@@ -52,6 +52,7 @@ struct DevScene {                        // ~55 KB of the 64 KB constant bank
     //   spheres 4 floats each (centre, radius^2), padded to whole groups of kSphereGroup with never-hit spheres (r^2 = -1).
     int32_t n_box_groups, n_plane_run, n_sphere_run, n_sphere_groups;
     int32_t plane_off4, sphere_off4, n_typed, pad_;                       // offsets in float4 units; n_typed = first "rest" index
+    float mesh_c[4], mesh_h[4];          // EXTENSION: bounds of all mesh triangles as (centre, half extent); h = -1 without meshes
     alignas(16) float scan_tab[PTB_MAX_OBJECTS * 6 + 16];
     DevSky sky;
     DevCamera cam;

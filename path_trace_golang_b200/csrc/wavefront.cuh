@@ -64,6 +64,7 @@ struct WfState : SlotState<WF_SLOTS> {
     unsigned short perm[WF_SLOTS];     // slot | class << 12
     alignas(4) unsigned short cnt[CL_COUNT * WF_WARPS];
     unsigned char trav[WF_SLOTS];      // MESH: 1 = the slot's traversal is suspended (state in FrameParams::trav_scratch)
+    int n_list, next_chunk;            // MESH: compacted list of slots to traverse (in perm[]) and its chunk dispenser
 };
 
 // Finish the slot's current sample and give it its next camera ray: next sample of the same pixel, or — when the
@@ -309,6 +310,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
         S.ox[j] = 0.f; S.oy[j] = 0.f; S.oz[j] = 0.f; S.dx[j] = 0.f; S.dy[j] = 0.f; S.dz[j] = 1.f;
         if (fp.max_depth > 0) path_regen<STATS>(S, fp, n_pix, j, false, st);
     }
+    if (tid == 0) { S.n_list = 0; S.next_chunk = 0; }
     __syncthreads();
 
 #ifdef PTB_WF_TIMING
@@ -383,21 +385,68 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
                     if (h) { best[k] = t; bid[k] = i; }
                 }
             }
-            bool susp[WF_SG];
+            if (MESH) {
+                // EXTENSION: triangle meshes, tested after the analytic objects (bvh.cuh).  Only rays that reach the meshes'
+                // bounds before their analytic hit (or whose traversal was suspended) are traversed, and they are compacted
+                // CTA-wide first: a warp walks the BVH with 32 such rays instead of the few its own slots happen to hold.
+                static_assert(WF_SPT == WF_SG, "the mesh path compacts all of a thread's slots at once");
+                const float4 mc = make_float4(c_scene.mesh_c[0], c_scene.mesh_c[1], c_scene.mesh_c[2], 0.0f);
+                const float4 mh = make_float4(c_scene.mesh_h[0], c_scene.mesh_h[1], c_scene.mesh_h[2], 0.0f);
 #pragma unroll
-            for (int k = 0; k < WF_SG; ++k) susp[k] = false;
-            if (MESH) {                      // EXTENSION: triangle meshes, tested after the analytic objects (bvh.cuh)
-#pragma unroll 1
                 for (int k = 0; k < WF_SG; ++k) {
                     const int j = tid + (g + k) * WF_THREADS;
-                    if (S.pix[j] >= 0 && S.depth[j] > 0) {
-                        const bool resume = S.trav[j] != 0;
-                        if (resume) { best[k] = S.best[j]; bid[k] = S.bid[j]; }      // the analytic result is already folded in
-                        int* save = fp.trav_scratch + ((size_t)blockIdx.x * WF_SLOTS + j) * kTravStride;
-                        const bool fin = bvh_closest<STATS>(fp.bvh_nodes, fp.bvh_tris, ray[k], 0.001f, best[k], bid[k], st, save, resume, PTB_BVH_STEP_BUDGET);
-                        S.trav[j] = fin ? 0 : 1;
-                        susp[k] = !fin;
+                    const bool live = S.pix[j] >= 0 && S.depth[j] > 0;
+                    const bool resume = live && S.trav[j] != 0;
+                    float tb;
+                    const bool need = resume || (live && hit_box(mc, mh, ray[k], 0.001f, best[k], tb));
+                    if (!resume) { S.best[j] = best[k]; S.bid[j] = bid[k]; }     // a suspended slot keeps its partial result
+                    const unsigned m = __ballot_sync(0xffffffffu, need);
+                    int base = 0;
+                    if (lane == 0 && m) base = atomicAdd(&S.n_list, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (need) S.perm[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;   // perm[] is free until the sort
+                }
+                __syncthreads();
+                const int n_list = S.n_list;
+                {   // persistent lanes: a lane whose ray finished (or ran out of budget) takes the next ray of the list
+                    int tj = -1;                     // slot this lane is traversing, -1 = none
+                    RayK tr;
+                    float tbest = 0.0f;
+                    int tbid = -1;
+                    TravState T;
+                    bool more = true;                // the list still has rays (warp-uniform)
+                    for (;;) {
+                        const unsigned idle = __ballot_sync(0xffffffffu, tj < 0);
+                        if (idle && more) {
+                            int base = 0;
+                            if (lane == 0) base = atomicAdd(&S.next_chunk, __popc(idle));
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            more = base + __popc(idle) < n_list;
+                            const int idx = base + __popc(idle & ((1u << lane) - 1u));
+                            if (tj < 0 && idx < n_list) {
+                                tj = S.perm[idx];
+                                tr = make_ray(f3(S.ox[tj], S.oy[tj], S.oz[tj]), f3(S.dx[tj], S.dy[tj], S.dz[tj]));
+                                tbest = S.best[tj]; tbid = S.bid[tj];
+                                trav_begin(T, fp.trav_scratch + ((size_t)blockIdx.x * WF_SLOTS + tj) * kTravStride, S.trav[tj] != 0, PTB_BVH_STEP_BUDGET);
+                            }
+                        }
+                        if (__ballot_sync(0xffffffffu, tj >= 0) == 0u) break;
+                        if (tj >= 0) {
+                            const int status = trav_round<STATS>(fp.bvh_nodes, fp.bvh_tris, tr, 0.001f, tbest, tbid, st, T, PTB_BVH_ROUND_NODES);
+                            if (status != 0) {
+                                if (status == 2) trav_save(T, fp.trav_scratch + ((size_t)blockIdx.x * WF_SLOTS + tj) * kTravStride);
+                                S.best[tj] = tbest; S.bid[tj] = tbid; S.trav[tj] = status == 2 ? 1 : 0;
+                                tj = -1;
+                            }
+                        }
                     }
+                }
+                __syncthreads();
+                if (tid == 0) { S.n_list = 0; S.next_chunk = 0; }                 // next use is behind the sort's barriers
+#pragma unroll
+                for (int k = 0; k < WF_SG; ++k) {
+                    const int j = tid + (g + k) * WF_THREADS;
+                    best[k] = S.best[j]; bid[k] = S.bid[j];
                 }
             }
 #pragma unroll
@@ -406,7 +455,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
                 int c;
                 if (S.pix[j] < 0) c = CL_DEAD;
                 else if (S.depth[j] <= 0) c = CL_REGEN;
-                else if (MESH && susp[k]) c = CL_CONT;
+                else if (MESH && S.trav[j] != 0) c = CL_CONT;
                 else if (bid[k] < 0) c = CL_TERM;
                 else if (MESH && (bid[k] & kTriBit)) c = (__float_as_int(__ldg(fp.bvh_tris + 3 * (bid[k] & ~kTriBit) + 1).w) >> 3) & 7;
                 else c = (s_obj[bid[k]].meta >> 3) & 7;
