@@ -15,7 +15,7 @@ constexpr int kTravStride = kTravStack + 4;     // ints of global scratch per pa
 #define PTB_BVH_STEP_BUDGET 24                 // inner-node visits per ray and wavefront iteration
 #endif
 #ifndef PTB_BVH_ROUND_NODES
-#define PTB_BVH_ROUND_NODES 4                  // inner-node visits between two refills of a warp's idle lanes
+#define PTB_BVH_ROUND_NODES 8                  // inner-node visits between two refills of a warp's idle lanes
 #endif
 
 // a*b - c*d and a 3-term dot product with a fixed rounding sequence.
