@@ -53,6 +53,7 @@ struct ptb_ctx {
     int n_world64 = 0;
     BvhNode* d_bvh_nodes = nullptr;      // EXTENSION: mesh BVH
     BvhTri* d_bvh_tris = nullptr;
+    float* d_planes = nullptr; size_t planes_cap = 0;   // partial-sum planes of split (small) frames
     int* d_trav = nullptr; size_t trav_cap = 0;   // suspended-traversal scratch (wavefront kernel, mesh scenes)
     BvhNode* d_bvh_nodes_keep = nullptr; // last built BVH, reused when the same triangles are uploaded again
     BvhTri* d_bvh_tris_keep = nullptr;
@@ -235,8 +236,18 @@ int render_launch(ptb_ctx* c, const ptb_cfg* cfg, int s0, int s1, float* d_accum
     } else {
         fp.work_counter = c->d_work;
         CK(c, cudaMemsetAsync(c->d_work, 0, sizeof(unsigned int), stream));
+        fp.split_k = 1;
         if (cfg->flags & PTB_FLAG_WAVEQUEUE) e = launch_integrator_wq(fp, stats, c->h_scene->n_obj, c->h_scene->n_mat, c->prop.multiProcessorCount, stream);
-        else e = launch_integrator_wf(fp, stats, c->h_scene->n_obj, c->h_scene->n_mat, c->prop.multiProcessorCount, stream);
+        else {
+            const int k = std::getenv("PTB_NO_SPLIT") ? 1 : wf_split_factor(c->prop.multiProcessorCount, (long long)W * H, s1 - s0);
+            if (k > 1) {                                   // small frame: (pixel, sample sub-range) work items, summed afterwards
+                int rc = ensure(c, (void**)&c->d_planes, &c->planes_cap, (size_t)k * W * H * 3 * sizeof(float));
+                if (rc) return rc;
+                fp.split_k = k; fp.planes = c->d_planes;
+            }
+            e = launch_integrator_wf(fp, stats, c->h_scene->n_obj, c->h_scene->n_mat, c->prop.multiProcessorCount, stream);
+            if (!e && k > 1) e = launch_finalize_planes(c->d_planes, k, W, H, cfg->samples_per_px, d_accum, resume ? 1 : 0, d_rgba, stream);
+        }
     }
     if (e) return fail(c, PTB_ERR_CUDA, "integrator launch: %s", cudaGetErrorString((cudaError_t)e));
     return PTB_OK;
@@ -317,7 +328,7 @@ void ptb_destroy(ptb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_trav); cudaFree(c->d_blob); cudaFree(c->d_world64); cudaFree(c->d_bvh_nodes_keep); cudaFree(c->d_bvh_tris_keep); cudaFree(c->d_accum); cudaFree(c->d_rgba); cudaFree(c->d_stats); cudaFree(c->d_work);
+    cudaFree(c->d_planes); cudaFree(c->d_trav); cudaFree(c->d_blob); cudaFree(c->d_world64); cudaFree(c->d_bvh_nodes_keep); cudaFree(c->d_bvh_tris_keep); cudaFree(c->d_accum); cudaFree(c->d_rgba); cudaFree(c->d_stats); cudaFree(c->d_work);
     if (c->h_scene) cudaFreeHost(c->h_scene);
     if (c->h_rgba) cudaFreeHost(c->h_rgba);
     if (c->ev0) cudaEventDestroy(c->ev0);

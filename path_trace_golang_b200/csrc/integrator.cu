@@ -562,6 +562,22 @@ __global__ void finalize_kernel(const float* __restrict__ accum, int n_pix, doub
     rgba[i] = make_uchar4(to_u8(a[0], inv_spp), to_u8(a[1], inv_spp), to_u8(a[2], inv_spp), 255);
 }
 
+// Split frames (FrameParams::split_k > 1): add the k partial-sum planes of every pixel in plane order, then accumulation
+// buffer and / or pixel epilogue.
+__global__ void finalize_planes_kernel(const float* __restrict__ planes, int k, int n_pix, float* __restrict__ accum, int accum_resume,
+                                       double inv_spp, uchar4* __restrict__ rgba) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    float r = 0.0f, g = 0.0f, b = 0.0f;
+    if (accum && accum_resume) { r = accum[3 * (size_t)i]; g = accum[3 * (size_t)i + 1]; b = accum[3 * (size_t)i + 2]; }
+    for (int p = 0; p < k; ++p) {
+        const float* s = planes + ((size_t)p * n_pix + i) * 3;
+        r += s[0]; g += s[1]; b += s[2];
+    }
+    if (accum) { accum[3 * (size_t)i] = r; accum[3 * (size_t)i + 1] = g; accum[3 * (size_t)i + 2] = b; }
+    if (rgba) rgba[i] = make_uchar4(to_u8(r, inv_spp), to_u8(g, inv_spp), to_u8(b, inv_spp), 255);
+}
+
 // Multi-GPU reduce fused with the pixel epilogue: bufs[k] is device k's fp32 sum buffer; bufs[1..] are PEER pointers, read
 // over NVLink with 16-byte loads.  Sum order is device 0, 1, 2, ... (deterministic).
 __global__ void finalize_peers_kernel(const float* const* __restrict__ bufs, int n_bufs, int n_pix, double inv_spp, uchar4* __restrict__ rgba) {
@@ -642,7 +658,7 @@ static int launch_wf_variant(const FrameParams& fp, size_t smem, int sm_count, c
     }
     const long long n_pix = (long long)fp.width * fp.height;
     long long grid = (long long)sm_count * (MESH && blocks_per_sm > kMeshBlocksPerSm ? kMeshBlocksPerSm : blocks_per_sm);   // trav_scratch is sized for kMeshBlocksPerSm
-    const long long need = (n_pix + WF_SLOTS - 1) / WF_SLOTS;
+    const long long need = (n_pix * (fp.split_k > 1 ? fp.split_k : 1) + WF_SLOTS - 1) / WF_SLOTS;
     if (grid > need) grid = need;
     integrate_wf_kernel<STATS, MESH><<<(unsigned)grid, WF_THREADS, smem, stream>>>(fp);
     return (int)cudaGetLastError();
@@ -692,6 +708,24 @@ int launch_finalize(const float* accum, int width, int height, int spp_total, ui
     finalize_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(accum, n, 1.0 / (double)spp_total,
                                                                       reinterpret_cast<uchar4*>(rgba));
     return (int)cudaGetLastError();
+}
+
+int launch_finalize_planes(const float* planes, int split_k, int width, int height, int spp_total, float* accum, int accum_resume, uint8_t* rgba, void* stream) {
+    const int n = width * height, threads = 256;
+    finalize_planes_kernel<<<(n + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(planes, split_k, n, accum, accum_resume, 1.0 / (double)spp_total,
+                                                                                            reinterpret_cast<uchar4*>(rgba));
+    return (int)cudaGetLastError();
+}
+
+// Whole pixels as work items leave most path slots idle on small frames (and the last wave of a mid-size frame runs almost
+// empty): aim for at least 4 items per resident slot, items of at least one sample, at most 64 planes.
+int wf_split_factor(int sm_count, long long n_pix, int n_samples) {
+    const long long slots = (long long)sm_count * PTB_WF_MIN_BLOCKS * WF_SLOTS;
+    if (n_pix >= 4 * slots || n_samples < 2) return 1;
+    long long k = (4 * slots + n_pix - 1) / n_pix;
+    if (k > n_samples) k = n_samples;
+    if (k > 64) k = 64;
+    return (int)k;
 }
 
 int launch_finalize_peers(const float* const* d_bufs_on_dev0, int n_bufs, int width, int height, int spp_total, uint8_t* rgba, void* stream) {

@@ -84,7 +84,12 @@ struct FrameParams {
     int32_t accum_resume;        // 1: start each pixel's sum from accum[] (progressive batches), 0: from zero
     uint8_t* rgba;               // W*H*4 finalised pixels, or nullptr
     unsigned long long* stats;   // kStatsWords counters, or nullptr
-    unsigned int* work_counter;  // wavefront kernel: next unassigned pixel index (zeroed before the launch)
+    unsigned int* work_counter;  // wavefront kernel: next unassigned work item (zeroed before the launch)
+    // Small frames (fewer pixels than a few times the resident path slots): a work item is (pixel, 1/split_k of its sample
+    // range) instead of a whole pixel, item w = plane * n_pix + pixel; partial sums go to planes[plane][pixel][3] and
+    // finalize_planes_kernel adds the planes in order.  split_k == 1: one item per pixel, fused epilogue (large frames).
+    int32_t split_k;
+    float* planes;
     const float4* bvh_nodes;     // EXTENSION: BVH over the mesh triangles (bvh.h), nullptr when the scene has no mesh
     const float4* bvh_tris;
     int* trav_scratch;           // kTravStride ints per path slot of the launch (suspended traversals), mesh scenes only
@@ -107,6 +112,8 @@ int launch_finalize(const float* accum, int width, int height, int spp_total, ui
 int launch_primary_hits(const Obj64* d_world, int n_obj, const float4* bvh_nodes, const float4* bvh_tris, const Camera64& cam,
                         int width, int height, double xi_u, double xi_v, int32_t* d_ids, double* d_t, void* stream);
 int launch_finalize_peers(const float* const* d_bufs_on_dev0, int n_bufs, int width, int height, int spp_total, uint8_t* rgba, void* stream);
+int launch_finalize_planes(const float* planes, int split_k, int width, int height, int spp_total, float* accum, int accum_resume, uint8_t* rgba, void* stream);
+int wf_split_factor(int sm_count, long long n_pix, int n_samples);   // split_k the wavefront launcher wants for this frame
 int launch_fma_peak(float* d_out, int blocks, int threads, int iters, void* stream);
 
 }  // namespace ptb

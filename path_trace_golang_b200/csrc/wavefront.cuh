@@ -71,23 +71,36 @@ struct WfState : SlotState<WF_SLOTS> {
 // pixel is complete — write the pixel out and take the next pixel from the global counter (renderer.go:171-221).
 template <bool STATS, class SS>
 __device__ __forceinline__ void path_regen(SS& S, const FrameParams& fp, int n_pix, int j, bool sample_done, unsigned long long* st) {
-    int pix = S.pix[j];
+    int w = S.pix[j];                                     // work item: the pixel, or plane * n_pix + pixel when the frame is split
     int s = S.smp[j] + (sample_done ? 1 : 0);
-    if (pix < 0 || s >= fp.s_end) {
-        if (pix >= 0) {                                   // pixel complete: epilogue / accumulation buffer
+    const bool split = fp.split_k > 1;
+    int pix = w, plane = 0, s_end = fp.s_end;
+    if (split && w >= 0) {
+        plane = w / n_pix; pix = w - plane * n_pix;
+        s_end = fp.s_begin + (int)((unsigned)(fp.s_end - fp.s_begin) * (unsigned)(plane + 1) / (unsigned)fp.split_k);
+    }
+    if (w < 0 || s >= s_end) {
+        if (w >= 0) {                                     // item complete: epilogue / accumulation buffer / partial-sum plane
             const float sx = S.ax[j], sy = S.ay[j], sz = S.az[j];
-            if (fp.accum) { float* a = fp.accum + (size_t)pix * 3; a[0] = sx; a[1] = sy; a[2] = sz; }
-            if (fp.rgba) {
-                const double inv_spp = 1.0 / (double)fp.spp_total;
-                reinterpret_cast<uchar4*>(fp.rgba)[pix] = make_uchar4(to_u8(sx, inv_spp), to_u8(sy, inv_spp), to_u8(sz, inv_spp), 255);
+            if (split) {
+                float* a = fp.planes + (size_t)w * 3; a[0] = sx; a[1] = sy; a[2] = sz;
+            } else {
+                if (fp.accum) { float* a = fp.accum + (size_t)pix * 3; a[0] = sx; a[1] = sy; a[2] = sz; }
+                if (fp.rgba) {
+                    const double inv_spp = 1.0 / (double)fp.spp_total;
+                    reinterpret_cast<uchar4*>(fp.rgba)[pix] = make_uchar4(to_u8(sx, inv_spp), to_u8(sy, inv_spp), to_u8(sz, inv_spp), 255);
+                }
             }
         }
-        pix = (int)atomicAdd(fp.work_counter, 1u);
-        if (pix >= n_pix) { S.pix[j] = -1; S.depth[j] = 0; return; }
-        S.pix[j] = pix;
-        s = fp.s_begin;
+        w = (int)atomicAdd(fp.work_counter, 1u);
+        if (w >= n_pix * fp.split_k) { S.pix[j] = -1; S.depth[j] = 0; return; }
+        S.pix[j] = w;
+        pix = w; s = fp.s_begin;
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
-        if (fp.accum_resume) { const float* a = fp.accum + (size_t)pix * 3; a0 = a[0]; a1 = a[1]; a2 = a[2]; }
+        if (split) {
+            plane = w / n_pix; pix = w - plane * n_pix;
+            s = fp.s_begin + (int)((unsigned)(fp.s_end - fp.s_begin) * (unsigned)plane / (unsigned)fp.split_k);
+        } else if (fp.accum_resume) { const float* a = fp.accum + (size_t)pix * 3; a0 = a[0]; a1 = a[1]; a2 = a[2]; }
         S.ax[j] = a0; S.ay[j] = a1; S.az[j] = a2;
     }
     S.smp[j] = s;

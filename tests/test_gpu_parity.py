@@ -252,3 +252,26 @@ def test_partition_render_reduce_finalize_on_device(ctx, host_scenes):
         img = rgba.cpu().numpy()
         diff = np.abs(img.astype(int) - ref.astype(int))
         assert diff.max() <= 1 and (diff > 0).mean() < 0.01, (world, diff.max(), (diff > 0).mean())
+
+
+def test_small_frame_sample_split_matches_whole_pixels(ctx, host_scenes, monkeypatch):
+    """Frames with fewer pixels than a few times the resident path slots are traced as (pixel, sample sub-range) work
+    items whose partial sums are added afterwards (FrameParams::split_k): the same samples, re-associated sums."""
+    ctx.upload(host_scenes["metal_glass_room"])
+    for (w, h, spp, depth) in [(400, 225, 20, 20), (101, 67, 5, 8), (64, 64, 1, 4)]:
+        cfg = ctx.cfg(w, h, spp, depth, seed=3)
+        split = ctx.render_accum(cfg)
+        img_split = ctx.render(cfg)
+        monkeypatch.setenv("PTB_NO_SPLIT", "1")
+        whole = ctx.render_accum(cfg)
+        img_whole = ctx.render(cfg)
+        monkeypatch.delenv("PTB_NO_SPLIT")
+        assert np.allclose(split, whole, rtol=2e-6 * spp, atol=1e-6), (w, h, spp)
+        d = np.abs(img_split.astype(np.int16) - img_whole.astype(np.int16))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-3
+        assert np.array_equal(ctx.render_accum(cfg), split)                  # deterministic
+    # a sample range (multi-GPU partition) of a split frame
+    a = ctx.render_accum(ctx.cfg(320, 180, 16, 8, seed=1, sample_begin=0, sample_count=7))
+    b = ctx.render_accum(ctx.cfg(320, 180, 16, 8, seed=1, sample_begin=7, sample_count=9))
+    f = ctx.render_accum(ctx.cfg(320, 180, 16, 8, seed=1))
+    assert np.allclose(a.astype(np.float64) + b, f, rtol=1e-5, atol=1e-6)
