@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 2
+#define PTB_ABI_VERSION 3   /* 2: meshes (ptb_scene.n_mesh ...), 3: ptb_multi_* */
 
 enum {
     PTB_OK = 0,
