@@ -498,6 +498,32 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
     }
     for (int i = 0; i < (int)world.size(); i++)      // exit-search candidates: analytic dielectric objects (meshes are not searched)
         if (world[i].type != PTB_OBJ_MESH && world[i].mat_type == PTB_MAT_DIELECTRIC) hs.diel_idx[hs.n_diel++] = dev_of[i];
+    {   // typed copies for the exit search (scene_dev.h)
+        int nb = 0, ns = 0, other = 0;
+        for (int k = 0; k < hs.n_diel; k++) {
+            const int t = hs.obj[hs.diel_idx[k]].meta & 3;
+            if (t == PTB_OBJ_BOX) nb++; else if (t == PTB_OBJ_SPHERE) ns++; else other++;
+        }
+        hs.exit_typed = (other == 0 && nb <= kMaxExitTyped && ns <= kMaxExitTyped) ? 1 : 0;
+        hs.n_dbox = hs.n_dsph = 0; hs.dbox_off4 = hs.dsph_off4 = 0;
+        if (hs.exit_typed) {
+            int f = (hs.sphere_off4 + hs.n_sphere_groups * kSphereGroup) * 4;
+            hs.dbox_off4 = f / 4;
+            for (int k = 0; k < hs.n_diel; k++) {
+                const DevObj& o = hs.obj[hs.diel_idx[k]];
+                if ((o.meta & 3) != PTB_OBJ_BOX) continue;
+                float* b = hs.scan_tab + f; f += 8; hs.n_dbox++;
+                b[0] = o.ax; b[1] = o.ay; b[2] = o.az; b[3] = 0.0f; b[4] = o.bx; b[5] = o.by; b[6] = o.bz; b[7] = 0.0f;
+            }
+            hs.dsph_off4 = f / 4;
+            for (int k = 0; k < hs.n_diel; k++) {
+                const DevObj& o = hs.obj[hs.diel_idx[k]];
+                if ((o.meta & 3) != PTB_OBJ_SPHERE) continue;
+                float* b = hs.scan_tab + f; f += 4; hs.n_dsph++;
+                b[0] = o.ax; b[1] = o.ay; b[2] = o.az; b[3] = o.by;      // radius^2
+            }
+        }
+    }
 
     // EXTENSION: BVH over the mesh triangles
     c->d_bvh_nodes = nullptr; c->d_bvh_tris = nullptr;      // (the kept copy is freed when a different mesh set arrives)

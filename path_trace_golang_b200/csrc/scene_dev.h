@@ -41,6 +41,7 @@ struct DevSky {      // renderer.go:56-92
     float color[3], horizon[3], zenith[3];
 };
 
+constexpr int kMaxExitTyped = 64;
 struct DevScene {                        // ~55 KB of the 64 KB constant bank
     int32_t n_obj, n_mat, n_diel, n_box;   // n_mat counts the appended zero material (index n_mat-1); boxes are obj[0..n_box)
     // ---- the closest-hit scan's own tables (wavefront kernel).  Device order of the analytic objects:
@@ -53,7 +54,12 @@ struct DevScene {                        // ~55 KB of the 64 KB constant bank
     int32_t n_box_groups, n_plane_run, n_sphere_run, n_sphere_groups;
     int32_t plane_off4, sphere_off4, n_typed, pad_;                       // offsets in float4 units; n_typed = first "rest" index
     float mesh_c[4], mesh_h[4];          // EXTENSION: bounds of all mesh triangles as (centre, half extent); h = -1 without meshes
-    alignas(16) float scan_tab[PTB_MAX_OBJECTS * 6 + 16];
+    // dielectric exit search (renderer.go:316-371): when every dielectric object is a box or a sphere (and there are at
+    // most kMaxExitTyped of each) they are listed again behind the scan records — boxes as 2 x float4 (centre | half extent),
+    // spheres as 1 x float4 (centre, radius^2) — so the search runs branch-free loops without dependent index loads
+    int32_t exit_typed, n_dbox, n_dsph, dbox_off4;
+    int32_t dsph_off4, pad2_[3];
+    alignas(16) float scan_tab[PTB_MAX_OBJECTS * 6 + 16 + kMaxExitTyped * 12];
     DevSky sky;
     DevCamera cam;
     int32_t diel_idx[PTB_MAX_OBJECTS];   // DEVICE indices of objects with a dielectric material, in ascending world order

@@ -217,19 +217,51 @@ __device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const D
                 float exit_t = FLT_MAX;
                 bool hit_exit = false;
                 F3 ep = p;
-                const int n_diel = c_scene.n_diel;
-                for (int k = 0; k < n_diel; ++k) {        // only dielectric objects can be accepted (:335)
-                    const int ei = c_scene.diel_idx[k];
-                    const DevObj& eo = c_scene.obj[ei];
-                    const int et = eo.meta & 3;
-                    float t;
-                    if (!hit_any(obj_lo(ei), obj_hi(ei), et, er, 0.0001f, exit_t, t)) continue;
-                    F3 q;
-                    const bool qf = front_face_only(eo, et, p, sd, t, q);
-                    if (!qf && t < exit_t) {
+                // only dielectric objects can be accepted (:335): a back-face hit closer than the best so far whose squared
+                // distance from p lies in (1e-8, 1000)
+                auto consider = [&](float t, bool q_front, F3 q) {
+                    if (!q_front && t < exit_t) {
                         float ex = q.x - p.x, ey = q.y - p.y, ez = q.z - p.z;
                         float d2 = ex * ex + ey * ey + ez * ez;
                         if (d2 > 1e-8f && d2 < 1000.0f) { hit_exit = true; exit_t = t; ep = q; }
+                    }
+                };
+                if (c_scene.exit_typed) {                 // every dielectric object is a box or a sphere: typed records, no index loads
+                    const float4* tab4 = reinterpret_cast<const float4*>(c_scene.scan_tab);
+                    const int n_dbox = c_scene.n_dbox, n_dsph = c_scene.n_dsph;
+                    const float4* dbox = tab4 + c_scene.dbox_off4;
+                    const float4* dsph = tab4 + c_scene.dsph_off4;
+                    for (int k = 0; k < n_dbox; ++k) {
+                        const float4 bc = dbox[2 * k], bh = dbox[2 * k + 1];
+                        float t;
+                        if (!hit_box(bc, bh, er, 0.0001f, exit_t, t)) continue;
+                        DevObj eo;
+                        eo.ax = bc.x; eo.ay = bc.y; eo.az = bc.z; eo.bx = bh.x; eo.by = bh.y; eo.bz = bh.z; eo.meta = PTB_OBJ_BOX; eo.world_idx = 0;
+                        F3 q;
+                        const bool qf = front_face_only(eo, PTB_OBJ_BOX, p, sd, t, q);
+                        consider(t, qf, q);
+                    }
+                    for (int k = 0; k < n_dsph; ++k) {
+                        const float4 sp = dsph[k];
+                        float t;
+                        if (!hit_sphere4(sp.x, sp.y, sp.z, sp.w, er, 0.0001f, exit_t, t)) continue;
+                        DevObj eo;
+                        eo.ax = sp.x; eo.ay = sp.y; eo.az = sp.z; eo.bx = eo.by = eo.bz = 0.0f; eo.meta = PTB_OBJ_SPHERE; eo.world_idx = 0;
+                        F3 q;
+                        const bool qf = front_face_only(eo, PTB_OBJ_SPHERE, p, sd, t, q);
+                        consider(t, qf, q);
+                    }
+                } else {
+                    const int n_diel = c_scene.n_diel;
+                    for (int k = 0; k < n_diel; ++k) {
+                        const int ei = c_scene.diel_idx[k];
+                        const DevObj& eo = c_scene.obj[ei];
+                        const int et = eo.meta & 3;
+                        float t;
+                        if (!hit_any(obj_lo(ei), obj_hi(ei), et, er, 0.0001f, exit_t, t)) continue;
+                        F3 q;
+                        const bool qf = front_face_only(eo, et, p, sd, t, q);
+                        consider(t, qf, q);
                     }
                 }
                 if (hit_exit) {                           // renderer.go:352-369
