@@ -86,3 +86,21 @@ def test_bench_reference_arm_schema():
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=120, env={**os.environ, "RANK": "1", "WORLD_SIZE": "2"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_cgo_shim_only_uses_declared_entry_points():
+    """go/internal/engine/cuda/cuda.go cannot be compiled here (no Go toolchain): at least every C.ptb_* it calls must be
+    declared in include/ptb200.h and exported by the library."""
+    import re
+    from path_trace_golang_b200 import _lib
+    src = (ROOT / "go" / "internal" / "engine" / "cuda" / "cuda.go").read_text()
+    header = (ROOT / "include" / "ptb200.h").read_text()
+    used = set(re.findall(r"C\.(ptb_[a-z0-9_]+)\(", src))
+    assert {"ptb_create", "ptb_scene_upload", "ptb_render", "ptb_multi_create", "ptb_multi_render"} <= used
+    lib = _lib.lib()
+    for name in used - {"ptb_go_progress_ptr"}:            # (the trampoline getter is defined in the cgo preamble)
+        assert re.search(r"\b%s\s*\(" % name, header), f"{name} is not declared in ptb200.h"
+        assert hasattr(lib, name), f"{name} is not exported"
+    # struct fields the shim fills must exist in the header's ptb_scene / ptb_cfg
+    for field in re.findall(r"\bf\.s\.([a-z_0-9]+)\s*=", src):
+        assert re.search(r"\b%s\b" % field, header), f"ptb_scene.{field} missing from the header"
