@@ -351,19 +351,35 @@ int ptb_get_device_info(ptb_ctx* c, ptb_device_info* out) {
     return PTB_OK;
 }
 
-int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
-    if (!c) return PTB_ERR_INVALID;
-    std::lock_guard<std::mutex> lk(c->mu);
-    if (!s) return fail(c, PTB_ERR_INVALID, "scene is NULL");
-    if (s->n_obj < 0 || s->n_mat < 0) return fail(c, PTB_ERR_INVALID, "negative counts");
-    if (s->n_obj > 0 && (!s->obj_type || !s->obj_mat || !s->obj_pos || !s->obj_size)) return fail(c, PTB_ERR_INVALID, "object arrays are NULL");
-    if (s->n_mat > 0 && (!s->mat_type || !s->mat_albedo || !s->mat_rough || !s->mat_ior || !s->mat_emit || !s->mat_power ||
-                         !s->mat_absorption || !s->mat_smoothness)) return fail(c, PTB_ERR_INVALID, "material arrays are NULL");
-    if (s->n_mat > PTB_MAX_MATERIALS) return fail(c, PTB_ERR_LIMIT, "%d materials > PTB_MAX_MATERIALS=%d", s->n_mat, PTB_MAX_MATERIALS);
-    CK(c, cudaSetDevice(c->device));
+}  // extern "C"
 
+namespace {
+// DevObj::meta / triangle tag: type, dielectric bit, shading class of the wavefront kernel (enum in wavefront.cuh: 0 dielectric,
+// 1 terminate (emissive), 3 diffuse (lambert, rough metal), 4 specular (mirror, smooth metal)), material slot.
+int meta_of(const World64Entry& w) {
+    int cls = 3;
+    if (w.mat_type == PTB_MAT_METAL) cls = ((float)w.rough > 1e-6f) ? 3 : 4;
+    else if (w.mat_type == PTB_MAT_MIRROR) cls = 4;
+    else if (w.mat_type == PTB_MAT_DIELECTRIC) cls = 0;
+    else if (w.mat_type == PTB_MAT_EMISSIVE) cls = 1;
+    return w.type | ((w.mat_type == PTB_MAT_DIELECTRIC) << 2) | (cls << 3) | (w.mat_slot << 6);
+}
+
+// convertMaterial + sceneToWorld in binary64 (materials.go:28-55, objects.go:225-269), plus the triangle soup of the mesh objects.
+struct WorldBuild {
+    std::vector<World64Entry> mats, world;
+    std::vector<float> tri_v;                  // triangles of the mesh objects, concatenated in world order
+    std::vector<int32_t> tri_world;            // per triangle: world index of its mesh object
+    int n_analytic = 0;
+};
+int build_world(ptb_ctx* c, const ptb_scene* s, WorldBuild& wb) {
+    std::vector<World64Entry>& mats = wb.mats;
+    std::vector<World64Entry>& world = wb.world;
+    std::vector<float>& tri_v = wb.tri_v;
+    std::vector<int32_t>& tri_world = wb.tri_world;
+    int& n_analytic = wb.n_analytic;
     // materials (convertMaterial) + the zero material in slot n_mat (objects.go:234: missing map key)
-    std::vector<World64Entry> mats(s->n_mat + 1);
+    mats.assign(s->n_mat + 1, World64Entry{});
     for (int i = 0; i < s->n_mat; i++) convert_material(s, i, mats[i]);
     {
         World64Entry& z = mats[s->n_mat];
@@ -373,11 +389,7 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
     // objects (sceneToWorld); EXTENSION: mesh objects are world entries too (type PTB_OBJ_MESH, a/b = bounding box)
     if (s->n_mesh < 0 || (s->n_mesh > 0 && (!s->obj_mesh || !s->mesh_tri_begin || !s->tri_vertices)))
         return fail(c, PTB_ERR_INVALID, "mesh arrays are NULL");
-    std::vector<World64Entry> world;
-    std::vector<float> tri_v;                  // triangles of the mesh objects, concatenated in world order
-    std::vector<int32_t> tri_world;            // per triangle: world index of its mesh object
     std::vector<char> mesh_used(s->n_mesh > 0 ? s->n_mesh : 0, 0);
-    int n_analytic = 0;
     for (int i = 0; i < s->n_obj; i++) {
         const int t = s->obj_type[i];
         if (t != PTB_OBJ_SPHERE && t != PTB_OBJ_PLANE && t != PTB_OBJ_BOX && t != PTB_OBJ_MESH) continue;   // dropped (objects.go:237-266)
@@ -415,20 +427,16 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
         world.push_back(w);
     }
     if (n_analytic > PTB_MAX_OBJECTS) return fail(c, PTB_ERR_LIMIT, "%d analytic objects > PTB_MAX_OBJECTS=%d", n_analytic, PTB_MAX_OBJECTS);
-    auto meta_of = [](const World64Entry& w) {
-        // shading class of the wavefront kernel (enum in wavefront.cuh): 0 dielectric, 1 terminate (emissive),
-        // 3 diffuse (lambert, rough metal), 4 specular (mirror, smooth metal)
-        int cls = 3;
-        if (w.mat_type == PTB_MAT_METAL) cls = ((float)w.rough > 1e-6f) ? 3 : 4;
-        else if (w.mat_type == PTB_MAT_MIRROR) cls = 4;
-        else if (w.mat_type == PTB_MAT_DIELECTRIC) cls = 0;
-        else if (w.mat_type == PTB_MAT_EMISSIVE) cls = 1;
-        return w.type | ((w.mat_type == PTB_MAT_DIELECTRIC) << 2) | (cls << 3) | (w.mat_slot << 6);
-    };
+    return PTB_OK;
+}
 
-    // binary32 device tables
-    DevScene& hs = *c->h_scene;
-    hs.n_obj = n_analytic; hs.n_mat = s->n_mat + 1; hs.n_diel = 0;
+// binary32 device tables: materials, analytic objects in device order, the scan tables and the exit-search tables
+// (scene_dev.h).  w64 = the analytic objects in world order for the binary64 parity kernel.
+void build_device_tables(const WorldBuild& wb, int n_mat_in, DevScene& hs, std::vector<Obj64>& w64) {
+    const std::vector<World64Entry>& mats = wb.mats;
+    const std::vector<World64Entry>& world = wb.world;
+    const int n_analytic = wb.n_analytic;
+    hs.n_obj = n_analytic; hs.n_mat = n_mat_in + 1; hs.n_diel = 0;
     for (int i = 0; i < hs.n_mat; i++) {
         DevMat& m = hs.mat[i];
         const World64Entry& w = mats[i];
@@ -451,7 +459,7 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
         order.insert(order.end(), rest.begin(), rest.end());
         hs.n_typed = hs.n_box + hs.n_plane_run + hs.n_sphere_run;
     }
-    std::vector<Obj64> w64;
+    w64.clear();
     for (int i = 0; i < (int)world.size(); i++) {
         if (world[i].type == PTB_OBJ_MESH) continue;
         Obj64 o64;
@@ -525,7 +533,14 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
         }
     }
 
-    // EXTENSION: BVH over the mesh triangles
+}
+
+// EXTENSION: bounds of all mesh triangles and the BVH over them (built on the host, bvh.cpp).  Re-uploading the same meshes
+// (RenderInto takes the scene on every call, renderer.go:34) does not rebuild: key = FNV-1a over the triangle soup and tags.
+int build_mesh_accel(ptb_ctx* c, const WorldBuild& wb, DevScene& hs) {
+    const std::vector<World64Entry>& world = wb.world;
+    const std::vector<float>& tri_v = wb.tri_v;
+    const std::vector<int32_t>& tri_world = wb.tri_world;
     c->d_bvh_nodes = nullptr; c->d_bvh_tris = nullptr;      // (the kept copy is freed when a different mesh set arrives)
     c->bvh = ptb_bvh_info{};
     for (int k = 0; k < 4; k++) { hs.mesh_c[k] = 0.0f; hs.mesh_h[k] = -1.0f; }
@@ -572,6 +587,30 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
         c->d_bvh_nodes_keep = c->d_bvh_nodes; c->d_bvh_tris_keep = c->d_bvh_tris; c->bvh_keep = c->bvh; c->bvh_key = key;
         }
     }
+    return PTB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
+    if (!c) return PTB_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(c->mu);
+    if (!s) return fail(c, PTB_ERR_INVALID, "scene is NULL");
+    if (s->n_obj < 0 || s->n_mat < 0) return fail(c, PTB_ERR_INVALID, "negative counts");
+    if (s->n_obj > 0 && (!s->obj_type || !s->obj_mat || !s->obj_pos || !s->obj_size)) return fail(c, PTB_ERR_INVALID, "object arrays are NULL");
+    if (s->n_mat > 0 && (!s->mat_type || !s->mat_albedo || !s->mat_rough || !s->mat_ior || !s->mat_emit || !s->mat_power ||
+                         !s->mat_absorption || !s->mat_smoothness)) return fail(c, PTB_ERR_INVALID, "material arrays are NULL");
+    if (s->n_mat > PTB_MAX_MATERIALS) return fail(c, PTB_ERR_LIMIT, "%d materials > PTB_MAX_MATERIALS=%d", s->n_mat, PTB_MAX_MATERIALS);
+    CK(c, cudaSetDevice(c->device));
+
+    WorldBuild wb;
+    int rc = build_world(c, s, wb);
+    if (rc) return rc;
+    DevScene& hs = *c->h_scene;
+    std::vector<Obj64> w64;
+    build_device_tables(wb, s->n_mat, hs, w64);
+    if ((rc = build_mesh_accel(c, wb, hs))) return rc;
     hs.sky.kind = s->sky.kind == PTB_SKY_GRADIENT ? PTB_SKY_GRADIENT : PTB_SKY_CONST;
     for (int k = 0; k < 3; k++) { hs.sky.color[k] = (float)s->sky.color[k]; hs.sky.horizon[k] = (float)s->sky.horizon[k]; hs.sky.zenith[k] = (float)s->sky.zenith[k]; }
 
@@ -587,7 +626,7 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
     if (!w64.empty()) CK(c, cudaMemcpy(c->d_world64, w64.data(), sizeof(Obj64) * w64.size(), cudaMemcpyHostToDevice));
     c->n_world64 = (int)w64.size();
 
-    c->world = world;
+    c->world = wb.world;
     c->cam = s->camera;
     c->has_scene = true;
     return PTB_OK;
