@@ -368,15 +368,14 @@ int meta_of(const World64Entry& w) {
 // convertMaterial + sceneToWorld in binary64 (materials.go:28-55, objects.go:225-269), plus the triangle soup of the mesh objects.
 struct WorldBuild {
     std::vector<World64Entry> mats, world;
-    std::vector<float> tri_v;                  // triangles of the mesh objects, concatenated in world order
-    std::vector<int32_t> tri_world;            // per triangle: world index of its mesh object
+    struct MeshRef { int64_t t0, t1; int32_t world_idx; };   // triangles [t0, t1) of ptb_scene::tri_vertices belong to world[world_idx]
+    std::vector<MeshRef> meshes;               // the non-empty mesh objects in world order
+    int64_t n_tris = 0;
     int n_analytic = 0;
 };
 int build_world(ptb_ctx* c, const ptb_scene* s, WorldBuild& wb) {
     std::vector<World64Entry>& mats = wb.mats;
     std::vector<World64Entry>& world = wb.world;
-    std::vector<float>& tri_v = wb.tri_v;
-    std::vector<int32_t>& tri_world = wb.tri_world;
     int& n_analytic = wb.n_analytic;
     // materials (convertMaterial) + the zero material in slot n_mat (objects.go:234: missing map key)
     mats.assign(s->n_mat + 1, World64Entry{});
@@ -412,16 +411,19 @@ int build_world(ptb_ctx* c, const ptb_scene* s, WorldBuild& wb) {
             const int64_t t0 = s->mesh_tri_begin[m], t1 = s->mesh_tri_begin[m + 1];
             if (t0 < 0 || t1 < t0) return fail(c, PTB_ERR_INVALID, "mesh_tri_begin is not monotone");
             if (t1 == t0) continue;            // empty mesh: dropped
-            if ((int64_t)(tri_v.size() / 9) + (t1 - t0) > (1ll << 28)) return fail(c, PTB_ERR_LIMIT, "more than 2^28 triangles");
-            for (int k = 0; k < 3; k++) { w.a[k] = INFINITY; w.b[k] = -INFINITY; }
-            for (int64_t q = t0 * 9; q < t1 * 9; q++) {
-                const float v = s->tri_vertices[q];
-                if (!(v == v) || std::fabs(v) > 1e18f) return fail(c, PTB_ERR_INVALID, "non-finite mesh vertex");
-                const int k = (int)(q % 3);
-                w.a[k] = std::fmin(w.a[k], (double)v); w.b[k] = std::fmax(w.b[k], (double)v);
+            if (wb.n_tris + (t1 - t0) > (1ll << 28)) return fail(c, PTB_ERR_LIMIT, "more than 2^28 triangles");
+            float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+            bool finite = true;
+            const float* v = s->tri_vertices + t0 * 9;
+            for (int64_t q = 0; q < (t1 - t0) * 3; q++, v += 3) {          // one vertex per trip; NaN fails the range test
+                finite &= (std::fabs(v[0]) <= 1e18f) & (std::fabs(v[1]) <= 1e18f) & (std::fabs(v[2]) <= 1e18f);
+                lo[0] = std::min(lo[0], v[0]); lo[1] = std::min(lo[1], v[1]); lo[2] = std::min(lo[2], v[2]);
+                hi[0] = std::max(hi[0], v[0]); hi[1] = std::max(hi[1], v[1]); hi[2] = std::max(hi[2], v[2]);
             }
-            tri_v.insert(tri_v.end(), s->tri_vertices + t0 * 9, s->tri_vertices + t1 * 9);
-            tri_world.insert(tri_world.end(), (size_t)(t1 - t0), (int32_t)world.size());
+            if (!finite) return fail(c, PTB_ERR_INVALID, "non-finite mesh vertex");
+            for (int k = 0; k < 3; k++) { w.a[k] = lo[k]; w.b[k] = hi[k]; }
+            wb.meshes.push_back({t0, t1, (int32_t)world.size()});
+            wb.n_tris += t1 - t0;
         }
         if (t != PTB_OBJ_MESH) n_analytic++;
         world.push_back(w);
@@ -537,56 +539,63 @@ void build_device_tables(const WorldBuild& wb, int n_mat_in, DevScene& hs, std::
 
 // EXTENSION: bounds of all mesh triangles and the BVH over them (built on the host, bvh.cpp).  Re-uploading the same meshes
 // (RenderInto takes the scene on every call, renderer.go:34) does not rebuild: key = FNV-1a over the triangle soup and tags.
-int build_mesh_accel(ptb_ctx* c, const WorldBuild& wb, DevScene& hs) {
+int build_mesh_accel(ptb_ctx* c, const ptb_scene* s, const WorldBuild& wb, DevScene& hs) {
     const std::vector<World64Entry>& world = wb.world;
-    const std::vector<float>& tri_v = wb.tri_v;
-    const std::vector<int32_t>& tri_world = wb.tri_world;
     c->d_bvh_nodes = nullptr; c->d_bvh_tris = nullptr;      // (the kept copy is freed when a different mesh set arrives)
     c->bvh = ptb_bvh_info{};
     for (int k = 0; k < 4; k++) { hs.mesh_c[k] = 0.0f; hs.mesh_h[k] = -1.0f; }
-    if (!tri_world.empty()) {
-        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-        for (size_t q = 0; q < tri_v.size(); q++) { const float v = tri_v[q]; const int a = (int)(q % 3); lo[a] = std::min(lo[a], v); hi[a] = std::max(hi[a], v); }
-        for (int k = 0; k < 3; k++) {        // padded like the BVH boxes so that the prefilter never rejects what the root would accept
-            const float pad = 1e-5f * std::max(1.0f, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
-            hs.mesh_c[k] = 0.5f * (lo[k] + hi[k]); hs.mesh_h[k] = 0.5f * (hi[k] - lo[k]) + 2.0f * pad;
-        }
-        std::vector<int32_t> tri_meta(tri_world.size());
-        for (size_t q = 0; q < tri_world.size(); q++) tri_meta[q] = meta_of(world[tri_world[q]]);
-        // Re-uploading the same meshes (RenderInto takes the scene on every call, renderer.go:34) must not rebuild the BVH:
-        // key = FNV-1a over the triangle soup and the per-triangle material/world tags.
-        auto fnv = [](uint64_t h, const void* p, size_t n) {
-            const uint64_t* w = (const uint64_t*)p;
-            for (size_t i = 0; i < n / 8; i++) { h ^= w[i]; h *= 0x100000001b3ull; }
-            const unsigned char* b = (const unsigned char*)p + (n / 8) * 8;
-            for (size_t i = 0; i < n % 8; i++) { h ^= b[i]; h *= 0x100000001b3ull; }
-            return h;
-        };
-        uint64_t key = fnv(0xcbf29ce484222325ull, tri_v.data(), tri_v.size() * sizeof(float));
-        key = fnv(key, tri_meta.data(), tri_meta.size() * 4);
-        key = fnv(key, tri_world.data(), tri_world.size() * 4);
-        if (c->d_bvh_nodes_keep && c->bvh_key == key && c->bvh_keep.n_triangles == (int64_t)tri_world.size()) {
-            c->d_bvh_nodes = c->d_bvh_nodes_keep; c->d_bvh_tris = c->d_bvh_tris_keep; c->bvh = c->bvh_keep;
-        } else {
-        BvhBuildInput in{tri_v.data(), (int64_t)tri_world.size(), tri_meta.data(), tri_world.data()};
-        BvhBuildOutput out;
-        unsigned hw = std::thread::hardware_concurrency();
-        build_bvh(in, out, hw ? (int)hw : 4);
-        CK(c, cudaMalloc((void**)&c->d_bvh_nodes, out.nodes.size() * sizeof(BvhNode)));
-        CK(c, cudaMalloc((void**)&c->d_bvh_tris, out.tris.size() * sizeof(BvhTri)));
-        CK(c, cudaMemcpy(c->d_bvh_nodes, out.nodes.data(), out.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
-        CK(c, cudaMemcpy(c->d_bvh_tris, out.tris.data(), out.tris.size() * sizeof(BvhTri), cudaMemcpyHostToDevice));
-        c->bvh.n_triangles = (int64_t)out.tris.size(); c->bvh.n_nodes = (int64_t)out.nodes.size();
-        c->bvh.max_depth = out.max_depth; c->bvh.sah_cost = out.sah_cost; c->bvh.build_ms = out.build_ms;
-        c->bvh.node_bytes = sizeof(BvhNode); c->bvh.triangle_bytes = sizeof(BvhTri);
-        if (out.max_depth > 38) {
-            cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_tris); c->d_bvh_nodes = nullptr; c->d_bvh_tris = nullptr;
-            return fail(c, PTB_ERR_LIMIT, "BVH depth %d exceeds the traversal stack", out.max_depth);
-        }
-        cudaFree(c->d_bvh_nodes_keep); cudaFree(c->d_bvh_tris_keep);
-        c->d_bvh_nodes_keep = c->d_bvh_nodes; c->d_bvh_tris_keep = c->d_bvh_tris; c->bvh_keep = c->bvh; c->bvh_key = key;
-        }
+    if (wb.n_tris == 0) return PTB_OK;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (const WorldBuild::MeshRef& m : wb.meshes) {     // union of the mesh objects' boxes (computed from their vertices in build_world)
+        const World64Entry& w = world[m.world_idx];
+        for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], (float)w.a[k]); hi[k] = std::max(hi[k], (float)w.b[k]); }
     }
+    for (int k = 0; k < 3; k++) {        // padded like the BVH boxes so that the prefilter never rejects what the root would accept
+        const float pad = 1e-5f * std::max(1.0f, std::max(std::fabs(lo[k]), std::fabs(hi[k])));
+        hs.mesh_c[k] = 0.5f * (lo[k] + hi[k]); hs.mesh_h[k] = 0.5f * (hi[k] - lo[k]) + 2.0f * pad;
+    }
+    auto fnv = [](uint64_t h, const void* p, size_t n) {
+        const uint64_t* w = (const uint64_t*)p;
+        for (size_t i = 0; i < n / 8; i++) { uint64_t x; std::memcpy(&x, w + i, 8); h ^= x; h *= 0x100000001b3ull; }
+        const unsigned char* b = (const unsigned char*)p + (n / 8) * 8;
+        for (size_t i = 0; i < n % 8; i++) { h ^= b[i]; h *= 0x100000001b3ull; }
+        return h;
+    };
+    uint64_t key = 0xcbf29ce484222325ull;
+    for (const WorldBuild::MeshRef& m : wb.meshes) {     // vertices in place (no copy), then the tags every triangle of the mesh carries
+        key = fnv(key, s->tri_vertices + m.t0 * 9, (size_t)(m.t1 - m.t0) * 9 * sizeof(float));
+        const int64_t tag[3] = {m.t1 - m.t0, (int64_t)m.world_idx, (int64_t)meta_of(world[m.world_idx])};
+        key = fnv(key, tag, sizeof tag);
+    }
+    if (c->d_bvh_nodes_keep && c->bvh_key == key && c->bvh_keep.n_triangles == wb.n_tris) {
+        c->d_bvh_nodes = c->d_bvh_nodes_keep; c->d_bvh_tris = c->d_bvh_tris_keep; c->bvh = c->bvh_keep;
+        return PTB_OK;
+    }
+    std::vector<float> tri_v;                  // triangles of the mesh objects, concatenated in world order
+    std::vector<int32_t> tri_world, tri_meta;  // per triangle: world index of its mesh object, DevObj-style tag
+    tri_v.reserve((size_t)wb.n_tris * 9); tri_world.reserve((size_t)wb.n_tris); tri_meta.reserve((size_t)wb.n_tris);
+    for (const WorldBuild::MeshRef& m : wb.meshes) {
+        tri_v.insert(tri_v.end(), s->tri_vertices + m.t0 * 9, s->tri_vertices + m.t1 * 9);
+        tri_world.insert(tri_world.end(), (size_t)(m.t1 - m.t0), m.world_idx);
+        tri_meta.insert(tri_meta.end(), (size_t)(m.t1 - m.t0), (int32_t)meta_of(world[m.world_idx]));
+    }
+    BvhBuildInput in{tri_v.data(), (int64_t)tri_world.size(), tri_meta.data(), tri_world.data()};
+    BvhBuildOutput out;
+    unsigned hw = std::thread::hardware_concurrency();
+    build_bvh(in, out, hw ? (int)hw : 4);
+    CK(c, cudaMalloc((void**)&c->d_bvh_nodes, out.nodes.size() * sizeof(BvhNode)));
+    CK(c, cudaMalloc((void**)&c->d_bvh_tris, out.tris.size() * sizeof(BvhTri)));
+    CK(c, cudaMemcpy(c->d_bvh_nodes, out.nodes.data(), out.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+    CK(c, cudaMemcpy(c->d_bvh_tris, out.tris.data(), out.tris.size() * sizeof(BvhTri), cudaMemcpyHostToDevice));
+    c->bvh.n_triangles = (int64_t)out.tris.size(); c->bvh.n_nodes = (int64_t)out.nodes.size();
+    c->bvh.max_depth = out.max_depth; c->bvh.sah_cost = out.sah_cost; c->bvh.build_ms = out.build_ms;
+    c->bvh.node_bytes = sizeof(BvhNode); c->bvh.triangle_bytes = sizeof(BvhTri);
+    if (out.max_depth > 38) {
+        cudaFree(c->d_bvh_nodes); cudaFree(c->d_bvh_tris); c->d_bvh_nodes = nullptr; c->d_bvh_tris = nullptr;
+        return fail(c, PTB_ERR_LIMIT, "BVH depth %d exceeds the traversal stack", out.max_depth);
+    }
+    cudaFree(c->d_bvh_nodes_keep); cudaFree(c->d_bvh_tris_keep);
+    c->d_bvh_nodes_keep = c->d_bvh_nodes; c->d_bvh_tris_keep = c->d_bvh_tris; c->bvh_keep = c->bvh; c->bvh_key = key;
     return PTB_OK;
 }
 }  // namespace
@@ -610,7 +619,7 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
     DevScene& hs = *c->h_scene;
     std::vector<Obj64> w64;
     build_device_tables(wb, s->n_mat, hs, w64);
-    if ((rc = build_mesh_accel(c, wb, hs))) return rc;
+    if ((rc = build_mesh_accel(c, s, wb, hs))) return rc;
     hs.sky.kind = s->sky.kind == PTB_SKY_GRADIENT ? PTB_SKY_GRADIENT : PTB_SKY_CONST;
     for (int k = 0; k < 3; k++) { hs.sky.color[k] = (float)s->sky.color[k]; hs.sky.horizon[k] = (float)s->sky.horizon[k]; hs.sky.zenith[k] = (float)s->sky.zenith[k]; }
 

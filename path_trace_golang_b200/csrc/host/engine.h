@@ -40,5 +40,7 @@ void SavePNG(const std::string& path, const uint8_t* pix, size_t stride, int w, 
 // Same as RenderInto but on an explicit context and raw image memory (what the C ABI wrapper calls).
 int RenderIntoCtx(ptb_ctx* ctx, const scene::Scene& sc, RenderConfig cfg, uint32_t seed, uint8_t* pix, size_t stride,
                   int img_w, int img_h, ptb_progress_fn progress, void* user);
+int RenderFlatCtx(ptb_ctx* ctx, const ptb_scene& view, RenderConfig cfg, uint32_t seed, uint8_t* pix, size_t stride,
+                  int img_w, int img_h, ptb_progress_fn progress, void* user);
 
 }  // namespace engine
