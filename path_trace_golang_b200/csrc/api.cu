@@ -48,7 +48,7 @@ struct ptb_ctx {
     std::vector<World64Entry> world;
     DevScene* h_scene = nullptr;        // pinned
     uint4* d_blob = nullptr;            // obj[] then mat[] (global copy for the smem fill)
-    size_t blob_words = 0;
+    size_t blob_words = 0, blob_cap = 0, world64_cap = 0;
     Obj64* d_world64 = nullptr;
     int n_world64 = 0;
     BvhNode* d_bvh_nodes = nullptr;      // EXTENSION: mesh BVH
@@ -625,13 +625,14 @@ int ptb_scene_upload(ptb_ctx* c, const ptb_scene* s) {
 
     // global copies
     const size_t words = (size_t)hs.n_obj * 2 + (size_t)hs.n_mat * 3;
-    cudaFree(c->d_blob); c->d_blob = nullptr;
-    cudaFree(c->d_world64); c->d_world64 = nullptr;
-    CK(c, cudaMalloc((void**)&c->d_blob, words * sizeof(uint4)));
+    // grow-only buffers (an interactive host uploads before every frame; cudaMalloc/cudaFree per upload cost more than a
+    // preview frame).  A frame still in flight on some stream reads them: wait for the device first, as cudaFree used to.
+    CK(c, cudaDeviceSynchronize());
+    if ((rc = ensure(c, (void**)&c->d_blob, &c->blob_cap, words * sizeof(uint4)))) return rc;
     CK(c, cudaMemcpy(c->d_blob, hs.obj, (size_t)hs.n_obj * sizeof(DevObj), cudaMemcpyHostToDevice));
     CK(c, cudaMemcpy(c->d_blob + (size_t)hs.n_obj * 2, hs.mat, (size_t)hs.n_mat * sizeof(DevMat), cudaMemcpyHostToDevice));
     c->blob_words = words;
-    CK(c, cudaMalloc((void**)&c->d_world64, sizeof(Obj64) * (w64.size() + 1)));
+    if ((rc = ensure(c, (void**)&c->d_world64, &c->world64_cap, sizeof(Obj64) * (w64.size() + 1)))) return rc;
     if (!w64.empty()) CK(c, cudaMemcpy(c->d_world64, w64.data(), sizeof(Obj64) * w64.size(), cudaMemcpyHostToDevice));
     c->n_world64 = (int)w64.size();
 
