@@ -67,7 +67,10 @@ struct DevScene {                        // ~55 KB of the 64 KB constant bank
     DevMat mat[PTB_MAX_MATERIALS + 1];   // slot n_mat-1 = the zero material (missing material_id, objects.go:234)
 };
 constexpr int kBoxGroup = 4;
-constexpr int kSphereGroup = 2;
+#ifndef PTB_SPHERE_GROUP
+#define PTB_SPHERE_GROUP 2
+#endif
+constexpr int kSphereGroup = PTB_SPHERE_GROUP;
 
 // fp64 world for the primary-hit parity kernel (global memory; N is tiny).
 struct Obj64 {

@@ -10,7 +10,7 @@ for spec in "$@"; do
   tmp=$(mktemp -d)
   nvcc $FLAGS $defs -Xptxas -v -c -o $tmp/integrator.o integrator.cu 2>&1 | grep -A2 "integrate_wf_kernelILb0" | grep -E "Used|spill" | tr '\n' ' '
   nvcc $FLAGS -fmad=false -c -o $tmp/primary_fp64.o primary_fp64.cu
-  nvcc $FLAGS -c -o $tmp/api.o api.cu
+  nvcc $FLAGS $defs -c -o $tmp/api.o api.cu
   nvcc $FLAGS -x cu -c -o $tmp/bvh.o bvh.cpp
   nvcc $FLAGS -x cu -c -o $tmp/host_scene.o host/scene.cpp
   nvcc $FLAGS -x cu -c -o $tmp/host_engine.o host/engine.cpp
