@@ -66,7 +66,10 @@ struct DevScene {                        // ~55 KB of the 64 KB constant bank
     DevObj obj[PTB_MAX_OBJECTS];
     DevMat mat[PTB_MAX_MATERIALS + 1];   // slot n_mat-1 = the zero material (missing material_id, objects.go:234)
 };
-constexpr int kBoxGroup = 4;
+#ifndef PTB_BOX_GROUP
+#define PTB_BOX_GROUP 4
+#endif
+constexpr int kBoxGroup = PTB_BOX_GROUP;
 #ifndef PTB_SPHERE_GROUP
 #define PTB_SPHERE_GROUP 2
 #endif
