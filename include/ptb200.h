@@ -17,6 +17,10 @@
  * an internal mutex); any OS thread may call (cudaSetDevice is done per call), which is what
  * a goroutine-per-render caller such as internal/ui/app.go:135 needs.
  * Ownership: the library never keeps a host pointer after a call returns.
+ * Determinism: a render is a pure function of (scene, cfg): same bytes run to run and on any number of streams.  Per
+ * pixel the samples are added in index order; frames with fewer than ~1.2 M pixels add them in up to 64 sub-range
+ * sums that are then added in order (so does a multi-device render), i.e. the same samples with fp32 sums
+ * re-associated.  ptb_scene_upload waits for the device before it replaces the scene.
  * One device, one frame at a time: the scene of the frame being rendered lives in the device's constant bank, so
  * renders issued through DIFFERENT contexts (or streams) of the SAME device must be ordered by the caller; the
  * host-buffer calls (ptb_render, ptb_render_accum, ptb_primary_hits) synchronise before they return.
