@@ -162,6 +162,8 @@ def main():
     ap.add_argument("--workload", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-spp", type=int, default=0, help="spp of the bounded CPU sample (0 = calibrate: ~15 s, or ~6 s per step for --impl reference)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--partition", default="samples", choices=["samples", "rows"],
+                    help="N > 1: sample ranges + NCCL reduce of the fp32 sums (default), or interleaved rows + all_gather of RGBA8")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3                      # timing rule: W >= 3
@@ -173,7 +175,8 @@ def main():
     mesh_note = f" + {C4_MESH[args.workload][0] * C4_MESH[args.workload][1] * 2} triangle heightfield" if args.workload in C4_MESH else ""
     config = {"workload": f"{args.workload}: scenes/{name}.json{mesh_note} {W}x{H}, {spp} spp, max depth {depth}", "scene": name,
               "width": W, "height": H, "samples_per_px": spp, "max_depth": depth,
-              "partition": "sample ranges per rank + NCCL reduce to rank 0" if world > 1 else "single GPU",
+              "partition": ("single GPU" if world == 1 else "interleaved rows per rank + all_gather of RGBA8" if args.partition == "rows"
+                            else "sample ranges per rank + NCCL reduce to rank 0"),
               "l2": "flushed between steps (256 MiB write); inputs are a few KB of constants"}
     cores = os.cpu_count() or 1
 
@@ -226,6 +229,8 @@ def main():
         flush.zero_()                                            # L2 flush (a torch memset, not one of our kernels)
         if world == 1:
             ctx.render_device(cfg, rgba.data_ptr(), stream)      # 1 launch: integrate + epilogue
+        elif args.partition == "rows":
+            pdist.render_rows_distributed(ctx, cfg)              # interleaved rows, fused epilogue, all_gather of RGBA8
         else:
             pdist.render_partition(ctx, cfg, rank, world, accum, stream)
             pdist.reduce_to_root(accum)
@@ -240,6 +245,11 @@ def main():
         if world == 1:
             # the reference-facing call: scene flatten + upload (H2D), render, D2H into the caller's image
             engine.RenderInto(sc, engine.RenderConfig(W, H, spp, depth), host_img, ctx=ctx, seed=1)
+        elif args.partition == "rows":
+            ctx.upload(sc)
+            img = pdist.render_rows_distributed(ctx, cfg)
+            if rank == 0:
+                host_pinned.copy_(img)
         else:
             ctx.upload(sc)
             pdist.render_partition(ctx, cfg, rank, world, accum, stream)
@@ -337,7 +347,7 @@ def main():
                     "d2h_bytes_per_step": W * H * 4, "ms_per_step": e2e_s / args.steps * 1e3,
                     "api": "engine.RenderInto(scene, cfg, host image)" if world == 1 else
                            "scene upload + dist.render_partition + NCCL reduce + epilogue + D2H on rank 0"},
-            "gpu_launches": args.steps * (1 if world == 1 else 2),
+            "gpu_launches": args.steps * (1 if world == 1 or args.partition == "rows" else 2),
             "clocks": clocks,
         }
         if bvh["n_triangles"]:

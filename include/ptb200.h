@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 3   /* 2: meshes (ptb_scene.n_mesh ...), 3: ptb_multi_* */
+#define PTB_ABI_VERSION 4   /* 2: meshes (ptb_scene.n_mesh ...), 3: ptb_multi_*, 4: ptb_cfg.row_offset/row_step */
 
 enum {
     PTB_OK = 0,
@@ -120,6 +120,12 @@ typedef struct {
     int32_t sample_begin;   /* this context traces samples [sample_begin, sample_begin+sample_count) of    */
     int32_t sample_count;   /* every pixel; sample_count <= 0 means all of [0, samples_per_px)            */
     uint32_t flags;         /* PTB_FLAG_* */
+    /* Row partition (multi-GPU by image tiles instead of sample ranges): row_step > 1 renders only the rows
+     * row_offset, row_offset + row_step, ... of the frame.  Every output of such a call is COMPACT: it holds just
+     * those rows, ptb_rows_of(cfg) of them, in order.  Pixels are computed exactly as in a whole-frame render (same
+     * camera, same RNG keys), so interleaving the ranks' rows gives the single-device image bit for bit.
+     * row_step <= 1: all rows (row_offset must then be 0). */
+    int32_t row_offset, row_step;
 } ptb_cfg;
 
 #define PTB_FLAG_STATS 1u       /* run the counting variant of the integrator (slower); fills ptb_stats */
@@ -184,6 +190,7 @@ int ptb_world_get(ptb_ctx* ctx, int i, double out[19]);
 /* The whole of renderIntoCPU (renderer.go:44-246) into a HOST image: rgba is height rows of
  * `stride` bytes (stride >= 4*width), top row first, R,G,B,A=255 per pixel — the layout of
  * image.RGBA.Pix/.Stride the caller of RenderInto owns.  progress may be NULL. */
+int ptb_rows_of(const ptb_cfg* cfg);   /* rows a call with this cfg outputs: height, or ceil((height - row_offset) / row_step) */
 int ptb_render(ptb_ctx* ctx, const ptb_cfg* cfg, uint8_t* rgba, size_t stride,
                ptb_progress_fn progress, void* user);
 

@@ -48,7 +48,7 @@ class PtbScene(C.Structure):
 class PtbCfg(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("samples_per_px", C.c_int32),
                 ("max_depth", C.c_int32), ("seed", C.c_uint32), ("sample_begin", C.c_int32),
-                ("sample_count", C.c_int32), ("flags", C.c_uint32)]
+                ("sample_count", C.c_int32), ("flags", C.c_uint32), ("row_offset", C.c_int32), ("row_step", C.c_int32)]
 
 
 class PtbStats(C.Structure):
@@ -90,6 +90,7 @@ SYMBOLS = {
     "ptb_scene_upload": (C.c_int, [C.c_void_p, C.POINTER(PtbScene)]),
     "ptb_world_size": (C.c_int, [C.c_void_p]),
     "ptb_world_get": (C.c_int, [C.c_void_p, C.c_int, _dp]),
+    "ptb_rows_of": (C.c_int, [C.POINTER(PtbCfg)]),
     "ptb_render": (C.c_int, [C.c_void_p, C.POINTER(PtbCfg), C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "ptb_render_accum": (C.c_int, [C.c_void_p, C.POINTER(PtbCfg), C.c_void_p]),
     "ptb_render_accum_device": (C.c_int, [C.c_void_p, C.POINTER(PtbCfg), C.c_void_p, C.c_void_p]),

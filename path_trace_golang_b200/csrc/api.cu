@@ -179,6 +179,11 @@ int ensure(ptb_ctx* c, void** p, size_t* cap, size_t need, bool pinned_host = fa
     return PTB_OK;
 }
 
+int rows_of(const ptb_cfg* cfg) {
+    if (cfg->row_step <= 1) return cfg->height;
+    return (cfg->height - cfg->row_offset + cfg->row_step - 1) / cfg->row_step;
+}
+
 int check_cfg(ptb_ctx* c, const ptb_cfg* cfg, int& s0, int& s1) {
     if (!cfg) return fail(c, PTB_ERR_INVALID, "cfg is NULL");
     if (cfg->width < 2 || cfg->height < 2)   // 1/(W-1), 1/(H-1) (renderer.go:95-96) need W,H >= 2
@@ -191,6 +196,8 @@ int check_cfg(ptb_ctx* c, const ptb_cfg* cfg, int& s0, int& s1) {
         if (s0 < 0 || s1 > cfg->samples_per_px)
             return fail(c, PTB_ERR_INVALID, "sample range [%d,%d) outside [0,%d)", s0, s1, cfg->samples_per_px);
     }
+    if (cfg->row_step <= 1 ? cfg->row_offset != 0 : (cfg->row_offset < 0 || cfg->row_offset >= cfg->row_step || cfg->row_offset >= cfg->height))
+        return fail(c, PTB_ERR_INVALID, "row partition (offset %d, step %d) is not valid for %d rows", cfg->row_offset, cfg->row_step, cfg->height);
     if (!c->has_scene) return fail(c, PTB_ERR_NO_SCENE, "no scene uploaded");
     return PTB_OK;
 }
@@ -217,8 +224,10 @@ int render_launch(ptb_ctx* c, const ptb_cfg* cfg, int s0, int s1, float* d_accum
     const bool dbg_timing = std::getenv("PTB_DEBUG_TIMING") != nullptr;   // only meaningful in -DPTB_WF_TIMING builds
     if (stats || dbg_timing) CK(c, cudaMemsetAsync(c->d_stats, 0, sizeof(unsigned long long) * (kStatsWords + 24), stream));
 
+    const int R = rows_of(cfg);                       // rows this launch outputs (row partition: a subset, compact)
     FrameParams fp{};
     fp.width = W; fp.height = H; fp.s_begin = s0; fp.s_end = s1;
+    fp.rows = R; fp.row_offset = cfg->row_step > 1 ? cfg->row_offset : 0; fp.row_step = cfg->row_step > 1 ? cfg->row_step : 1;
     fp.spp_total = cfg->samples_per_px; fp.max_depth = cfg->max_depth;
     fp.seed_key = fmix_host(cfg->seed ^ 0x9E3779B9u);
     fp.inv_w = 1.0f / (float)(W - 1); fp.inv_h = 1.0f / (float)(H - 1); fp.h_minus_1 = (float)(H - 1);
@@ -231,6 +240,10 @@ int render_launch(ptb_ctx* c, const ptb_cfg* cfg, int s0, int s1, float* d_accum
     }
     const bool mega = (cfg->flags & PTB_FLAG_MEGAKERNEL) != 0 || cfg->max_depth <= 0;
     if (mega && cfg->max_depth > 0 && c->d_bvh_nodes) return fail(c, PTB_ERR_INVALID, "the megakernel integrator does not support meshes");
+    if (mega && R != H) {
+        if (cfg->max_depth > 0) return fail(c, PTB_ERR_INVALID, "the megakernel integrator does not support row partitions");
+        fp.height = R;                                    // black frame: only the output size matters
+    }
     if (mega) {
         e = launch_integrator(fp, stats, c->h_scene->n_obj, c->h_scene->n_mat, stream);
     } else {
@@ -239,14 +252,14 @@ int render_launch(ptb_ctx* c, const ptb_cfg* cfg, int s0, int s1, float* d_accum
         fp.split_k = 1;
         if (cfg->flags & PTB_FLAG_WAVEQUEUE) e = launch_integrator_wq(fp, stats, c->h_scene->n_obj, c->h_scene->n_mat, c->prop.multiProcessorCount, stream);
         else {
-            const int k = std::getenv("PTB_NO_SPLIT") ? 1 : wf_split_factor(c->prop.multiProcessorCount, (long long)W * H, s1 - s0);
+            const int k = std::getenv("PTB_NO_SPLIT") ? 1 : wf_split_factor(c->prop.multiProcessorCount, (long long)W * H, s1 - s0);   // of the WHOLE frame: a row partition adds every pixel's samples in the same order
             if (k > 1) {                                   // small frame: (pixel, sample sub-range) work items, summed afterwards
-                int rc = ensure(c, (void**)&c->d_planes, &c->planes_cap, (size_t)k * W * H * 3 * sizeof(float));
+                int rc = ensure(c, (void**)&c->d_planes, &c->planes_cap, (size_t)k * W * R * 3 * sizeof(float));
                 if (rc) return rc;
                 fp.split_k = k; fp.planes = c->d_planes;
             }
             e = launch_integrator_wf(fp, stats, c->h_scene->n_obj, c->h_scene->n_mat, c->prop.multiProcessorCount, stream);
-            if (!e && k > 1) e = launch_finalize_planes(c->d_planes, k, W, H, cfg->samples_per_px, d_accum, resume ? 1 : 0, d_rgba, stream);
+            if (!e && k > 1) e = launch_finalize_planes(c->d_planes, k, W, R, cfg->samples_per_px, d_accum, resume ? 1 : 0, d_rgba, stream);
         }
     }
     if (e) return fail(c, PTB_ERR_CUDA, "integrator launch: %s", cudaGetErrorString((cudaError_t)e));
@@ -291,6 +304,7 @@ int fetch_stats(ptb_ctx* c, bool stats, float ms) {
 extern "C" {
 
 int ptb_abi_version(void) { return PTB_ABI_VERSION; }
+int ptb_rows_of(const ptb_cfg* cfg) { return cfg ? rows_of(cfg) : PTB_ERR_INVALID; }
 
 int ptb_create(int device, ptb_ctx** out) {
     if (!out) return fail(nullptr, PTB_ERR_INVALID, "out is NULL");
@@ -705,7 +719,7 @@ int ptb_render_accum(ptb_ctx* c, const ptb_cfg* cfg, float* rgb_sum) {
     if ((rc = check_cfg(c, cfg, s0, s1))) return rc;
     if (!rgb_sum) return fail(c, PTB_ERR_INVALID, "rgb_sum is NULL");
     CK(c, cudaSetDevice(c->device));
-    const size_t bytes = (size_t)cfg->width * cfg->height * 3 * sizeof(float);
+    const size_t bytes = (size_t)cfg->width * rows_of(cfg) * 3 * sizeof(float);
     if ((rc = ensure(c, (void**)&c->d_accum, &c->accum_cap, bytes))) return rc;
     CK(c, cudaEventRecord(c->ev0, c->stream));
     if ((rc = render_launch(c, cfg, s0, s1, c->d_accum, nullptr, c->stream))) return rc;
@@ -723,7 +737,7 @@ int ptb_render(ptb_ctx* c, const ptb_cfg* cfg, uint8_t* rgba, size_t stride, ptb
     int s0 = 0, s1 = 0, rc;
     if ((rc = check_cfg(c, cfg, s0, s1))) return rc;
     if (!rgba) return fail(c, PTB_ERR_INVALID, "rgba is NULL");
-    const int W = cfg->width, H = cfg->height;
+    const int W = cfg->width, H = rows_of(cfg);       // (row partition: H compact rows)
     if (stride < (size_t)W * 4) return fail(c, PTB_ERR_INVALID, "stride %zu < 4*width", stride);
     if (s0 != 0 || s1 != cfg->samples_per_px) return fail(c, PTB_ERR_INVALID, "ptb_render needs the full sample range (use ptb_render_accum*)");
     CK(c, cudaSetDevice(c->device));
@@ -885,6 +899,7 @@ int ptb_multi_render(ptb_multi* m, const ptb_cfg* cfg, uint8_t* rgba, size_t str
     std::lock_guard<std::mutex> lk(m->mu);
     const int n = (int)m->ctx.size(), W = cfg->width, H = cfg->height, spp = cfg->samples_per_px;
     if (W < 2 || H < 2 || spp < 1) return mfail(m, PTB_ERR_INVALID, "bad frame configuration");
+    if (cfg->row_step > 1 || cfg->row_offset != 0) return mfail(m, PTB_ERR_INVALID, "ptb_multi_render partitions the samples itself: no row partition");
     if (stride < (size_t)W * 4) return mfail(m, PTB_ERR_INVALID, "stride < 4*width");
     const size_t bytes = (size_t)W * H * 3 * sizeof(float);
     if (m->accum_cap < bytes) {

@@ -656,7 +656,7 @@ static int launch_wf_variant(const FrameParams& fp, size_t smem, int sm_count, c
         if (e != cudaSuccess) return (int)e;
         blocks_per_sm = nb > 0 ? nb : 1;
     }
-    const long long n_pix = (long long)fp.width * fp.height;
+    const long long n_pix = (long long)fp.width * fp.rows;
     long long grid = (long long)sm_count * (MESH && blocks_per_sm > kMeshBlocksPerSm ? kMeshBlocksPerSm : blocks_per_sm);   // trav_scratch is sized for kMeshBlocksPerSm
     const long long need = (n_pix * (fp.split_k > 1 ? fp.split_k : 1) + WF_SLOTS - 1) / WF_SLOTS;
     if (grid > need) grid = need;

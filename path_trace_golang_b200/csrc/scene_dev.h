@@ -86,6 +86,7 @@ struct Camera64 {
 
 struct FrameParams {
     int32_t width, height;
+    int32_t rows, row_offset, row_step;   // wavefront kernel: the launch renders `rows` rows (row_offset + k * row_step) into compact outputs
     int32_t s_begin, s_end;      // sample range of every pixel traced by this launch
     int32_t spp_total;           // divisor of the pixel epilogue
     int32_t max_depth;

@@ -104,9 +104,10 @@ __device__ __forceinline__ void path_regen(SS& S, const FrameParams& fp, int n_p
         S.ax[j] = a0; S.ay[j] = a1; S.az[j] = a2;
     }
     S.smp[j] = s;
-    const int px = pix % fp.width, py = pix / fp.width;
+    const int ly = pix / fp.width, px = pix - ly * fp.width;
+    const int py = ly * fp.row_step + fp.row_offset;         // row partition: compact row ly is row py of the frame
     Rng rng;
-    rng.key = fmix(fmix(fp.seed_key ^ (uint32_t)pix) + (uint32_t)s * kGolden);
+    rng.key = fmix(fmix(fp.seed_key ^ (uint32_t)(py * fp.width + px)) + (uint32_t)s * kGolden);
     rng.ctr = 0u;
     const float u = ((float)px + rng.peek(0)) * fp.inv_w;                       // renderer.go:182
     const float v = ((fp.h_minus_1 - (float)py) + rng.peek(1)) * fp.inv_h;      // renderer.go:174,183
@@ -342,7 +343,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
     const DevMat* __restrict__ s_mat = reinterpret_cast<const DevMat*>(s_blob + 2 * n_obj);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int n_pix = fp.width * fp.height;
+    const int n_pix = fp.width * fp.rows;
     const int n_box = c_scene.n_box;
     const int n_box_groups = c_scene.n_box_groups, n_plane_run = c_scene.n_plane_run, n_sphere_groups = c_scene.n_sphere_groups;
     const int plane_off4 = c_scene.plane_off4, sphere_off4 = c_scene.sphere_off4, n_typed = c_scene.n_typed, sphere_base = n_box + n_plane_run;

@@ -90,18 +90,23 @@ class Context:
 
     @staticmethod
     def cfg(width, height, spp, max_depth, seed=1, sample_begin=0, sample_count=0, stats=False, megakernel=False,
-            wavequeue=None) -> PtbCfg:
+            wavequeue=None, row_offset=0, row_step=0) -> PtbCfg:
         import os
         if wavequeue is None:
             wavequeue = bool(os.environ.get("PTB_WAVEQUEUE"))
         flags = (PTB_FLAG_STATS if stats else 0) | (PTB_FLAG_MEGAKERNEL if megakernel else 0) | (4 if wavequeue and not megakernel else 0)
         return PtbCfg(int(width), int(height), int(spp), int(max_depth), int(seed) & 0xFFFFFFFF, int(sample_begin),
-                      int(sample_count), flags)
+                      int(sample_count), flags, int(row_offset), int(row_step))
+
+    @staticmethod
+    def rows_of(cfg: PtbCfg) -> int:
+        """Rows a call with this cfg outputs (row partition: a compact subset of the frame's rows)."""
+        return cfg.height if cfg.row_step <= 1 else (cfg.height - cfg.row_offset + cfg.row_step - 1) // cfg.row_step
 
     def render(self, cfg: PtbCfg, out: np.ndarray | None = None, progress=None) -> np.ndarray:
         """ptb_render: host RGBA8 image (H, W, 4)."""
         if out is None:
-            out = np.zeros((cfg.height, cfg.width, 4), dtype=np.uint8)
+            out = np.zeros((self.rows_of(cfg), cfg.width, 4), dtype=np.uint8)
         assert out.dtype == np.uint8 and out.ndim == 3 and out.shape[2] == 4 and out.strides[1] == 4 and out.strides[2] == 1
         cb = PROGRESS_FN(lambda _u: progress()) if progress is not None else None
         self._check(self._L.ptb_render(self._h, C.byref(cfg), out.ctypes.data, out.strides[0],
@@ -110,7 +115,7 @@ class Context:
 
     def render_accum(self, cfg: PtbCfg) -> np.ndarray:
         """ptb_render_accum: host fp32 sums (H, W, 3) of the cfg's sample range."""
-        out = np.empty((cfg.height, cfg.width, 3), dtype=np.float32)
+        out = np.empty((self.rows_of(cfg), cfg.width, 3), dtype=np.float32)
         self._check(self._L.ptb_render_accum(self._h, C.byref(cfg), out.ctypes.data))
         return out
 

@@ -89,3 +89,49 @@ def test_finalize_host_matches_oracle_epilogue(oracle_mod):
     sums = (rng.random((31, 17, 3)) ** 3 * 40).astype(np.float32)
     sums[0, 0] = [0.0, 1e-9, 1e6]
     assert (finalize_host(sums, 7) == oracle_mod.finalize(sums.astype(np.float64), 7)).all()
+
+
+def test_row_partition_assembles_the_frame():
+    """Interleaved-row partition (dist.rows_of_rank / assemble_rows): the ranks' compact row sets tile the frame."""
+    from path_trace_golang_b200.dist import assemble_rows, rows_of_rank
+    for H in (2, 3, 7, 90, 1080):
+        for world in (1, 2, 3, 8):
+            assert sum(rows_of_rank(H, r, world) for r in range(world)) == H
+            full = torch.arange(H * 5 * 4, dtype=torch.int64).reshape(H, 5, 4)
+            rows_max = rows_of_rank(H, 0, world)
+            parts = []
+            for r in range(world):
+                p = torch.full((rows_max, 5, 4), -1, dtype=torch.int64)      # padded like the all_gather buffer
+                mine = full[r::world]
+                p[:mine.shape[0]] = mine
+                parts.append(p)
+            assert torch.equal(assemble_rows(parts, H), full)
+
+
+def _rows_worker(rank, world, port, H, W, out_path):
+    import sys
+    sys.path.insert(0, str(ROOT))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from path_trace_golang_b200 import dist as pdist
+    full = (torch.arange(H * W * 4, dtype=torch.int64) % 251).to(torch.uint8).reshape(H, W, 4)    # what a renderer would produce
+    rows_max = pdist.rows_of_rank(H, 0, world)
+    mine = torch.zeros((rows_max, W, 4), dtype=torch.uint8)
+    part = full[rank::world]
+    mine[:part.shape[0]] = part
+    gathered = torch.empty((world * rows_max, W, 4), dtype=torch.uint8)
+    dist.all_gather_into_tensor(gathered, mine)
+    img = pdist.assemble_rows(list(gathered.view(world, rows_max, W, 4)), H)
+    ok = torch.equal(img, full)
+    if rank == 0:
+        np.save(out_path, np.array([int(ok)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_partition_gather_gloo(world, tmp_path):
+    out = tmp_path / "ok.npy"
+    mp.spawn(_rows_worker, args=(world, _free_port(), 37, 16, str(out)), nprocs=world, join=True)
+    assert np.load(out)[0] == 1

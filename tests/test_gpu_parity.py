@@ -275,3 +275,27 @@ def test_small_frame_sample_split_matches_whole_pixels(ctx, host_scenes, monkeyp
     b = ctx.render_accum(ctx.cfg(320, 180, 16, 8, seed=1, sample_begin=7, sample_count=9))
     f = ctx.render_accum(ctx.cfg(320, 180, 16, 8, seed=1))
     assert np.allclose(a.astype(np.float64) + b, f, rtol=1e-5, atol=1e-6)
+
+
+def test_row_partition_is_bit_identical(ctx, host_scenes):
+    """ptb_cfg.row_offset/row_step (multi-GPU by image tiles): every rank's compact rows, interleaved, are the
+    single-device image bit for bit — same camera rays, same RNG keys, same per-pixel sums (ranks emulated here)."""
+    from path_trace_golang_b200.dist import rows_of_rank
+    ctx.upload(host_scenes["metal_glass_room"])
+    for (w, h, spp, depth, world) in [(320, 180, 8, 8, 2), (101, 67, 5, 8, 3), (1920, 1080, 2, 6, 8)]:
+        whole_img = ctx.render(ctx.cfg(w, h, spp, depth, seed=4))
+        whole_sum = ctx.render_accum(ctx.cfg(w, h, spp, depth, seed=4))
+        img = np.zeros_like(whole_img)
+        acc = np.zeros_like(whole_sum)
+        for r in range(world):
+            cfg = ctx.cfg(w, h, spp, depth, seed=4, row_offset=r, row_step=world)
+            assert ctx.rows_of(cfg) == rows_of_rank(h, r, world)
+            part = ctx.render(cfg)
+            assert part.shape == (rows_of_rank(h, r, world), w, 4)
+            img[r::world] = part
+            acc[r::world] = ctx.render_accum(cfg)
+        assert np.array_equal(acc, whole_sum) and np.array_equal(img, whole_img), (w, h, world)
+    with pytest.raises(Exception):
+        ctx.render(ctx.cfg(64, 64, 2, 4, row_offset=3, row_step=2))
+    with pytest.raises(Exception):
+        ctx.render(ctx.cfg(64, 64, 2, 4, row_offset=1, row_step=0))
