@@ -252,7 +252,8 @@ int render_launch(ptb_ctx* c, const ptb_cfg* cfg, int s0, int s1, float* d_accum
         fp.split_k = 1;
         if (cfg->flags & PTB_FLAG_WAVEQUEUE) e = launch_integrator_wq(fp, stats, c->h_scene->n_obj, c->h_scene->n_mat, c->prop.multiProcessorCount, stream);
         else {
-            const int k = std::getenv("PTB_NO_SPLIT") ? 1 : wf_split_factor(c->prop.multiProcessorCount, (long long)W * H, s1 - s0);   // of the WHOLE frame: a row partition adds every pixel's samples in the same order
+            int k = std::getenv("PTB_NO_SPLIT") ? 1 : wf_split_factor(c->prop.multiProcessorCount, (long long)W * H, s1 - s0);
+            if (const char* force = std::getenv("PTB_SPLIT")) { k = std::atoi(force); if (k < 1) k = 1; if (k > s1 - s0) k = s1 - s0; if (k > 64) k = 64; }   // tuning   // of the WHOLE frame: a row partition adds every pixel's samples in the same order
             if (k > 1) {                                   // small frame: (pixel, sample sub-range) work items, summed afterwards
                 int rc = ensure(c, (void**)&c->d_planes, &c->planes_cap, (size_t)k * W * R * 3 * sizeof(float));
                 if (rc) return rc;
