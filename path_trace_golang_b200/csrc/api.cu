@@ -917,7 +917,6 @@ int ptb_multi_render(ptb_multi* m, const ptb_cfg* cfg, uint8_t* rgba, size_t str
         m->accum_cap = bytes;
     }
     // every device traces its sample range (asynchronous launches: the devices run concurrently)
-    int active = 0;
     for (int k = 0; k < n; k++) {
         const int base = spp / n, rem = spp % n;
         const int b = k * base + (k < rem ? k : rem), cnt = base + (k < rem ? 1 : 0);
@@ -930,7 +929,6 @@ int ptb_multi_render(ptb_multi* m, const ptb_cfg* cfg, uint8_t* rgba, size_t str
             sub.flags &= ~PTB_FLAG_STATS;
             int rc = ptb_render_accum_device(c, &sub, m->d_accum[k], c->stream);
             if (rc != PTB_OK) return mfail(m, rc, ptb_last_error(c));
-            active++;
         } else {
             cudaMemsetAsync(m->d_accum[k], 0, bytes, c->stream);
         }
@@ -962,7 +960,6 @@ int ptb_multi_render(ptb_multi* m, const ptb_cfg* cfg, uint8_t* rgba, size_t str
         float t = 0;
         if (cudaEventElapsedTime(&t, m->begin[k], m->done[k]) == cudaSuccess && t > m->render_ms) m->render_ms = t;
     }
-    (void)active;
     return PTB_OK;
 }
 
