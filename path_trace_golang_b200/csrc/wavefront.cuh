@@ -6,20 +6,23 @@
 // lives in shared memory (WF_SLOTS = 512 slots per 256-thread CTA) and, after every scan, the CTA's slots are
 // counting-sorted by the class of work they need, so that a warp shades 32 slots of the SAME class:
 //
-//   loop:  SCAN   thread i <-> slots i, i+256   closest hit over the world, two rays per object record
-//                                               (warp-uniform loop, operands from the constant bank via LDCU)
-//          SORT   ballot/popc per class -> per-warp counts -> shuffle prefix scan -> stable permutation (2 barriers)
+//   loop:  SCAN   thread i <-> slots i, i+256   closest hit over the world, two rays per record of the per-type scan
+//                                               tables (warp-uniform loops, operands from the constant bank via LDCU)
+//          SORT   ballots of the class bits -> in-warp ranks -> per-warp counts -> one shuffle prefix scan over
+//                                               pair-packed counts -> stable permutation (2 barriers)
 //          SHADE  warp w <-> 32-slot chunks w and 15-w of perm[]   scatter / terminate / regenerate, one class per
 //                                               chunk; perm[] is sorted heaviest class first (serpentine pairing)
 //
 // A slot is bound to one pixel at a time and walks that pixel's samples in order with its fp32 sum in shared
 // memory (deterministic per-pixel sum order, no atomics on radiance); when the pixel is done the slot writes it
 // out and takes the next pixel index from a global atomic counter — dynamic scheduling at pixel granularity, so
-// cheap sky pixels and expensive glass pixels balance across the whole chip.
+// cheap sky pixels and expensive glass pixels balance across the whole chip.  On small frames a work item is a
+// (pixel, sample sub-range) pair instead (FrameParams::split_k); with a row partition the items cover a subset of rows.
 //
 // Semantics are those of integrate_kernel (same helpers, same counter-RNG draw order), hence of the reference.
 // MESH = true adds the BVH traversal of bvh.cuh to the scan (separate instantiation: the traversal code costs the
-// mesh-free path 10 % if it is merely present).
+// mesh-free path 10 % if it is merely present): rays that reach the meshes' bounds are compacted CTA-wide, traversed by
+// persistent lanes under a per-iteration step budget, and suspended (class CL_CONT) when the budget runs out.
 #pragma once
 
 namespace ptb {
