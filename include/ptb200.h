@@ -232,6 +232,12 @@ int ptb_multi_render(ptb_multi* m, const ptb_cfg* cfg, uint8_t* rgba, size_t str
 /* device time of the last ptb_multi_render: slowest device's integrator, and the fused reduce+epilogue on device 0 */
 int ptb_multi_last_timing(ptb_multi* m, double* render_ms, double* reduce_ms);
 
+/* Test hook, host only (no CUDA call): builds the BVH over n_tri world-space triangles (9 floats each) exactly as
+ * ptb_scene_upload does and checks the emitted node array: every child box (centre/half extent in binary32) contains all
+ * the triangles below it, every triangle sits in exactly one leaf, links and counts are consistent.
+ * Returns the number of violations (0 = sound) or a negative PTB_ERR_*; n_nodes / max_depth may be NULL. */
+int64_t ptb_bvh_selfcheck(const float* tri_vertices, int64_t n_tri, int64_t* n_nodes, int32_t* max_depth);
+
 /* Measurement helper: FP32 FMA throughput of the device (2 flop per FMA), the roofline
  * denominator MEASURED_PEAKS.json does not carry. */
 int ptb_measure_fp32_peak(ptb_ctx* ctx, double* tflops);

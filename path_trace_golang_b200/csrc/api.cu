@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <array>
 #include <cfloat>
 #include <mutex>
 #include <string>
@@ -968,6 +969,64 @@ int ptb_multi_last_timing(ptb_multi* m, double* render_ms, double* reduce_ms) {
     if (render_ms) *render_ms = m->render_ms;
     if (reduce_ms) *reduce_ms = m->reduce_ms;
     return PTB_OK;
+}
+
+int64_t ptb_bvh_selfcheck(const float* tri_vertices, int64_t n_tri, int64_t* n_nodes, int32_t* max_depth) {
+    if (!tri_vertices || n_tri < 1) return PTB_ERR_INVALID;
+    std::vector<int32_t> zeros((size_t)n_tri, 0);
+    BvhBuildInput in{tri_vertices, n_tri, zeros.data(), zeros.data()};
+    BvhBuildOutput out;
+    unsigned hw = std::thread::hardware_concurrency();
+    build_bvh(in, out, hw ? (int)hw : 4);
+    if (n_nodes) *n_nodes = (int64_t)out.nodes.size();
+    if (max_depth) *max_depth = out.max_depth;
+    int64_t bad = 0;
+    std::vector<char> seen((size_t)n_tri, 0);
+    auto f2i = [](float f) { int32_t i; std::memcpy(&i, &f, 4); return i; };
+    // walk the tree; `box` = (c, h) of the child we came through (nullptr for the root)
+    struct Item { int32_t link; float c[3], h[3]; bool has_box; };
+    std::vector<Item> stack;
+    stack.push_back({0, {0, 0, 0}, {0, 0, 0}, false});
+    auto inside = [](const float* c, const float* h, const float* p) {
+        for (int k = 0; k < 3; k++) if (!((double)p[k] >= (double)c[k] - h[k] && (double)p[k] <= (double)c[k] + h[k])) return false;
+        return true;
+    };
+    // containment is checked triangle by triangle against EVERY ancestor box: carry the chain of boxes
+    std::vector<std::vector<std::pair<std::array<float, 3>, std::array<float, 3>>>> chains;
+    chains.push_back({});
+    std::vector<int> chain_of{0};
+    while (!stack.empty()) {
+        Item it = stack.back(); stack.pop_back();
+        const int my_chain = chain_of.back(); chain_of.pop_back();
+        if (it.link >= 0) {
+            if (it.link >= (int32_t)out.nodes.size()) { bad++; continue; }
+            const BvhNode& nd = out.nodes[it.link];
+            for (int ch = 0; ch < 2; ch++) {
+                const int32_t l = f2i(nd.q[12 + ch]);
+                if (l == kEmptyLeaf) { if (!(nd.q[6 * ch + 3] < 0.0f)) bad++; continue; }
+                Item nx{l, {nd.q[6 * ch], nd.q[6 * ch + 1], nd.q[6 * ch + 2]}, {nd.q[6 * ch + 3], nd.q[6 * ch + 4], nd.q[6 * ch + 5]}, true};
+                auto chain = chains[my_chain];
+                chain.push_back({{nx.c[0], nx.c[1], nx.c[2]}, {nx.h[0], nx.h[1], nx.h[2]}});
+                chains.push_back(std::move(chain));
+                stack.push_back(nx); chain_of.push_back((int)chains.size() - 1);
+            }
+        } else {
+            const int32_t link = ~it.link, first = link >> 2, cnt = (link & 3) + 1;
+            for (int k = 0; k < cnt; k++) {
+                if (first + k >= (int32_t)out.tris.size()) { bad++; continue; }
+                const BvhTri& t = out.tris[first + k];
+                const int32_t id = f2i(t.q[3]);
+                if (id < 0 || id >= n_tri || seen[id]) { bad++; continue; }
+                seen[id] = 1;
+                const float* v = tri_vertices + 9 * (size_t)id;
+                for (const auto& bx : chains[my_chain])
+                    for (int q = 0; q < 3; q++) if (!inside(bx.first.data(), bx.second.data(), v + 3 * q)) bad++;
+            }
+        }
+        chains[my_chain].clear(); chains[my_chain].shrink_to_fit();
+    }
+    for (int64_t i = 0; i < n_tri; i++) if (!seen[i]) bad++;
+    return bad;
 }
 
 int ptb_measure_fp32_peak(ptb_ctx* c, double* tflops) {

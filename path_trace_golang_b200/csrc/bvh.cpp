@@ -70,7 +70,18 @@ struct Builder {
             }
         }
         int64_t mid;
-        if (best_axis < 0) {                 // all centroids coincide: split in the middle
+        int lg = 0;
+        while ((1ll << lg) < count) lg++;
+        if (best_axis >= 0 && depth + lg >= 35) {
+            // SAH on overlapping triangle soup can peel off a few triangles per level; the traversal stack is finite
+            // (api.cu rejects depth > 38), so near the limit split at the centroid median of the widest axis instead:
+            // from here on depth + log2(count) no longer grows
+            int ax = 0;
+            for (int k = 1; k < 3; k++) if (cb.hi[k] - cb.lo[k] > cb.hi[ax] - cb.lo[ax]) ax = k;
+            std::nth_element(idx.begin() + first, idx.begin() + first + count / 2, idx.begin() + first + count,
+                             [&](int64_t a, int64_t b) { return cent[3 * a + ax] < cent[3 * b + ax]; });
+            mid = first + count / 2;
+        } else if (best_axis < 0) {          // all centroids coincide: split in the middle
             mid = first + count / 2;
         } else {
             const float lo = cb.lo[best_axis], scale = kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
@@ -147,10 +158,17 @@ void build_bvh(const BvhBuildInput& in, BvhBuildOutput& out, int threads) {
         return ~(int32_t)((c->first << 2) | (c->count - 1));
     };
     auto put_box = [&](BvhNode& nd, int which, const Box* b) {
-        float lo[3], hi[3];
-        for (int k = 0; k < 3; k++) { lo[k] = b ? b->lo[k] - pad : INFINITY; hi[k] = b ? b->hi[k] + pad : -INFINITY; }
-        if (which == 0) { nd.q[0] = lo[0]; nd.q[1] = lo[1]; nd.q[2] = lo[2]; nd.q[3] = hi[0]; nd.q[4] = hi[1]; nd.q[5] = hi[2]; }
-        else { nd.q[6] = lo[0]; nd.q[7] = lo[1]; nd.q[8] = lo[2]; nd.q[9] = hi[0]; nd.q[10] = hi[1]; nd.q[11] = hi[2]; }
+        // (centre, half extent) in binary32 such that [c - h, c + h] contains the padded box: the half extent absorbs the
+        // rounding of the centre and is rounded up.  An empty child gets h = -1 (far < near on every axis: never hit).
+        float c[3] = {0.0f, 0.0f, 0.0f}, h[3] = {-1.0f, -1.0f, -1.0f};
+        if (b) for (int k = 0; k < 3; k++) {
+            const double lo = (double)b->lo[k] - pad, hi = (double)b->hi[k] + pad;
+            c[k] = (float)(0.5 * (lo + hi));
+            const double need = std::max(hi - (double)c[k], (double)c[k] - lo);
+            h[k] = std::nextafter((float)need, INFINITY);
+        }
+        float* q = nd.q + (which == 0 ? 0 : 6);
+        q[0] = c[0]; q[1] = c[1]; q[2] = c[2]; q[3] = h[0]; q[4] = h[1]; q[5] = h[2];
     };
     out.nodes.emplace_back();
     if (!root->child[0]) {                                   // <= kMaxLeafTris triangles: root with one leaf child

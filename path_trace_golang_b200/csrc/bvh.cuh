@@ -56,16 +56,13 @@ __device__ __forceinline__ int trav_round(const float4* __restrict__ nodes, cons
         const float4 q0 = __ldg(nodes + 4 * cur), q1 = __ldg(nodes + 4 * cur + 1), q2 = __ldg(nodes + 4 * cur + 2),
                      q3 = __ldg(nodes + 4 * cur + 3);
         if (STATS) st[ST_BVH_NODES]++;
-        float ax = fmaf(q0.x, r.inv.x, -r.oi.x), bx = fmaf(q0.w, r.inv.x, -r.oi.x);
-        float ay = fmaf(q0.y, r.inv.y, -r.oi.y), by = fmaf(q1.x, r.inv.y, -r.oi.y);
-        float az = fmaf(q0.z, r.inv.z, -r.oi.z), bz = fmaf(q1.y, r.inv.z, -r.oi.z);
-        const float n0 = fmaxf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)), tmin);
-        const float f0 = fminf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), best);
-        ax = fmaf(q1.z, r.inv.x, -r.oi.x); bx = fmaf(q2.y, r.inv.x, -r.oi.x);
-        ay = fmaf(q1.w, r.inv.y, -r.oi.y); by = fmaf(q2.z, r.inv.y, -r.oi.y);
-        az = fmaf(q2.x, r.inv.z, -r.oi.z); bz = fmaf(q2.w, r.inv.z, -r.oi.z);
-        const float n1 = fmaxf(fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fminf(az, bz)), tmin);
-        const float f1 = fminf(fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fmaxf(az, bz)), best);
+        // children as (centre, half extent): near/far of an axis are (c - o)/d -+ h/|d| (see hit_box)
+        float cx = fmaf(q0.x, r.inv.x, -r.oi.x), cy = fmaf(q0.y, r.inv.y, -r.oi.y), cz = fmaf(q0.z, r.inv.z, -r.oi.z);
+        const float n0 = fmaxf(fmaxf(fmaxf(fmaf(-q0.w, r.ainv.x, cx), fmaf(-q1.x, r.ainv.y, cy)), fmaf(-q1.y, r.ainv.z, cz)), tmin);
+        const float f0 = fminf(fminf(fminf(fmaf(q0.w, r.ainv.x, cx), fmaf(q1.x, r.ainv.y, cy)), fmaf(q1.y, r.ainv.z, cz)), best);
+        cx = fmaf(q1.z, r.inv.x, -r.oi.x); cy = fmaf(q1.w, r.inv.y, -r.oi.y); cz = fmaf(q2.x, r.inv.z, -r.oi.z);
+        const float n1 = fmaxf(fmaxf(fmaxf(fmaf(-q2.y, r.ainv.x, cx), fmaf(-q2.z, r.ainv.y, cy)), fmaf(-q2.w, r.ainv.z, cz)), tmin);
+        const float f1 = fminf(fminf(fminf(fmaf(q2.y, r.ainv.x, cx), fmaf(q2.z, r.ainv.y, cy)), fmaf(q2.w, r.ainv.z, cz)), best);
         const bool h0 = f0 >= n0, h1 = f1 >= n1;
         const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
         if (h0 && h1) {

@@ -4,9 +4,10 @@
 // Layout (device, global memory, fetched with 16-byte loads):
 //   node  = 64 bytes = 4 x float4, cache-line aligned:  both children's boxes + both child links, so ONE node fetch
 //           decides both children ("Aila-Laine" BVH2 layout)
-//             q0 = (lo0.x, lo0.y, lo0.z, hi0.x)   q1 = (hi0.y, hi0.z, lo1.x, lo1.y)   q2 = (lo1.z, hi1.x, hi1.y, hi1.z)
-//             q3 = (bits c0, bits c1, 0, 0)       c >= 0: inner node index;  c < 0: leaf, ~c = first_tri << 2 | (count - 1)
-//           an empty child has an inverted box (lo = +inf, hi = -inf) and c = kEmptyLeaf
+//             boxes as (centre c, half extent h), the form whose slab test needs no per-axis min/max (integrator.cu hit_box):
+//             q0 = (c0.x, c0.y, c0.z, h0.x)   q1 = (h0.y, h0.z, c1.x, c1.y)   q2 = (c1.z, h1.x, h1.y, h1.z)
+//             q3 = (bits l0, bits l1, 0, 0)   link l >= 0: inner node index;  l < 0: leaf, ~l = first_tri << 2 | (count - 1)
+//           an empty child has h = -1 (never hit) and link kEmptyLeaf
 //   tri   = 48 bytes = 3 x float4, in leaf order:  (v0.xyz, bits tri_id)  (e1.xyz, bits meta)  (e2.xyz, bits world_idx)
 //           e1 = v1 - v0, e2 = v2 - v0 (binary32);  meta = the DevObj::meta of the mesh's material
 // Boxes are padded by 1e-5 x (largest absolute coordinate of the scene, at least 1) so that the fp32 slab test with
@@ -19,7 +20,7 @@ namespace ptb {
 
 struct alignas(64) BvhNode { float q[16]; };
 struct alignas(16) BvhTri { float q[12]; };
-constexpr int32_t kEmptyLeaf = 0x7fffffff;   // never followed (its box is inverted)
+constexpr int32_t kEmptyLeaf = 0x7fffffff;   // never followed (its box has a negative half extent)
 constexpr int kMaxLeafTris = 4;
 
 struct BvhBuildInput {

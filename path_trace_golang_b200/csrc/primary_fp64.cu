@@ -62,13 +62,13 @@ __device__ __forceinline__ bool hit64(const Obj64& ob, const double o[3], const 
 // binary64 (conservative), triangles are the binary32 (v0, e1, e2) records widened to binary64; Moeller-Trumbore
 // without FMA.  Result = the triangle of smallest t (lowest triangle id on ties), independent of the traversal order,
 // so it equals the oracle's brute-force scan bit for bit.
-__device__ __forceinline__ bool slab64(const float lo[3], const float hi[3], const double o[3], const double d[3], double tMin, double tMax) {
+__device__ __forceinline__ bool slab64(const double lo[3], const double hi[3], const double o[3], const double d[3], double tMin, double tMax) {
     double t0 = tMin, t1 = tMax;
 #pragma unroll
     for (int i = 0; i < 3; i++) {
         double invD = 1 / d[i];
-        double tNear = ((double)lo[i] - o[i]) * invD;
-        double tFar = ((double)hi[i] - o[i]) * invD;
+        double tNear = (lo[i] - o[i]) * invD;
+        double tFar = (hi[i] - o[i]) * invD;
         if (invD < 0) { double s = tNear; tNear = tFar; tFar = s; }
         if (tNear > t0) t0 = tNear;
         if (tFar < t1) t1 = tFar;
@@ -82,7 +82,9 @@ __device__ void bvh_closest64(const float4* __restrict__ nodes, const float4* __
     for (;;) {
         if (cur >= 0) {
             const float4 q0 = __ldg(nodes + 4 * cur), q1 = __ldg(nodes + 4 * cur + 1), q2 = __ldg(nodes + 4 * cur + 2), q3 = __ldg(nodes + 4 * cur + 3);
-            const float lo0[3] = {q0.x, q0.y, q0.z}, hi0[3] = {q0.w, q1.x, q1.y}, lo1[3] = {q1.z, q1.w, q2.x}, hi1[3] = {q2.y, q2.z, q2.w};
+            // nodes store (centre, half extent) in binary32; c -+ h is exact in binary64
+            const double lo0[3] = {(double)q0.x - q0.w, (double)q0.y - q1.x, (double)q0.z - q1.y}, hi0[3] = {(double)q0.x + q0.w, (double)q0.y + q1.x, (double)q0.z + q1.y};
+            const double lo1[3] = {(double)q1.z - q2.y, (double)q1.w - q2.z, (double)q2.x - q2.w}, hi1[3] = {(double)q1.z + q2.y, (double)q1.w + q2.z, (double)q2.x + q2.w};
             const bool h0 = slab64(lo0, hi0, o, d, tMin, closest), h1 = slab64(lo1, hi1, o, d, tMin, closest);
             const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
             if (h0 && h1) { if (sp < 48) stack[sp++] = c1; cur = c0; }

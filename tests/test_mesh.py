@@ -195,3 +195,29 @@ def test_gpu_bvh_is_reused_for_identical_meshes(ctx):
     assert ctx.bvh_info()["build_ms"] != first["build_ms"] and ctx.bvh_info()["n_triangles"] == first["n_triangles"]
     ctx.upload(scene.Parse(json.dumps(scene_json("example_simple"))))
     assert ctx.bvh_info()["n_triangles"] == 0
+
+
+def test_bvh_builder_selfcheck_cpu():
+    """Host-only: the emitted node array is sound — every child box (centre / half extent, binary32) contains all the
+    triangles below it, every triangle is in exactly one leaf (ptb_bvh_selfcheck, no CUDA involved)."""
+    import ctypes as C
+    from path_trace_golang_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(7)
+    cases = []
+    cases.append(rng.uniform(-5, 5, size=(20000, 9)).astype(np.float32))                      # soup
+    g = np.stack(np.meshgrid(np.arange(120), np.arange(80), indexing="ij"), -1).reshape(-1, 2).astype(np.float32)
+    h = lambda p: np.sin(p[:, 0] * 0.3) * np.cos(p[:, 1] * 0.2)
+    def vert(p): return np.stack([p[:, 0] * 0.1 - 6, h(p), p[:, 1] * 0.1 - 4], -1)
+    a, b, c, d = vert(g), vert(g + [1, 0]), vert(g + [0, 1]), vert(g + [1, 1])
+    cases.append(np.concatenate([np.concatenate([a, b, c], 1), np.concatenate([b, d, c], 1)]).astype(np.float32))   # heightfield
+    flat = rng.uniform(-1, 1, size=(3000, 9)).astype(np.float32); flat[:, 1::3] = 0.25            # axis-aligned, zero thickness
+    cases.append(flat)
+    cases.append((rng.uniform(-1, 1, size=(5000, 9)) * 1e4 + 3e5).astype(np.float32))            # large coordinates
+    cases.append(rng.uniform(-1, 1, size=(3, 9)).astype(np.float32))                             # fewer triangles than a leaf holds
+    for tri in cases:
+        tri = np.ascontiguousarray(tri)
+        n_nodes, depth = C.c_int64(), C.c_int32()
+        bad = L.ptb_bvh_selfcheck(tri.ctypes.data_as(C.POINTER(C.c_float)), len(tri), C.byref(n_nodes), C.byref(depth))
+        assert bad == 0, (len(tri), bad)
+        assert 1 <= n_nodes.value <= max(1, len(tri)) and 1 <= depth.value <= 38
