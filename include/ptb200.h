@@ -232,6 +232,13 @@ int ptb_multi_render(ptb_multi* m, const ptb_cfg* cfg, uint8_t* rgba, size_t str
 /* device time of the last ptb_multi_render: slowest device's integrator, and the fused reduce+epilogue on device 0 */
 int ptb_multi_last_timing(ptb_multi* m, double* render_ms, double* reduce_ms);
 
+/* Test hook, host only (no CUDA call): the device layout ptb_scene_upload would give the scene's analytic objects.
+ * order[k] = world index of device object k (at most cap entries are written); counts = {boxes, planes in the typed
+ * plane run, spheres in the typed sphere run, objects left to the generic loop, dielectric boxes and dielectric
+ * spheres of the typed exit search (both 0 when the search is not typed)}.  Returns the number of analytic objects
+ * or a negative PTB_ERR_* (message: ptb_last_error(NULL)). */
+int ptb_scene_device_order(const ptb_scene* scene, int32_t* order, int32_t cap, int32_t counts[6]);
+
 /* Test hook, host only (no CUDA call): builds the BVH over n_tri world-space triangles (9 floats each) exactly as
  * ptb_scene_upload does and checks the emitted node array: every child box (centre/half extent in binary32) contains all
  * the triangles below it, every triangle sits in exactly one leaf, links and counts are consistent.

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <array>
 #include <cfloat>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -969,6 +970,24 @@ int ptb_multi_last_timing(ptb_multi* m, double* render_ms, double* reduce_ms) {
     if (render_ms) *render_ms = m->render_ms;
     if (reduce_ms) *reduce_ms = m->reduce_ms;
     return PTB_OK;
+}
+
+int ptb_scene_device_order(const ptb_scene* s, int32_t* order, int32_t cap, int32_t counts[6]) {
+    if (!s || (!order && cap > 0) || !counts) return fail(nullptr, PTB_ERR_INVALID, "NULL argument");
+    if (s->n_obj < 0 || s->n_mat < 0 || s->n_mat > PTB_MAX_MATERIALS) return fail(nullptr, PTB_ERR_INVALID, "bad counts");
+    if (s->n_obj > 0 && (!s->obj_type || !s->obj_mat || !s->obj_pos || !s->obj_size)) return fail(nullptr, PTB_ERR_INVALID, "object arrays are NULL");
+    if (s->n_mat > 0 && (!s->mat_type || !s->mat_albedo || !s->mat_rough || !s->mat_ior || !s->mat_emit || !s->mat_power ||
+                         !s->mat_absorption || !s->mat_smoothness)) return fail(nullptr, PTB_ERR_INVALID, "material arrays are NULL");
+    WorldBuild wb;
+    int rc = build_world(nullptr, s, wb);
+    if (rc) return rc;
+    auto hs = std::make_unique<DevScene>();
+    std::vector<Obj64> w64;
+    build_device_tables(wb, s->n_mat, *hs, w64);
+    for (int k = 0; k < hs->n_obj && k < cap; k++) order[k] = hs->obj[k].world_idx;
+    counts[0] = hs->n_box; counts[1] = hs->n_plane_run; counts[2] = hs->n_sphere_run; counts[3] = hs->n_obj - hs->n_typed;
+    counts[4] = hs->n_dbox; counts[5] = hs->n_dsph;
+    return hs->n_obj;
 }
 
 int64_t ptb_bvh_selfcheck(const float* tri_vertices, int64_t n_tri, int64_t* n_nodes, int32_t* max_depth) {

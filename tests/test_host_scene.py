@@ -145,3 +145,52 @@ def test_save_png(tmp_path):
     engine.SavePNG(p, img)
     back = np.array(Image.open(p))
     assert back.shape == img.shape and (back == img).all()
+
+
+def test_device_order_keeps_the_tie_rules():
+    """Host-only hook ptb_scene_device_order: boxes first (world order), then the non-box objects in world order, of
+    which the leading planes and the spheres right after them get typed scan tables.  The reference's tie rules
+    (renderer.go:292-302: a later sphere/plane wins a tie, the first box wins) only survive if nothing else is reordered."""
+    import ctypes as C
+    import json
+    from path_trace_golang_b200 import _lib, scene
+    L = _lib.lib()
+
+    def order_of(sc):
+        flat = sc.flat()
+        buf = (C.c_int32 * 600)()
+        counts = (C.c_int32 * 6)()
+        n = L.ptb_scene_device_order(C.byref(flat), buf, 600, counts)
+        assert n >= 0, L.ptb_last_error(None)
+        return list(buf[:n]), list(counts)
+
+    def types_of(doc):
+        kept = [o["type"] for o in doc["objects"] if o["type"] in ("sphere", "sphere_light", "plane", "box")]
+        return ["sphere" if t == "sphere_light" else t for t in kept]
+
+    docs = [json.loads(open(scene_path(n)).read()) for n in ("example_simple", "test_scene", "metal_glass_room", "gpu_showcase", "test_comprehensive")]
+    mat = {"id": "m", "type": "lambert", "albedo": {"r": 0.5, "g": 0.5, "b": 0.5}}
+    glass = {"id": "g", "type": "dielectric", "ior": 1.5}
+    def obj(t, m="m"): return {"type": t, "position": {"x": 0, "y": 1, "z": 0}, "size": {"x": 1, "y": 1, "z": 1}, "material_id": m}
+    base = docs[0]
+    for seq in (["sphere", "plane", "box", "sphere", "plane", "box"], ["plane", "plane", "sphere", "box", "sphere"],
+                ["sphere", "sphere", "plane"], ["box"], ["plane"], []):
+        d = dict(base); d["materials"] = [mat, glass]
+        d["objects"] = [obj(t, "g" if i % 2 else "m") for i, t in enumerate(seq)]
+        docs.append(d)
+    for doc in docs:
+        sc = scene.Parse(json.dumps(doc))
+        order, (n_box, n_plane, n_sph, n_rest, n_dbox, n_dsph) = order_of(sc)
+        types = types_of(doc)
+        assert sorted(order) == list(range(len(types)))                       # a permutation of the kept objects
+        assert n_box + n_plane + n_sph + n_rest == len(types)
+        boxes, others = order[:n_box], order[n_box:]
+        assert all(types[i] == "box" for i in boxes) and boxes == sorted(boxes)
+        assert all(types[i] != "box" for i in others) and others == sorted(others)      # world order kept
+        assert all(types[i] == "plane" for i in others[:n_plane])
+        assert all(types[i] == "sphere" for i in others[n_plane:n_plane + n_sph])
+        rest = others[n_plane + n_sph:]
+        assert not rest or types[rest[0]] == "plane"                          # the generic loop starts where a plane follows a sphere
+        n_diel = sum(1 for o in doc["objects"] if o["type"] in ("sphere", "sphere_light", "plane", "box")
+                     and any(m.get("id") == o.get("material_id") and m.get("type") == "dielectric" for m in doc["materials"]))
+        assert n_dbox + n_dsph in (0, n_diel)
