@@ -42,7 +42,7 @@ struct DevSky {      // renderer.go:56-92
 };
 
 constexpr int kMaxExitTyped = 64;
-struct DevScene {                        // ~55 KB of the 64 KB constant bank
+struct DevScene {                        // 57.3 KB of the 64 KB constant bank
     int32_t n_obj, n_mat, n_diel, n_box;   // n_mat counts the appended zero material (index n_mat-1); boxes are obj[0..n_box)
     // ---- the closest-hit scan's own tables (wavefront kernel).  Device order of the analytic objects:
     //   [0, n_box) boxes | [n_box, n_box + n_plane_run) planes | [.., + n_sphere_run) spheres | rest (generic loop),
@@ -74,6 +74,8 @@ constexpr int kBoxGroup = PTB_BOX_GROUP;
 #define PTB_SPHERE_GROUP 2
 #endif
 constexpr int kSphereGroup = PTB_SPHERE_GROUP;
+
+static_assert(sizeof(DevScene) <= 64 * 1024, "DevScene must fit the 64 KB constant bank");
 
 // fp64 world for the primary-hit parity kernel (global memory; N is tiny).
 struct Obj64 {
