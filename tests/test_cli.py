@@ -70,3 +70,39 @@ def test_cpp_driver_renders_png(tmp_path):
     from path_trace_golang_b200 import engine, scene
     ref = engine.Render(scene.Load(scene_path("metal_glass_room")), engine.RenderConfig(192, 108, 8, 16), seed=3)
     assert (img == ref).all()
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+    exe = tmp_path / "render_c"
+    lib_dir = ROOT / "path_trace_golang_b200"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", f"-I{ROOT / 'include'}", "-o", str(exe), str(ROOT / "examples" / "render_c.c"),
+                           f"-L{lib_dir}", "-lptb200", f"-Wl,-rpath,{lib_dir}"])
+    return exe
+
+
+def test_c_example_builds_and_fails_loudly_without_gpu(tmp_path):
+    """examples/render_c.c drives the library from plain C99 (what a cgo binding does); on a box without CUDA it must
+    exit 1 with the library's message instead of producing an image."""
+    import subprocess
+    import torch
+    exe = _build_c_example(tmp_path)
+    r = subprocess.run([str(exe), "/nonexistent.json"], capture_output=True, text=True)
+    assert r.returncode == 1 and "open scene" in r.stderr
+    if not torch.cuda.is_available():
+        out = tmp_path / "o.png"
+        r = subprocess.run([str(exe), str(scene_path("example_simple")), str(out), "64", "36", "2", "4"], capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr and not out.exists()
+
+
+@pytest.mark.gpu
+def test_c_example_renders(tmp_path):
+    import subprocess
+    from PIL import Image
+    exe = _build_c_example(tmp_path)
+    out = tmp_path / "o.png"
+    r = subprocess.run([str(exe), str(scene_path("example_simple")), str(out), "160", "90", "16", "8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "progress callbacks" in r.stdout
+    img = np.array(Image.open(out))
+    assert img.shape == (90, 160, 4) and (img[..., 3] == 255).all() and img[..., :3].std() > 5
