@@ -10,8 +10,13 @@ plus Mrays/s, `roofline` (FP32 issue roofline of the integrator kernel), `cpu_ba
 restatement of the Go CPU renderer, timed on this box's host cores), `e2e` (through engine.RenderInto with host
 buffers), `clocks`, `gpu_launches`.
 
-N > 1 (torchrun, one rank per GPU): the frame's samples are split across ranks (strong scaling: total work
-fixed), the fp32 accumulation buffers are reduced to rank 0 with NCCL, rank 0 runs the pixel epilogue.
+N > 1 (torchrun, one rank per GPU): the frame's samples are split across ranks (strong scaling: total work fixed); the
+exchange is ONE kernel per rank that does reduce-scatter + pixel epilogue + gather over NVLink peer memory (--exchange peer,
+default; NCCL only carries the IPC handles and the barriers), or the same data movement with NCCL collectives (--exchange
+scatter), or round 1's reduce-to-root + epilogue on rank 0 (--exchange reduce).
+
+The line also carries `parity` (the run's own check against the oracle and the committed converged golden, outside every timed
+region) and, at N = 1, `configs`: short resident passes of the other BASELINE configurations (C1, C2, C5, C4 with 1 M triangles).
 """
 from __future__ import annotations
 
@@ -129,6 +134,94 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm)}
 
 
+def traffic_record():
+    """DRAM bytes per launch of the dominant kernel from the newest committed ncu --set full capture (profiles/traffic.json,
+    written by tools/ncu_traffic.py from the .ncu-rep: dram__bytes_read.sum + dram__bytes_write.sum of one launch)."""
+    try:
+        return json.load(open(ROOT / "profiles" / "traffic.json"))
+    except Exception:
+        return None
+
+
+def parity_block(ctx, workload, W, H, depth):
+    """The run's own parity evidence (outside every timed region; the oracle is the checker, never the thing measured):
+    primary-hit ids/t of the workload's frame, bit-exact, and the converged block-mean comparison of tests/test_gpu_converged.py."""
+    import numpy as np
+    out = {"oracle": "oracle/ (C++ restatement of the Go CPU path; pinned by hand-derived KATs only: the Go toolchain is absent, "
+                     "the reference ships no golden vectors — go/tools/gen_golden.go produces them on a box with Go)"}
+    ora = load_oracle(workload)
+    ids, t = ctx.primary_hits(W, H, 0.5, 0.5)
+    oids, ot = ora.primary_hits(W, H, 0.5, 0.5)
+    out["primary_hit_pixels"] = int(ids.size)
+    out["primary_hit_mismatches"] = int((ids != oids).sum())
+    out["primary_t_mismatches"] = int((t.view(np.uint64) != ot.view(np.uint64)).sum())
+    name = WORKLOADS[workload][0]
+    gpath = ROOT / "tests" / "golden" / f"converged_{name}.npz"
+    if workload not in C4_MESH and gpath.exists():
+        z = np.load(gpath)
+        a, b, meta = z["a"].astype(np.float64), z["b"].astype(np.float64), json.loads(str(z["meta"]))
+        gold = 0.5 * (a + b)
+        gw, gh, spp = meta["width"], meta["height"], 16384
+        dev = ctx.render_accum(ctx.cfg(gw, gh, spp, meta["max_depth"], seed=77)).astype(np.float64) / spp
+        hh = gh // 4 * 4
+        db = dev[:hh].reshape(hh // 4, 4, gw // 4, 4, 3).mean(axis=(1, 3))
+        lum = lambda x: float((0.2126 * x[..., 0] + 0.7152 * x[..., 1] + 0.0722 * x[..., 2]).mean())
+        out.update({"rel_rmse": float(np.sqrt(((db - gold) ** 2).mean()) / gold.mean()), "lum_ratio": lum(db) / lum(gold),
+                    "tolerance": {"rel_rmse": min(meta["floor_rel_rmse"], 0.02), "lum_ratio": 0.005,
+                                  "basis": "rel_rmse <= 1.0 x the oracle-vs-oracle floor (two 4096-spp fp64 estimates, "
+                                           f"{meta['floor_rel_rmse']:.5f}); an exact implementation scores 0.61 x"},
+                    "what": f"{gw}x{gh}, device {spp} spp (fp32) vs fp64 oracle {2 * meta['spp_each']} spp, 4x4-block means of linear RGB"})
+        out["pass"] = bool(out["primary_hit_mismatches"] == 0 and out["rel_rmse"] <= out["tolerance"]["rel_rmse"]
+                           and abs(out["lum_ratio"] - 1) <= 0.005)
+    else:
+        out["pass"] = bool(out["primary_hit_mismatches"] == 0)
+    return out
+
+
+def config_pass(ctx, engine, workload, fp32_peak, hbm_peak, flush, dev, stream):
+    """One short resident + end-to-end pass of another BASELINE configuration (N = 1; reduced spp where the full config takes
+    seconds — samples/s does not depend on spp for frames this large)."""
+    import numpy as np
+    import torch
+    name, W, H, spp, depth = WORKLOADS[workload]
+    spp_timed = min(spp, 32) if W * H * spp > 3e8 else spp
+    sc = load_scene(workload)
+    ctx.upload(sc)
+    ctx.render_accum(ctx.cfg(W, H, min(spp_timed, 8), depth, seed=1, stats=True))
+    st = ctx.stats()
+    fps = flops_per_sample(st, world_counts(ctx), spp)
+    rgba = torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
+    cfg = ctx.cfg(W, H, spp_timed, depth, seed=1)
+    for _ in range(3):
+        flush.zero_(); ctx.render_device(cfg, rgba.data_ptr(), stream)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ms = []
+    for _ in range(3):
+        flush.zero_()
+        k0.record(); ctx.render_device(cfg, rgba.data_ptr(), stream); k1.record()
+        torch.cuda.synchronize(dev)
+        ms.append(k0.elapsed_time(k1))
+    ms = sum(ms) / len(ms)
+    host = np.zeros((H, W, 4), dtype=np.uint8)
+    engine.RenderInto(sc, engine.RenderConfig(W, H, spp_timed, depth), host, ctx=ctx, seed=1)
+    t0 = time.perf_counter()
+    for _ in range(2):
+        engine.RenderInto(sc, engine.RenderConfig(W, H, spp_timed, depth), host, ctx=ctx, seed=1)
+    e2e_ms = (time.perf_counter() - t0) / 2 * 1e3
+    n = W * H * spp_timed
+    out = {"workload": f"scenes/{name}.json {W}x{H}, {spp} spp, depth {depth}", "spp_timed": spp_timed, "ms": ms,
+           "msamples_s": n / ms / 1e3, "e2e_msamples_s": n / e2e_ms / 1e3, "e2e_ms": e2e_ms, "kernel": ctx.last_kernel(),
+           "rays_per_sample": st["segments"] / st["samples"], "flops_per_sample": fps,
+           "frac": fps * n / (ms * 1e-3) / 1e12 / fp32_peak if fp32_peak else None, "bound": "fp32"}
+    bvh = ctx.bvh_info()
+    if bvh["n_triangles"]:
+        bps = (st["bvh_nodes_visited"] * bvh["node_bytes"] + st["bvh_tris_tested"] * bvh["triangle_bytes"]) / st["samples"]
+        out.update({"bound": "hbm", "frac_fp32": out["frac"], "frac": bps * n / (ms * 1e-3) / 1e9 / hbm_peak, "bytes_per_sample": bps,
+                    "triangles": bvh["n_triangles"], "nodes_per_ray": st["bvh_nodes_visited"] / st["segments"],
+                    "bvh_stack_overflows": st["bvh_stack_overflows"]})
+    return out
+
+
 def cpu_calibrate_spp(name, W, H, depth, threads, target_s, max_spp):
     """Pick the spp of the bounded CPU sample so that one full-resolution step takes about target_s seconds."""
     ora = load_oracle(name)
@@ -163,7 +256,10 @@ def main():
     ap.add_argument("--cpu-spp", type=int, default=0, help="spp of the bounded CPU sample (0 = calibrate: ~15 s, or ~6 s per step for --impl reference)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--partition", default="samples", choices=["samples", "rows"],
-                    help="N > 1: sample ranges + NCCL reduce of the fp32 sums (default), or interleaved rows + all_gather of RGBA8")
+                    help="N > 1: sample ranges + exchange of the fp32 sums (default), or interleaved rows + all_gather of RGBA8")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "scatter", "reduce"],
+                    help="N > 1, sample ranges: fused peer-memory kernel (default), NCCL reduce_scatter + gather, or NCCL reduce to rank 0")
+    ap.add_argument("--no-extras", action="store_true", help="skip the parity block and the other-config passes")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3                      # timing rule: W >= 3
@@ -176,7 +272,9 @@ def main():
     config = {"workload": f"{args.workload}: scenes/{name}.json{mesh_note} {W}x{H}, {spp} spp, max depth {depth}", "scene": name,
               "width": W, "height": H, "samples_per_px": spp, "max_depth": depth,
               "partition": ("single GPU" if world == 1 else "interleaved rows per rank + all_gather of RGBA8" if args.partition == "rows"
-                            else "sample ranges per rank + NCCL reduce to rank 0"),
+                            else {"peer": "sample ranges per rank; one kernel per rank: reduce-scatter + epilogue + gather over NVLink peer memory (CUDA IPC)",
+                                  "scatter": "sample ranges per rank; NCCL reduce_scatter + per-rank epilogue + gather of RGBA8 to rank 0",
+                                  "reduce": "sample ranges per rank + NCCL reduce to rank 0 + epilogue on rank 0"}[args.exchange]),
               "l2": "flushed between steps (256 MiB write); inputs are a few KB of constants"}
     cores = os.cpu_count() or 1
 
@@ -187,6 +285,7 @@ def main():
         cpu_spp = args.cpu_spp or cpu_calibrate_spp(args.workload, W, H, depth, cores, 6.0, spp)
         msps, rays_per_sample, dt = cpu_reference_run(args.workload, W, H, depth, cpu_spp, args.steps, min(args.warmup, 1), cores)
         sample = f"{W}x{H}, {cpu_spp} of {spp} spp per step (samples/s is spp-independent), depth {depth}"
+        config["spp_timed"] = cpu_spp
         print(json.dumps({
             "impl": "reference", "metric": "Msamples/s", "value": msps, "unit": "Msamples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -218,26 +317,45 @@ def main():
     cfg = ctx.cfg(W, H, spp, depth, seed=1)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     rgba = torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
-    accum = torch.empty((H, W, 3), dtype=torch.float32, device=dev) if world > 1 else None
+    accum = peers = accum_padded = rgba_padded = None
+    if world > 1 and args.partition == "samples":
+        if args.exchange == "peer":
+            peers = pdist.PeerGroup(ctx, W, H)
+        elif args.exchange == "scatter":
+            chunk = pdist.slice_pixels(W * H, world)
+            accum_padded = torch.zeros((world * chunk, 3), dtype=torch.float32, device=dev)
+            rgba_padded = torch.zeros((world * chunk, 4), dtype=torch.uint8, device=dev) if rank == 0 else None
+        else:
+            accum = torch.empty((H, W, 3), dtype=torch.float32, device=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    def step_resident():
-        flush.zero_()                                            # L2 flush (a torch memset, not one of our kernels)
+    def step_resident_image():
         if world == 1:
             ctx.render_device(cfg, rgba.data_ptr(), stream)      # 1 launch: integrate + epilogue
-        elif args.partition == "rows":
-            pdist.render_rows_distributed(ctx, cfg)              # interleaved rows, fused epilogue, all_gather of RGBA8
-        else:
-            pdist.render_partition(ctx, cfg, rank, world, accum, stream)
-            pdist.reduce_to_root(accum)
-            if rank == 0:
-                ctx.finalize_device(accum.data_ptr(), W, H, spp, rgba.data_ptr(), stream)
+            return rgba
+        if args.partition == "rows":
+            return pdist.render_rows_distributed(ctx, cfg)       # interleaved rows, fused epilogue, all_gather of RGBA8
+        if peers is not None:
+            return pdist.render_distributed_peer(ctx, cfg, peers)    # 2 launches per rank: integrate, reduce+epilogue+gather slice
+        if accum_padded is not None:
+            return pdist.render_distributed_scatter(ctx, cfg, accum_padded, rgba_padded)
+        pdist.render_partition(ctx, cfg, rank, world, accum, stream)
+        pdist.reduce_to_root(accum)
+        if rank == 0:
+            ctx.finalize_device(accum.data_ptr(), W, H, spp, rgba.data_ptr(), stream)
+        return rgba if rank == 0 else None
+
+    def step_resident():
+        flush.zero_()                                            # L2 flush (a torch memset, not one of our kernels)
+        step_resident_image()
 
     host_img = np.zeros((H, W, 4), dtype=np.uint8)
+    if world == 1:
+        ctx.pin(host_img)          # the caller's long-lived image, page-locked once (ptb_host_buffer_pin): D2H lands in it directly
     host_pinned = torch.empty((H, W, 4), dtype=torch.uint8, pin_memory=True) if world > 1 else None
 
     def step_e2e():
@@ -245,18 +363,11 @@ def main():
         if world == 1:
             # the reference-facing call: scene flatten + upload (H2D), render, D2H into the caller's image
             engine.RenderInto(sc, engine.RenderConfig(W, H, spp, depth), host_img, ctx=ctx, seed=1)
-        elif args.partition == "rows":
-            ctx.upload(sc)
-            img = pdist.render_rows_distributed(ctx, cfg)
-            if rank == 0:
-                host_pinned.copy_(img)
         else:
-            ctx.upload(sc)
-            pdist.render_partition(ctx, cfg, rank, world, accum, stream)
-            pdist.reduce_to_root(accum)
+            ctx.upload(sc)                               # every rank: scene flatten + H2D
+            img = step_resident_image()
             if rank == 0:
-                ctx.finalize_device(accum.data_ptr(), W, H, spp, rgba.data_ptr(), stream)
-                host_pinned.copy_(rgba)                  # D2H into pinned host memory (the caller's image)
+                host_pinned.copy_(img)                   # D2H into pinned host memory (the caller's image)
 
     # counters for the roofline (one stats pass at reduced spp, outside every timed region)
     counts = world_counts(ctx)
@@ -294,14 +405,17 @@ def main():
     for _ in range(max(3, args.steps)):
         flush.zero_()
         k0.record()
-        if world == 1:
-            ctx.render_device(cfg, rgba.data_ptr(), stream)
+        if world == 1 or args.partition == "rows":
+            ctx.render_device(cfg if world == 1 else ctx.cfg(W, H, spp, depth, seed=1, row_offset=rank, row_step=world), rgba.data_ptr(), stream)
         else:
-            pdist.render_partition(ctx, cfg, rank, world, accum, stream)
+            b_, e_ = pdist.sample_range(spp, rank, world)
+            target = peers.accum_ptr if peers is not None else (accum_padded if accum_padded is not None else accum).data_ptr()
+            ctx.render_accum_device(ctx.cfg(W, H, spp, depth, seed=1, sample_begin=b_, sample_count=e_ - b_), target, stream)
         k1.record()
         torch.cuda.synchronize(dev)
         kms.append(k0.elapsed_time(k1))
     kernel_ms = sum(kms) / len(kms)
+    kernel_name = ctx.last_kernel()
 
     # ---- timed region 2: end to end through the public API (host buffers)
     for _ in range(2):
@@ -326,17 +440,21 @@ def main():
         achieved = fps * (samples / world) / (kernel_ms * 1e-3) / 1e12
         flat = sc.flat()
         h2d = 8 * (flat.n_obj * 8 + flat.n_mat * 12) + 512          # flattened SoA + camera/sky structs (bytes, approx. exact)
+        tr = traffic_record()
+        split_k = 1                                                 # (frames of >= 1.2 M pixels are not split: 1 launch per frame)
+        per_rank_launches = 1 if (world == 1 or args.partition == "rows") else 2
         out = {
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "mrays_per_s": value * rays_per_sample, "rays_per_sample": rays_per_sample,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp32_peak if fp32_peak else None, "traffic": 51200,
-                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one integrate_wf_kernel launch from the ncu "
-                                         "--set full capture profiles/r01j_ncu_details.txt (44 KB read, 7 KB written: the scene is "
-                                         "constant/shared-memory resident and the 33 MB image stays in the 126 MB L2 for the kernel's lifetime)",
-                         "kernel": "integrate_wf_kernel<false>", "kernel_ms": kernel_ms,
+                         "frac": achieved / fp32_peak if fp32_peak else None,
+                         "traffic": (tr["dram_bytes_read"] + tr["dram_bytes_write"]) if tr and tr.get("workload") == args.workload else None,
+                         "traffic_note": (f"dram__bytes_read.sum + dram__bytes_write.sum of one {tr['kernel']} launch, ncu --set full capture "
+                                          f"{tr['source']} ({tr['what']}); read from profiles/traffic.json at run time") if tr else
+                                         "no ncu capture recorded in profiles/traffic.json",
+                         "kernel": kernel_name, "kernel_ms": kernel_ms,
                          "flops_per_sample": fps, "simt_lane_utilisation": simt_util,
                          "peak_source": "measured here: ptb_measure_fp32_peak (FFMA microbenchmark, 2 flop/FMA); "
                                         "MEASURED_PEAKS.json has no fp32 entry; nominal 148x128x2x1.965 GHz = 74.5",
@@ -347,7 +465,10 @@ def main():
                     "d2h_bytes_per_step": W * H * 4, "ms_per_step": e2e_s / args.steps * 1e3,
                     "api": "engine.RenderInto(scene, cfg, host image)" if world == 1 else
                            "scene upload + dist.render_partition + NCCL reduce + epilogue + D2H on rank 0"},
-            "gpu_launches": args.steps * (1 if world == 1 or args.partition == "rows" else 2),
+            "gpu_launches": args.steps * per_rank_launches * world * split_k,
+            "gpu_launches_note": f"{per_rank_launches} kernel(s) of libptb200.so per rank and step in timed region 1 ({kernel_name}"
+                                 + (" + reduce_finalize_slice_kernel" if per_rank_launches == 2 and args.exchange == "peer" else
+                                    " + finalize_kernel" if per_rank_launches == 2 else "") + f") x {world} rank(s); the L2 flush is a torch memset",
             "clocks": clocks,
         }
         if bvh["n_triangles"]:
@@ -362,7 +483,9 @@ def main():
             ach = bytes_per_sample * (samples / world) / (kernel_ms * 1e-3) / 1e9
             out["roofline_fp32"] = out["roofline"]
             out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak or 6650.0, "unit": "GB/s",
-                               "frac": ach / (hbm_peak or 6650.0), "traffic": None, "kernel": "integrate_wf_kernel<false>",
+                               "frac": ach / (hbm_peak or 6650.0),
+                               "traffic": (tr["dram_bytes_read"] + tr["dram_bytes_write"]) if tr and tr.get("workload") == args.workload else None,
+                               "kernel": kernel_name,
                                "kernel_ms": kernel_ms, "bytes_per_sample": bytes_per_sample,
                                "nodes_per_ray": st["bvh_nodes_visited"] / st["segments"], "tris_per_ray": st["bvh_tris_tested"] / st["segments"],
                                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else "fallback 6.65 TB/s (of fallback)",
@@ -372,6 +495,19 @@ def main():
             # from identical triangles is reused, so it crosses PCIe once per mesh, not once per step
             out["e2e"]["h2d_bytes_per_step"] = h2d
             out["e2e"]["host_bytes_hashed_per_step"] = int(bvh["n_triangles"]) * 36
+        if not args.no_extras:
+            out["parity"] = parity_block(ctx, args.workload, W, H, depth)
+            if world == 1:
+                hbm = None
+                try:
+                    hbm = json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"]
+                except Exception:
+                    pass
+                out["configs"] = {}
+                for wl in ["C1", "C2", "C5", "C4_1M", "C3"]:
+                    if wl != args.workload:
+                        out["configs"][wl] = config_pass(ctx, engine, wl, fp32_peak, hbm or 6650.0, flush, dev, stream)
+                ctx.upload(sc)
         if not args.no_cpu and world == 1:
             cpu_spp = args.cpu_spp or cpu_calibrate_spp(args.workload, W, H, depth, cores, 15.0, spp)
             msps, _, dt = cpu_reference_run(args.workload, W, H, depth, cpu_spp, 1, 0, cores)
@@ -379,6 +515,8 @@ def main():
                                    "sample": f"{W}x{H}, {cpu_spp} of {spp} spp, depth {depth}, {dt:.1f} s, {cores} worker threads",
                                    "note": "C++ restatement of the Go CPU path (Go toolchain unavailable)"}
         print(json.dumps(out))
+    if peers is not None:
+        peers.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -15,7 +15,9 @@ package cuda
 #include <stdlib.h>
 #include "ptb200.h"
 
-extern void ptbGoProgress(void* user);   // exported below
+// ptbGoProgress is the Go function exported from callback.go.  cgo forbids DEFINITIONS in the preamble of a file that
+// uses //export (that preamble is emitted twice), so the export lives in its own file and this file only wraps its address.
+void ptbGoProgress(void* user);
 static ptb_progress_fn ptb_go_progress_ptr(void) { return (ptb_progress_fn)ptbGoProgress; }
 */
 import "C"
@@ -24,6 +26,8 @@ import (
 	"errors"
 	"fmt"
 	"image"
+	"hash/fnv"
+	"math"
 	"runtime/cgo"
 	"sync"
 	"unsafe"
@@ -42,7 +46,8 @@ type RenderConfig struct {
 // Seed is the key of the counter RNG (the CPU path seeds from the clock, random.go:14-16).
 var Seed uint32 = 1
 
-// Device is the CUDA device ordinal used by the process-wide context.
+// Device is the CUDA device ordinal of the single-device context.  Changing it (or Devices) between renders takes effect
+// on the next Render: the context is rebuilt under the lock.
 var Device = 0
 
 // Devices > 1 renders every frame on devices 0..Devices-1 of the box (ptb_multi_*: sample ranges per device, reduced on
@@ -50,34 +55,47 @@ var Device = 0
 var Devices = 1
 
 var (
-	mu      sync.Mutex // one render at a time per context (the GL path serialises on its worker, gpu.go:266-297)
-	ctx     *C.ptb_ctx
-	multi   *C.ptb_multi
-	initErr error
-	once    sync.Once
+	mu         sync.Mutex // one render at a time per context (the GL path serialises on its worker, gpu.go:266-297)
+	ctx        *C.ptb_ctx
+	multi      *C.ptb_multi
+	ctxDevice  = -1
+	multiCount = 0
 )
 
 func lastError(c *C.ptb_ctx) error { return errors.New(C.GoString(C.ptb_last_error(c))) }
 
+// ensureContext (called with mu held) creates the context for the current Device / Devices setting, replacing one made for
+// other settings.  A failure is returned to the caller and retried on the next render (a GPU may have come back); nothing
+// is rendered on the CPU instead.
 func ensureContext() error {
-	once.Do(func() {
-		if Devices > 1 {
-			if rc := C.ptb_multi_create(nil, C.int(Devices), &multi); rc != C.PTB_OK {
-				initErr = fmt.Errorf("CUDA initialization failed: %s", C.GoString(C.ptb_multi_last_error(nil)))
-			}
-			return
+	if Devices > 1 {
+		if multi != nil && multiCount == Devices {
+			return nil
 		}
-		if rc := C.ptb_create(C.int(Device), &ctx); rc != C.PTB_OK {
-			initErr = fmt.Errorf("CUDA initialization failed: %w", lastError(nil))
+		if multi != nil {
+			C.ptb_multi_destroy(multi)
+			multi = nil
 		}
-	})
-	return initErr // sticky, like the GL worker's init failure (gpu.go:279-286)
-}
-
-//export ptbGoProgress
-func ptbGoProgress(user unsafe.Pointer) {
-	h := *(*cgo.Handle)(user)
-	h.Value().(func())()
+		if rc := C.ptb_multi_create(nil, C.int(Devices), &multi); rc != C.PTB_OK {
+			multi = nil
+			return fmt.Errorf("CUDA initialization failed: %s", C.GoString(C.ptb_multi_last_error(nil)))
+		}
+		multiCount = Devices
+		return nil
+	}
+	if ctx != nil && ctxDevice == Device {
+		return nil
+	}
+	if ctx != nil {
+		C.ptb_destroy(ctx)
+		ctx = nil
+	}
+	if rc := C.ptb_create(C.int(Device), &ctx); rc != C.PTB_OK {
+		ctx = nil
+		return fmt.Errorf("CUDA initialization failed: %w", lastError(nil))
+	}
+	ctxDevice = Device
+	return nil
 }
 
 func materialCode(t scene.MaterialType) C.int32_t { // materials.go:33-54
@@ -103,6 +121,8 @@ func objectCode(t scene.ObjectType) C.int32_t { // objects.go:237-266
 		return C.PTB_OBJ_PLANE
 	case scene.ObjectBox:
 		return C.PTB_OBJ_BOX
+	case scene.ObjectMesh: // extension, go/internal/scene/mesh.go
+		return C.PTB_OBJ_MESH
 	default:
 		return -1 // dropped by the library, like sceneToWorld drops unknown types
 	}
@@ -134,6 +154,26 @@ func (f *flatScene) doubles(v []float64) *C.double {
 	return (*C.double)(p)
 }
 
+func (f *flatScene) floats(v []float32) *C.float {
+	if len(v) == 0 {
+		return nil
+	}
+	p := C.malloc(C.size_t(len(v) * 4))
+	copy(unsafe.Slice((*float32)(p), len(v)), v)
+	f.free = append(f.free, p)
+	return (*C.float)(p)
+}
+
+func (f *flatScene) int64s(v []int64) *C.int64_t {
+	if len(v) == 0 {
+		return nil
+	}
+	p := C.malloc(C.size_t(len(v) * 8))
+	copy(unsafe.Slice((*int64)(p), len(v)), v)
+	f.free = append(f.free, p)
+	return (*C.int64_t)(p)
+}
+
 func (f *flatScene) release() {
 	for _, p := range f.free {
 		C.free(p)
@@ -142,7 +182,7 @@ func (f *flatScene) release() {
 
 // flatten turns a scene.Scene into the SoA view of ptb_scene: RAW fields only — convertMaterial, the box min/max
 // arithmetic and newCamera run inside the library (include/ptb200.h).
-func flatten(sc *scene.Scene) *flatScene {
+func flatten(sc *scene.Scene) (*flatScene, error) {
 	f := &flatScene{}
 	byID := make(map[string]int32, len(sc.Materials)) // later duplicate wins (objects.go:226-229)
 	nm := len(sc.Materials)
@@ -160,8 +200,42 @@ func flatten(sc *scene.Scene) *flatScene {
 	no := len(sc.Objects)
 	ot, om := make([]int32, no), make([]int32, no)
 	pos, size := make([]float64, 3*no), make([]float64, 3*no)
+	// meshes (extension): one entry per mesh object; triangles in world space, binary32 (ptb_scene.tri_vertices).
+	// mesh_generation = hash of every mesh's (Generation, position, size): unchanged meshes cost nothing per frame.
+	objMesh := make([]int32, no)
+	triBegin := []int64{0}
+	var tris []float32
+	gen := fnv.New64a()
+	for i := range sc.Objects {
+		o := &sc.Objects[i]
+		objMesh[i] = -1
+		if o.Type != scene.ObjectMesh || o.Mesh == nil {
+			continue
+		}
+		var err error
+		if tris, err = o.WorldTriangles(tris); err != nil {
+			f.release()
+			return nil, err
+		}
+		if int64(len(tris)/9) == triBegin[len(triBegin)-1] {
+			continue // no triangles: the object is dropped (its type code stays, the library skips empty meshes)
+		}
+		objMesh[i] = int32(len(triBegin) - 1)
+		triBegin = append(triBegin, int64(len(tris)/9))
+		var b [8 * 7]byte
+		for k, v := range []uint64{o.Mesh.Generation(), math.Float64bits(o.Position.X), math.Float64bits(o.Position.Y), math.Float64bits(o.Position.Z),
+			math.Float64bits(o.Size.X), math.Float64bits(o.Size.Y), math.Float64bits(o.Size.Z)} {
+			for j := 0; j < 8; j++ {
+				b[8*k+j] = byte(v >> (8 * j))
+			}
+		}
+		gen.Write(b[:])
+	}
 	for i, o := range sc.Objects {
 		ot[i] = int32(objectCode(o.Type))
+		if o.Type == scene.ObjectMesh && objMesh[i] < 0 {
+			ot[i] = -1
+		}
 		if idx, ok := byID[o.MaterialID]; ok {
 			om[i] = idx
 		} else {
@@ -181,9 +255,10 @@ func flatten(sc *scene.Scene) *flatScene {
 	s.camera.up = [3]C.double{C.double(c.Up.X), C.double(c.Up.Y), C.double(c.Up.Z)}
 	s.camera.fov, s.camera.aperture = C.double(c.FOV), C.double(c.Aperture)
 	s.camera.focus_dist, s.camera.aspect_ratio = C.double(c.FocusDist), C.double(c.AspectRatio)
-	// no meshes: scene.Object has no mesh field in the reference (the extension is documented in DESIGN.md §3.7);
-	// a maintainer who adds it fills obj_mesh / mesh_tri_begin / tri_vertices here
-	s.n_mesh, s.obj_mesh, s.mesh_tri_begin, s.tri_vertices = 0, nil, nil, nil
+	if n := len(triBegin) - 1; n > 0 {
+		s.n_mesh, s.obj_mesh, s.mesh_tri_begin, s.tri_vertices = C.int32_t(n), f.ints(objMesh), f.int64s(triBegin), f.floats(tris)
+		s.mesh_generation = C.uint64_t(gen.Sum64() | 1)
+	}
 	// sky selection of renderIntoCPU, renderer.go:56-92
 	if sc.Sky != nil && sc.Sky.Type == "gradient" {
 		s.sky.kind = C.PTB_SKY_GRADIENT
@@ -197,7 +272,7 @@ func flatten(sc *scene.Scene) *flatScene {
 		s.sky.kind = C.PTB_SKY_CONST
 		s.sky.color = [3]C.double{C.double(bg.R), C.double(bg.G), C.double(bg.B)}
 	}
-	return f
+	return f, nil
 }
 
 // Render renders sc into img on the CUDA backend.  Same contract as gpu.Render (gpu.go:2534-2546): the caller owns
@@ -208,13 +283,16 @@ func Render(sc *scene.Scene, cfg RenderConfig, img *image.RGBA, progress func())
 	if b.Dx() != cfg.Width || b.Dy() != cfg.Height {
 		return nil
 	}
+	mu.Lock()
+	defer mu.Unlock()
 	if err := ensureContext(); err != nil {
 		return err
 	}
-	mu.Lock()
-	defer mu.Unlock()
 
-	f := flatten(sc)
+	f, err := flatten(sc)
+	if err != nil {
+		return err
+	}
 	defer f.release()
 	c := C.ptb_cfg{width: C.int32_t(cfg.Width), height: C.int32_t(cfg.Height), samples_per_px: C.int32_t(cfg.SamplesPerPx),
 		max_depth: C.int32_t(cfg.MaxDepth), seed: C.uint32_t(Seed)}

@@ -17,13 +17,14 @@
  * an internal mutex); any OS thread may call (cudaSetDevice is done per call), which is what
  * a goroutine-per-render caller such as internal/ui/app.go:135 needs.
  * Ownership: the library never keeps a host pointer after a call returns.
- * Determinism: a render is a pure function of (scene, cfg): same bytes run to run and on any number of streams.  Per
- * pixel the samples are added in index order; frames with fewer than ~1.2 M pixels add them in up to 64 sub-range
- * sums that are then added in order (so does a multi-device render), i.e. the same samples with fp32 sums
- * re-associated.  ptb_scene_upload waits for the device before it replaces the scene.
- * One device, one frame at a time: the scene of the frame being rendered lives in the device's constant bank, so
- * renders issued through DIFFERENT contexts (or streams) of the SAME device must be ordered by the caller; the
- * host-buffer calls (ptb_render, ptb_render_accum, ptb_primary_hits) synchronise before they return.
+ * Determinism: a render is a pure function of (scene, cfg): same bytes run to run, on any number of streams, with or
+ * without a progress callback.  Per pixel the samples are added in index order; frames with fewer than ~1.2 M pixels
+ * add them in up to 64 sub-range sums that are then added in order (so does a multi-device render), i.e. the same
+ * samples with fp32 sums re-associated.  ptb_scene_upload waits for the device before it replaces the scene.
+ * Isolation: a launch carries its scene tables and camera BY VALUE in its kernel parameters, so any number of
+ * contexts and streams may render on the same device concurrently, and a scene uploaded (or a frame of another size
+ * queued) afterwards cannot disturb a frame already in flight.  The host-buffer calls (ptb_render, ptb_render_accum,
+ * ptb_render_resume, ptb_primary_hits) synchronise before they return.
  */
 #ifndef PTB200_H
 #define PTB200_H
@@ -35,7 +36,9 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 4   /* 2: meshes (ptb_scene.n_mesh ...), 3: ptb_multi_*, 4: ptb_cfg.row_offset/row_step */
+#define PTB_ABI_VERSION 5   /* 2: meshes (ptb_scene.n_mesh ...), 3: ptb_multi_*, 4: ptb_cfg.row_offset/row_step,
+                               5: ptb_scene.mesh_generation, ptb_render_resume, ptb_host_buffer_pin, ptb_stats.bvh_stack_overflows,
+                                  no constant-bank limit on the number of objects */
 
 enum {
     PTB_OK = 0,
@@ -56,9 +59,12 @@ enum { PTB_OBJ_SPHERE = 0, PTB_OBJ_PLANE = 1, PTB_OBJ_BOX = 2,
  * (default branch, materials.go:50-53). */
 enum { PTB_MAT_LAMBERT = 0, PTB_MAT_METAL = 1, PTB_MAT_DIELECTRIC = 2, PTB_MAT_EMISSIVE = 3, PTB_MAT_MIRROR = 4 };
 
-/* Limits of the analytic (constant-memory resident) world; the shipped scenes have <= 44 / 27. */
-#define PTB_MAX_OBJECTS 512
-#define PTB_MAX_MATERIALS 511
+/* Limits of the analytic world (sceneToWorld itself has none, objects.go:225-269; the shipped scenes have <= 44 objects
+ * and 27 materials).  Worlds whose scan tables fit the kernel-parameter block (about 300 objects) are scanned from the
+ * constant bank; larger ones from global memory by the same code — a linear scan like the reference's, every object
+ * tested on every ray (renderer.go:297-302). */
+#define PTB_MAX_OBJECTS 1000000
+#define PTB_MAX_MATERIALS 1000000
 
 /* scene.Camera (internal/scene/scene.go:23-32), raw fields; newCamera (camera.go:19-58)
  * is evaluated inside the library in binary64 for the frame size of each render. */
@@ -111,6 +117,12 @@ typedef struct {
     const int32_t* obj_mesh;         /* [n_obj] mesh index for PTB_OBJ_MESH objects, -1 otherwise */
     const int64_t* mesh_tri_begin;   /* [n_mesh+1] triangle range of mesh k = [begin[k], begin[k+1]) */
     const float* tri_vertices;       /* [9 * mesh_tri_begin[n_mesh]] */
+    /* Caller-held identity of the triangle data: RenderInto hands the scene over on every call (renderer.go:34), and a
+     * 10 M-triangle mesh is 360 MB.  Non-zero: the caller's promise that two uploads with the same mesh_generation carry
+     * identical mesh_tri_begin / tri_vertices contents — the library then reuses the BVH it built for that generation
+     * without reading the triangles at all.  0: no promise; the triangles are hashed (all host cores) to recognise a
+     * BVH built before.  A host bumps the generation whenever it edits a mesh. */
+    uint64_t mesh_generation;
 } ptb_scene;
 
 /* engine.RenderConfig (renderer.go:17-22) + the extra knobs a GPU backend needs. */
@@ -128,9 +140,8 @@ typedef struct {
     int32_t row_offset, row_step;
 } ptb_cfg;
 
-#define PTB_FLAG_STATS 1u       /* run the counting variant of the integrator (slower); fills ptb_stats */
-#define PTB_FLAG_WAVEQUEUE 4u   /* EXPERIMENTAL, only in builds with -DPTB_ENABLE_WAVEQUEUE (otherwise the render call fails):
-                                   persistent warps + shared-memory work queues instead of barrier phases */
+#define PTB_FLAG_STATS 1u       /* run the counting variant of the integrator (slower); fills ptb_stats.  Ignored by ptb_render
+                                   when a progress callback is given (the batches are not counted) */
 #define PTB_FLAG_MEGAKERNEL 2u  /* use the pixel-per-lane megakernel instead of the default wavefront-in-shared-memory
                                    kernel (same results up to fp32 rounding; kept for A/B profiling) */
 
@@ -154,6 +165,7 @@ typedef struct {
     uint64_t accepts_mesh;      /* EXTENSION: winning hits on mesh triangles */
     uint64_t bvh_nodes_visited; /* 64-byte node fetches */
     uint64_t bvh_tris_tested;   /* 48-byte triangle fetches */
+    uint64_t bvh_stack_overflows; /* subtrees dropped because the traversal stack was full: must be 0 (the builder bounds the depth) */
 } ptb_stats;
 
 /* EXTENSION: the BVH built by ptb_scene_upload over the mesh triangles (all zero when the scene has no mesh). */
@@ -194,6 +206,14 @@ int ptb_rows_of(const ptb_cfg* cfg);   /* rows a call with this cfg outputs: hei
 int ptb_render(ptb_ctx* ctx, const ptb_cfg* cfg, uint8_t* rgba, size_t stride,
                ptb_progress_fn progress, void* user);
 
+/* Page-lock a caller-owned host buffer (cudaHostRegister) so that ptb_render / ptb_multi_render / ptb_render_resume copy
+ * the image straight into it instead of through the context's staging buffer (saves one 33 MB memcpy per 4K frame).
+ * Entirely optional and entirely the caller's: the library keeps no record of the buffer; unpin it before freeing it.
+ * A host that re-renders into one long-lived image (internal/ui/app.go:157-168 reallocates only on a size change) pins
+ * it once. */
+int ptb_host_buffer_pin(ptb_ctx* ctx, void* p, size_t bytes);
+int ptb_host_buffer_unpin(ptb_ctx* ctx, void* p);
+
 /* Linear fp32 radiance sums (NOT divided by the sample count) of this context's sample range,
  * width*height*3 floats, top row first — to a host buffer ... */
 int ptb_render_accum(ptb_ctx* ctx, const ptb_cfg* cfg, float* rgb_sum);
@@ -201,10 +221,21 @@ int ptb_render_accum(ptb_ctx* ctx, const ptb_cfg* cfg, float* rgb_sum);
  * void*, used exactly as given: NULL is the CUDA default stream, which is also PyTorch's default
  * stream).  This is what a multi-GPU caller reduces with NCCL. */
 int ptb_render_accum_device(ptb_ctx* ctx, const ptb_cfg* cfg, void* d_rgb_sum, void* stream);
+/* Checkpointable rendering (the reference persists only scenes and PNGs, util.go:45-55; a long render on a GPU backend
+ * wants to survive a restart): renders samples [sample_begin, sample_begin + sample_count) of cfg CONTINUING the sums
+ * in rgb_sum (host, width*height*3 floats): on entry the sums of samples [0, sample_begin) (ignored when sample_begin
+ * is 0), on return those of [0, sample_begin + sample_count).  rgba (may be NULL) receives the image of the mean over
+ * the samples so far.  Per pixel the samples are added strictly in index order, so ANY partition of [0, spp) into
+ * consecutive calls — with the sums written to disk and read back in between — gives the same bits as one call. */
+int ptb_render_resume(ptb_ctx* ctx, const ptb_cfg* cfg, float* rgb_sum, uint8_t* rgba, size_t stride);
+
 /* Pixel epilogue (renderer.go:189-221) on device buffers: mean over spp_total, sqrt, *255.999,
  * clamp, truncate, A=255.  d_rgba: height*width*4 bytes, tightly packed. */
 int ptb_finalize_device(ptb_ctx* ctx, const void* d_rgb_sum, int32_t width, int32_t height,
                         int32_t spp_total, void* d_rgba, void* stream);
+/* The same epilogue for HOST buffers: rgb_sum (width*height*3 floats) is sent to the device, finalised there, and the image
+ * comes back into rgba (stride >= 4*width).  Used to turn stored sums (a finished checkpoint) into an image. */
+int ptb_finalize_host(ptb_ctx* ctx, const float* rgb_sum, int32_t width, int32_t height, int32_t spp_total, uint8_t* rgba, size_t stride);
 /* Fused render + epilogue into a DEVICE RGBA8 image (no host copies; stream as above). */
 int ptb_render_device(ptb_ctx* ctx, const ptb_cfg* cfg, void* d_rgba, void* stream);
 
@@ -217,6 +248,9 @@ int ptb_primary_hits(ptb_ctx* ctx, const ptb_cfg* cfg, double xi_u, double xi_v,
 /* Counters of the last render that ran with PTB_FLAG_STATS (last_render_ms is always valid). */
 int ptb_get_stats(ptb_ctx* ctx, ptb_stats* out);
 int ptb_get_bvh_info(ptb_ctx* ctx, ptb_bvh_info* out);
+/* Symbol of the integrator kernel the last render of ctx launched, as ncu prints it (e.g. "integrate_wf_kernel<0, 0, 0>":
+ * counting build?, mesh traversal?, global-memory tables?).  Valid until the next render on ctx. */
+const char* ptb_last_kernel(ptb_ctx* ctx);
 
 /* ---- single-process multi-GPU (what a Go host that owns every GPU of the box calls; one process per GPU + NCCL is the
  * other supported arrangement).  Device k traces samples [k*spp/n, (k+1)*spp/n) of every pixel
@@ -232,6 +266,28 @@ int ptb_multi_render(ptb_multi* m, const ptb_cfg* cfg, uint8_t* rgba, size_t str
 /* device time of the last ptb_multi_render: slowest device's integrator, and the fused reduce+epilogue on device 0 */
 int ptb_multi_last_timing(ptb_multi* m, double* render_ms, double* reduce_ms);
 
+/* ---- multi-process multi-GPU: one process (rank) per GPU, as under torchrun / MPI.  The ranks' fp32 sum buffers and rank 0's
+ * image are shared through CUDA IPC, and ONE kernel per rank does reduce-scatter + pixel epilogue + gather: rank r sums its
+ * 1/world slice of the pixels over all ranks' buffers (NVLink peer loads) and stores the finalised RGBA8 pixels directly into
+ * rank 0's image (NVLink peer stores).  Against "NCCL reduce to rank 0, then finalise" this moves 12 B/pixel * (world-1)/world
+ * spread over all links plus 4 B/pixel into rank 0, instead of 12 B/pixel * (world-1) into rank 0 alone.
+ * Protocol: every rank ptb_peer_create -> ptb_peer_handles -> exchange the handles with the host's own communicator
+ * (all-gather of 64 bytes) -> ptb_peer_connect.  Per frame: render into ptb_peer_accum() (ptb_render_accum_device), make sure
+ * every rank's render has finished (a stream-ordered barrier of the host's communicator, e.g. a 4-byte NCCL all-reduce),
+ * ptb_peer_reduce_finalize on every rank, barrier again; rank 0 then owns the image at ptb_peer_image().
+ * Sum order is rank 0, 1, 2, ... on every rank: the image does not depend on which rank finalises which slice. */
+#define PTB_IPC_HANDLE_BYTES 64
+typedef struct ptb_peer ptb_peer;
+int ptb_peer_create(ptb_ctx* ctx, int rank, int world, int32_t max_width, int32_t max_height, ptb_peer** out);
+void ptb_peer_destroy(ptb_peer* p);
+int ptb_peer_handles(ptb_peer* p, unsigned char accum_handle[PTB_IPC_HANDLE_BYTES], unsigned char image_handle[PTB_IPC_HANDLE_BYTES]);
+int ptb_peer_connect(ptb_peer* p, const unsigned char* accum_handles /* world x 64 bytes, in rank order */,
+                     const unsigned char* root_image_handle /* rank 0's image handle */);
+void* ptb_peer_accum(ptb_peer* p);                 /* device pointer: this rank's width*height*3 float sums */
+void* ptb_peer_image(ptb_peer* p);                 /* device pointer on rank 0 (NULL elsewhere): width*height*4 bytes */
+int ptb_peer_slice(const ptb_peer* p, int32_t width, int32_t height, int64_t* begin, int64_t* end);   /* pixel range this rank finalises */
+int ptb_peer_reduce_finalize(ptb_peer* p, int32_t width, int32_t height, int32_t spp_total, void* stream);
+
 /* Test hook, host only (no CUDA call): the device layout ptb_scene_upload would give the scene's analytic objects.
  * order[k] = world index of device object k (at most cap entries are written); counts = {boxes, planes in the typed
  * plane run, spheres in the typed sphere run, objects left to the generic loop, dielectric boxes and dielectric
@@ -244,6 +300,20 @@ int ptb_scene_device_order(const ptb_scene* scene, int32_t* order, int32_t cap, 
  * the triangles below it, every triangle sits in exactly one leaf, links and counts are consistent.
  * Returns the number of violations (0 = sound) or a negative PTB_ERR_*; n_nodes / max_depth may be NULL. */
 int64_t ptb_bvh_selfcheck(const float* tri_vertices, int64_t n_tri, int64_t* n_nodes, int32_t* max_depth);
+
+/* Host only (no CUDA call): the BVH builder on its own — binned SAH over n_tri world-space triangles (9 floats each), output
+ * as the flattened arrays the device traverses: 64-byte cache-line-aligned nodes (both children's boxes as centre / half
+ * extent + links; layout in path_trace_golang_b200/csrc/bvh.h) and 48-byte triangles (v0, e1, e2) in leaf order carrying the
+ * original triangle index.  ptb_scene_upload calls the same builder; this entry point lets the host inspect, cache or
+ * serialise the structure (north-star: "internal/scene gains a BVH builder that emits a flattened, cache-line-aligned node
+ * array").  Free with ptb_bvh_free. */
+typedef struct {
+    const float* nodes;       /* info.n_nodes x 16 floats, 64-byte aligned */
+    const float* triangles;   /* info.n_triangles x 12 floats */
+    ptb_bvh_info info;
+} ptb_bvh;
+int ptb_bvh_build(const float* tri_vertices, int64_t n_tri, ptb_bvh* out);
+void ptb_bvh_free(ptb_bvh* b);
 
 /* Measurement helper: FP32 FMA throughput of the device (2 flop per FMA), the roofline
  * denominator MEASURED_PEAKS.json does not carry. */

@@ -51,6 +51,16 @@ int ptb_engine_render_into(ptb_ctx* ctx, const ptb_host_scene* sc, int32_t width
                            size_t stride, int32_t img_w, int32_t img_h, ptb_progress_fn progress,
                            void* user);
 
+/* Accumulation checkpoints (no reference equivalent: the reference persists only scenes and PNGs, util.go:45-55).  Renders
+ * like ptb_engine_render_into, in calls of samples_per_call samples (ptb_render_resume), rewriting the checkpoint file `path`
+ * after every call; if `path` already holds a checkpoint of this very render (same scene, size, spp, depth, seed) the render
+ * continues from it and finishes with the same bytes as an uninterrupted one.  max_calls > 0: stop after that many calls
+ * (what an interrupted run leaves behind).  *spp_done (may be NULL) = samples per pixel accumulated so far. */
+int ptb_engine_render_checkpointed(ptb_ctx* ctx, const ptb_host_scene* sc, int32_t width, int32_t height, int32_t samples_per_px,
+                                   int32_t max_depth, uint32_t seed, uint8_t* pix, size_t stride, int32_t img_w, int32_t img_h,
+                                   const char* path, int32_t samples_per_call, int32_t max_calls, int32_t* spp_done,
+                                   ptb_progress_fn progress, void* user);
+
 /* engine.SavePNG (util.go:45-55) for an RGBA8 image. */
 int ptb_engine_save_png(const char* path, const uint8_t* pix, size_t stride, int32_t width, int32_t height);
 

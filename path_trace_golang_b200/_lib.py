@@ -42,7 +42,7 @@ class PtbScene(C.Structure):
                 ("mat_emit", _dp), ("mat_power", _dp), ("mat_absorption", _dp), ("mat_smoothness", _dp),
                 ("camera", PtbCamera), ("sky", PtbSky),
                 ("n_mesh", C.c_int32), ("obj_mesh", _ip), ("mesh_tri_begin", C.POINTER(C.c_int64)),
-                ("tri_vertices", C.POINTER(C.c_float))]
+                ("tri_vertices", C.POINTER(C.c_float)), ("mesh_generation", C.c_uint64)]
 
 
 class PtbCfg(C.Structure):
@@ -57,7 +57,8 @@ class PtbStats(C.Structure):
                 ("end_emissive", C.c_uint64), ("end_rr", C.c_uint64), ("end_depth", C.c_uint64),
                 ("end_noscatter", C.c_uint64), ("lane_iters_active", C.c_uint64),
                 ("lane_iters_total", C.c_uint64), ("last_render_ms", C.c_double),
-                ("accepts_mesh", C.c_uint64), ("bvh_nodes_visited", C.c_uint64), ("bvh_tris_tested", C.c_uint64)]
+                ("accepts_mesh", C.c_uint64), ("bvh_nodes_visited", C.c_uint64), ("bvh_tris_tested", C.c_uint64),
+                ("bvh_stack_overflows", C.c_uint64)]
 
     def as_dict(self):
         d = {k: getattr(self, k) for k, _ in self._fields_ if k != "accepts"}
@@ -78,6 +79,10 @@ class PtbDeviceInfo(C.Structure):
                 ("cc_minor", C.c_int32), ("clock_khz", C.c_int32), ("global_mem_bytes", C.c_uint64)]
 
 
+class PtbBvh(C.Structure):
+    _fields_ = [("nodes", C.POINTER(C.c_float)), ("triangles", C.POINTER(C.c_float)), ("info", PtbBvhInfo)]
+
+
 PROGRESS_FN = C.CFUNCTYPE(None, C.c_void_p)
 
 # name -> (restype, argtypes): every symbol include/ptb200.h and include/ptb200_host.h declare
@@ -96,18 +101,33 @@ SYMBOLS = {
     "ptb_render_accum_device": (C.c_int, [C.c_void_p, C.POINTER(PtbCfg), C.c_void_p, C.c_void_p]),
     "ptb_finalize_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "ptb_render_device": (C.c_int, [C.c_void_p, C.POINTER(PtbCfg), C.c_void_p, C.c_void_p]),
+    "ptb_render_resume": (C.c_int, [C.c_void_p, C.POINTER(PtbCfg), C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ptb_finalize_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_size_t]),
+    "ptb_host_buffer_pin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "ptb_host_buffer_unpin": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ptb_primary_hits": (C.c_int, [C.c_void_p, C.POINTER(PtbCfg), C.c_double, C.c_double, C.c_void_p, C.c_void_p]),
     "ptb_get_stats": (C.c_int, [C.c_void_p, C.POINTER(PtbStats)]),
+    "ptb_last_kernel": (C.c_char_p, [C.c_void_p]),
     "ptb_get_bvh_info": (C.c_int, [C.c_void_p, C.POINTER(PtbBvhInfo)]),
     "ptb_measure_fp32_peak": (C.c_int, [C.c_void_p, _dp]),
     "ptb_scene_device_order": (C.c_int, [C.POINTER(PtbScene), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
     "ptb_bvh_selfcheck": (C.c_int64, [C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
+    "ptb_bvh_build": (C.c_int, [C.POINTER(C.c_float), C.c_int64, C.POINTER(PtbBvh)]),
+    "ptb_bvh_free": (None, [C.POINTER(PtbBvh)]),
     "ptb_multi_create": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
     "ptb_multi_destroy": (None, [C.c_void_p]),
     "ptb_multi_last_error": (C.c_char_p, [C.c_void_p]),
     "ptb_multi_scene_upload": (C.c_int, [C.c_void_p, C.POINTER(PtbScene)]),
     "ptb_multi_render": (C.c_int, [C.c_void_p, C.POINTER(PtbCfg), C.c_void_p, C.c_size_t]),
     "ptb_multi_last_timing": (C.c_int, [C.c_void_p, _dp, _dp]),
+    "ptb_peer_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
+    "ptb_peer_destroy": (None, [C.c_void_p]),
+    "ptb_peer_handles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ptb_peer_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ptb_peer_accum": (C.c_void_p, [C.c_void_p]),
+    "ptb_peer_image": (C.c_void_p, [C.c_void_p]),
+    "ptb_peer_slice": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "ptb_peer_reduce_finalize": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     # host mirror
     "ptb_host_last_error": (C.c_char_p, []),
     "ptb_host_scene_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
@@ -122,6 +142,9 @@ SYMBOLS = {
     "ptb_engine_render_into": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                          C.c_uint32, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_void_p,
                                          C.c_void_p]),
+    "ptb_engine_render_checkpointed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32,
+                                                 C.c_void_p, C.c_size_t, C.c_int32, C.c_int32, C.c_char_p, C.c_int32, C.c_int32,
+                                                 C.POINTER(C.c_int32), C.c_void_p, C.c_void_p]),
     "ptb_engine_save_png": (C.c_int, [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_int32]),
 }
 

@@ -67,7 +67,10 @@ __device__ __forceinline__ int trav_round(const float4* __restrict__ nodes, cons
         const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
         if (h0 && h1) {
             const bool first0 = n0 <= n1;
+            // the builder bounds the depth (bvh.cpp: depth + log2(count) <= 35 < kTravStack), so the stack cannot overflow;
+            // should that bound ever regress, the dropped subtree is counted (ptb_stats.bvh_stack_overflows, STATS builds)
             if (sp < kTravStack) T.stack[sp++] = first0 ? c1 : c0;
+            else if (STATS) st[ST_BVH_STACK_OVERFLOW]++;
             cur = first0 ? c0 : c1;
         } else if (h0) cur = c0;
         else if (h1) cur = c1;

@@ -1,6 +1,8 @@
 // engine.cpp — host mirror of internal/engine's public API over the C ABI, plus the ptb200_host.h exports.
 #include "engine.h"
 
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -101,6 +103,79 @@ int RenderInto(const scene::Scene& sc, RenderConfig cfg, RGBA& img, const std::f
         std::fprintf(stderr, "CUDA render error: %s\n", g_err.c_str());
     }
     return rc;
+}
+
+// ---- accumulation checkpoints.  File = CheckpointHeader + width*height*3 binary32 sums of samples [0, spp_done).
+namespace {
+struct CheckpointHeader {
+    char magic[8];                       // "PTBACC1\0"
+    int32_t width, height, spp_total, spp_done, max_depth;
+    uint32_t seed;
+    uint64_t scene_key;                  // FNV-1a of the flattened scene (analytic arrays, camera, sky, mesh generation-free triangle count)
+};
+uint64_t fnv(uint64_t h, const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 0x100000001b3ull; } return h; }
+uint64_t scene_key_of(const ptb_scene& v) {
+    uint64_t h = 0xcbf29ce484222325ull;
+    h = fnv(h, &v.n_obj, 4); h = fnv(h, &v.n_mat, 4);
+    if (v.n_obj > 0) { h = fnv(h, v.obj_type, 4 * (size_t)v.n_obj); h = fnv(h, v.obj_mat, 4 * (size_t)v.n_obj); h = fnv(h, v.obj_pos, 24 * (size_t)v.n_obj); h = fnv(h, v.obj_size, 24 * (size_t)v.n_obj); }
+    if (v.n_mat > 0) {
+        h = fnv(h, v.mat_type, 4 * (size_t)v.n_mat); h = fnv(h, v.mat_albedo, 24 * (size_t)v.n_mat); h = fnv(h, v.mat_rough, 8 * (size_t)v.n_mat);
+        h = fnv(h, v.mat_ior, 8 * (size_t)v.n_mat); h = fnv(h, v.mat_emit, 24 * (size_t)v.n_mat); h = fnv(h, v.mat_power, 8 * (size_t)v.n_mat);
+        h = fnv(h, v.mat_absorption, 24 * (size_t)v.n_mat); h = fnv(h, v.mat_smoothness, 8 * (size_t)v.n_mat);
+    }
+    h = fnv(h, &v.camera, sizeof v.camera); h = fnv(h, &v.sky.kind, 4); h = fnv(h, v.sky.color, 72);
+    if (v.n_mesh > 0) { h = fnv(h, v.mesh_tri_begin, 8 * (size_t)(v.n_mesh + 1)); h = fnv(h, v.tri_vertices, 36 * (size_t)v.mesh_tri_begin[v.n_mesh]); }
+    return h;
+}
+}  // namespace
+
+int RenderCheckpointed(ptb_ctx* ctx, const ptb_scene& view, RenderConfig cfg, uint32_t seed, uint8_t* pix, size_t stride, int img_w, int img_h,
+                       const std::string& path, int samples_per_call, int max_calls, int* spp_done_out, ptb_progress_fn progress, void* user) {
+    if (img_w != cfg.Width || img_h != cfg.Height) return PTB_OK;     // renderer.go:46-49
+    if (samples_per_call < 1) samples_per_call = cfg.SamplesPerPx;
+    int rc = ptb_scene_upload(ctx, &view);
+    if (rc != PTB_OK) return rc;
+    CheckpointHeader want{};
+    std::memcpy(want.magic, "PTBACC1", 8);
+    want.width = cfg.Width; want.height = cfg.Height; want.spp_total = cfg.SamplesPerPx; want.max_depth = cfg.MaxDepth; want.seed = seed;
+    want.scene_key = scene_key_of(view);
+    const size_t n = (size_t)cfg.Width * cfg.Height * 3;
+    std::vector<float> sums(n, 0.0f);
+    int done = 0;
+    {   // resume from the file when it belongs to this very render; anything else is ignored (and overwritten)
+        std::ifstream f(path, std::ios::binary);
+        CheckpointHeader h{};
+        if (f && f.read((char*)&h, sizeof h) && !std::memcmp(h.magic, want.magic, 8) && h.width == want.width && h.height == want.height &&
+            h.spp_total == want.spp_total && h.max_depth == want.max_depth && h.seed == want.seed && h.scene_key == want.scene_key &&
+            h.spp_done > 0 && h.spp_done <= h.spp_total && f.read((char*)sums.data(), (std::streamsize)(n * sizeof(float))))
+            done = h.spp_done;
+        else std::fill(sums.begin(), sums.end(), 0.0f);
+    }
+    ptb_cfg c{};
+    c.width = cfg.Width; c.height = cfg.Height; c.samples_per_px = cfg.SamplesPerPx; c.max_depth = cfg.MaxDepth; c.seed = seed;
+    int calls = 0;
+    if (done >= cfg.SamplesPerPx) {       // complete checkpoint: nothing left to trace, the device only runs the pixel epilogue
+        if ((rc = ptb_finalize_host(ctx, sums.data(), cfg.Width, cfg.Height, cfg.SamplesPerPx, pix, stride)) != PTB_OK) return rc;
+    }
+    while (done < cfg.SamplesPerPx && (max_calls <= 0 || calls < max_calls)) {
+        const int cnt = std::min(samples_per_call, cfg.SamplesPerPx - done);
+        c.sample_begin = done; c.sample_count = cnt;
+        if ((rc = ptb_render_resume(ctx, &c, sums.data(), pix, stride)) != PTB_OK) return rc;
+        done += cnt; calls++;
+        CheckpointHeader h = want;
+        h.spp_done = done;
+        const std::string tmp = path + ".tmp";
+        {
+            std::ofstream f(tmp, std::ios::binary | std::ios::trunc);
+            f.write((const char*)&h, sizeof h);
+            f.write((const char*)sums.data(), (std::streamsize)(n * sizeof(float)));
+            if (!f) { g_err = "checkpoint: write failed: " + tmp; return PTB_ERR_INVALID; }
+        }
+        if (std::rename(tmp.c_str(), path.c_str()) != 0) { g_err = "checkpoint: rename failed: " + path; return PTB_ERR_INVALID; }
+        if (progress) progress(user);
+    }
+    if (spp_done_out) *spp_done_out = done;
+    return PTB_OK;
 }
 
 RGBA Render(const scene::Scene& sc, RenderConfig cfg) {
@@ -240,6 +315,17 @@ int ptb_engine_render_into(ptb_ctx* ctx, const ptb_host_scene* sc, int32_t width
     // is reused; a 1 M-triangle mesh takes 35 ms to flatten
     int rc = engine::RenderFlatCtx(ctx, sc->flat.view(), engine::RenderConfig{width, height, spp, max_depth}, seed, pix, stride, img_w, img_h, progress, user);
     if (rc != PTB_OK) h_err = ptb_last_error(ctx);
+    return rc;
+}
+int ptb_engine_render_checkpointed(ptb_ctx* ctx, const ptb_host_scene* sc, int32_t width, int32_t height, int32_t spp, int32_t max_depth,
+                                   uint32_t seed, uint8_t* pix, size_t stride, int32_t img_w, int32_t img_h, const char* path,
+                                   int32_t samples_per_call, int32_t max_calls, int32_t* spp_done, ptb_progress_fn progress, void* user) {
+    if (!ctx || !sc || !pix || !path) return hfail(PTB_ERR_INVALID, "NULL argument");
+    int done = 0;
+    int rc = engine::RenderCheckpointed(ctx, sc->flat.view(), engine::RenderConfig{width, height, spp, max_depth}, seed, pix, stride, img_w, img_h,
+                                        path, samples_per_call, max_calls, &done, progress, user);
+    if (spp_done) *spp_done = done;
+    if (rc != PTB_OK) h_err = engine::LastError().empty() ? ptb_last_error(ctx) : engine::LastError();
     return rc;
 }
 int ptb_engine_save_png(const char* path, const uint8_t* pix, size_t stride, int32_t width, int32_t height) {

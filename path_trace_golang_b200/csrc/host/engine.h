@@ -43,4 +43,13 @@ int RenderIntoCtx(ptb_ctx* ctx, const scene::Scene& sc, RenderConfig cfg, uint32
 int RenderFlatCtx(ptb_ctx* ctx, const ptb_scene& view, RenderConfig cfg, uint32_t seed, uint8_t* pix, size_t stride,
                   int img_w, int img_h, ptb_progress_fn progress, void* user);
 
+
+// Accumulation checkpoints (the reference persists only scenes and PNGs, util.go:45-55): renders cfg in calls of
+// samples_per_call samples through ptb_render_resume and rewrites `path` (header + binary32 sums, atomically via rename) after
+// every call; a later call with the same scene / cfg / seed and an existing file continues where that one stopped and ends
+// with the same bits as an uninterrupted render.  max_calls > 0 stops after that many calls (an "interrupted" render);
+// *spp_done = samples accumulated so far.
+int RenderCheckpointed(ptb_ctx* ctx, const ptb_scene& view, RenderConfig cfg, uint32_t seed, uint8_t* pix, size_t stride, int img_w, int img_h,
+                       const std::string& path, int samples_per_call, int max_calls, int* spp_done, ptb_progress_fn progress, void* user);
+
 }  // namespace engine

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <atomic>
 #include <map>
 #include <sstream>
 #include <stdexcept>
@@ -444,8 +445,15 @@ static int32_t object_code(const std::string& t) {             // objects.go:237
     return -1;                                                 // dropped
 }
 
+uint64_t MeshData::NextGeneration() {
+    static std::atomic<uint64_t> next{1};
+    return next.fetch_add(1);
+}
+
 Flat Flatten(const Scene& sc) {
     Flat f;
+    uint64_t gen = 0xcbf29ce484222325ull;
+    auto fold = [&gen](const void* p, size_t n) { const unsigned char* b = (const unsigned char*)p; for (size_t i = 0; i < n; i++) { gen ^= b[i]; gen *= 0x100000001b3ull; } };
     std::map<std::string, int> by_id;                          // objects.go:226-229: later duplicate id wins
     for (size_t i = 0; i < sc.Materials.size(); i++) {
         const Material& m = sc.Materials[i];
@@ -467,6 +475,10 @@ Flat Flatten(const Scene& sc) {
             f.obj_mesh.push_back((int32_t)f.mesh_tri_begin.size() - 1);
             const double sx = o.Size.X != 0 ? o.Size.X : 1.0, sy = o.Size.Y != 0 ? o.Size.Y : 1.0, sz = o.Size.Z != 0 ? o.Size.Z : 1.0;
             const MeshData& m = *o.Mesh;
+            {   // identity of this object's world-space triangles: the mesh data's generation and the placement
+                const double place[6] = {o.Position.X, o.Position.Y, o.Position.Z, sx, sy, sz};
+                fold(&m.generation, sizeof m.generation); fold(place, sizeof place);
+            }
             for (uint32_t idx : m.triangles) {
                 f.tri_vertices.push_back((float)(o.Position.X + sx * (double)m.vertices[3 * idx]));
                 f.tri_vertices.push_back((float)(o.Position.Y + sy * (double)m.vertices[3 * idx + 1]));
@@ -482,6 +494,7 @@ Flat Flatten(const Scene& sc) {
         f.obj_pos.insert(f.obj_pos.end(), {o.Position.X, o.Position.Y, o.Position.Z});
         f.obj_size.insert(f.obj_size.end(), {o.Size.X, o.Size.Y, o.Size.Z});
     }
+    f.mesh_generation = f.mesh_tri_begin.size() > 1 ? (gen | 1) : 0;     // non-zero whenever there is a mesh
     const Camera& c = sc.Cam;
     f.camera = ptb_camera{{c.Position.X, c.Position.Y, c.Position.Z}, {c.Target.X, c.Target.Y, c.Target.Z}, {c.Up.X, c.Up.Y, c.Up.Z},
                           c.FOV, c.Aperture, c.FocusDist, c.AspectRatio};
@@ -550,6 +563,7 @@ ptb_scene Flat::view() const {
     s.camera = camera; s.sky = sky;
     s.n_mesh = (int32_t)mesh_tri_begin.size() - 1;
     s.obj_mesh = obj_mesh.data(); s.mesh_tri_begin = mesh_tri_begin.data(); s.tri_vertices = tri_vertices.data();
+    s.mesh_generation = mesh_generation;
     return s;
 }
 

@@ -57,6 +57,12 @@ constexpr const char* ObjectMesh = "mesh";   // EXTENSION (not in the reference)
 struct MeshData {
     std::vector<float> vertices;       // 3 per vertex, local space
     std::vector<uint32_t> triangles;   // 3 vertex indices per triangle
+    // Identity of the vertex / index data for ptb_scene.mesh_generation: unique per MeshData object at creation.  Code that
+    // edits vertices or triangles in place must call Touch() — the flattener folds it (with the owning object's position and
+    // size) into the generation the CUDA library uses to recognise an unchanged mesh without reading its triangles.
+    uint64_t generation = NextGeneration();
+    void Touch() { generation = NextGeneration(); }
+    static uint64_t NextGeneration();
     bool generated = false;            // true: came from the heightfield generator (Save writes the parameters back)
     int nx = 0, nz = 0, octaves = 0;
     uint32_t seed = 0;
@@ -114,6 +120,7 @@ struct Flat {
     std::vector<int32_t> obj_mesh;          // [n_obj] mesh index or -1
     std::vector<int64_t> mesh_tri_begin;    // [n_mesh+1] prefix of triangle counts
     std::vector<float> tri_vertices;        // 9 floats per triangle (v0, v1, v2), world space
+    uint64_t mesh_generation = 0;           // ptb_scene.mesh_generation: hash of every mesh object's (MeshData::generation, position, size)
     ptb_scene view() const;
 };
 Flat Flatten(const Scene& sc);

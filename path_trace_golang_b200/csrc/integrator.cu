@@ -26,8 +26,6 @@
 
 namespace ptb {
 
-__constant__ DevScene c_scene;
-
 #ifndef PTB_BLOCK_THREADS
 #define PTB_BLOCK_THREADS 128
 #endif
@@ -133,6 +131,15 @@ __device__ __forceinline__ F3 cosine_direction(F3 n, float r1, float r2) {
 struct RayK { F3 o, d, inv, oi, ainv; float a, inv_a; };
 __device__ __forceinline__ RayK make_ray(F3 o, F3 d) {
     RayK r;
+    // A direction component that is exactly 0 would make the (centre, half extent) slab form below compute inf - inf = NaN
+    // and silently drop that axis from the box test (the reference misses such a box when the origin is outside the
+    // slab: tNear, tFar = -+inf, objects.go:149-165).  Such components (about 2^-24 of all) become +-1e-30: 1/d = +-1e30
+    // stays finite, every slab distance keeps its sign, hit points and normals are unchanged in binary32.
+    if (fminf(fminf(fabsf(d.x), fabsf(d.y)), fabsf(d.z)) == 0.0f) {
+        if (d.x == 0.0f) d.x = copysignf(1e-30f, d.x);
+        if (d.y == 0.0f) d.y = copysignf(1e-30f, d.y);
+        if (d.z == 0.0f) d.z = copysignf(1e-30f, d.z);
+    }
     r.o = o; r.d = d;
     r.a = d.x * d.x + d.y * d.y + d.z * d.z;
     r.inv = f3(rcp_(d.x), rcp_(d.y), rcp_(d.z));
@@ -145,9 +152,9 @@ __device__ __forceinline__ RayK make_ray(F3 o, F3 d) {
 // box.hit (objects.go:141-183), branch-free: t0 = max(tmin, near_x, near_y, near_z), t1 = min(tmax, far_x, far_y,
 // far_z), hit iff t1 > t0 (the per-axis early exits of the reference are equivalent: t0 only grows, t1 only
 // shrinks).  near/far of an axis are min/max of the two slab distances, which is what the reference's swap on
-// invD < 0 produces.  [Only difference: a 0*inf = NaN slab distance (origin exactly on a slab plane AND that
-// direction component exactly 0) is dropped by min/max instead of poisoning the comparison; the binary64
-// parity kernel keeps the reference's exact form.]
+// invD < 0 produces.  make_ray keeps 1/d finite, so no slab distance is NaN (the reference's 0 * inf = NaN case —
+// origin exactly on a slab plane and that direction component exactly 0 — resolves here as "on the boundary = inside";
+// the binary64 parity kernel keeps the reference's exact form).
 __device__ __forceinline__ bool hit_box(float4 lo, float4 hi, const RayK& r, float tmin, float tmax, float& t_out) {
 #if PTB_FAST_MATH
     // record = (centre c, half extent h >= 0): the slab interval of an axis is (c - o)/d -+ h/|d|, so near and far come
@@ -208,9 +215,9 @@ __device__ __forceinline__ bool hit_plane(float4 lo, const RayK& r, float tmin, 
     t_out = t;
     return !(fabsf(r.d.y) < 1e-6f) && !(t < tmin || t > tmax);
 }
-// Constant-bank object record as two 16-byte vectors: lo = (a.xyz, meta), hi = (b.xyz, world_idx).
-__device__ __forceinline__ float4 obj_lo(int i) { return reinterpret_cast<const float4*>(&c_scene.obj[i])[0]; }
-__device__ __forceinline__ float4 obj_hi(int i) { return reinterpret_cast<const float4*>(&c_scene.obj[i])[1]; }
+// Object record as two 16-byte vectors: lo = (a.xyz, meta), hi = (b.xyz, world_idx).
+__device__ __forceinline__ float4 obj_lo(const DevObj* objs, int i) { return reinterpret_cast<const float4*>(objs + i)[0]; }
+__device__ __forceinline__ float4 obj_hi(const DevObj* objs, int i) { return reinterpret_cast<const float4*>(objs + i)[1]; }
 __device__ __forceinline__ bool hit_any(float4 lo, float4 hi, int type, const RayK& r, float tmin, float tmax, float& t) {
     if (type == PTB_OBJ_BOX) return hit_box(lo, hi, r, tmin, tmax, t);
     if (type == PTB_OBJ_SPHERE) return hit_sphere(lo, hi, r, tmin, tmax, t);
@@ -264,18 +271,18 @@ __device__ __forceinline__ bool front_face_only(const DevObj& ob, int type, F3 o
     return (qa > 0.0f ? da : -da) < 0.0f;
 }
 
-__device__ __forceinline__ F3 sky_color(F3 d) {                                                   // renderer.go:56-92
-    if (c_scene.sky.kind == PTB_SKY_GRADIENT) {
+__device__ __forceinline__ F3 sky_color(const DevSky& sky, F3 d) {                                // renderer.go:56-92
+    if (sky.kind == PTB_SKY_GRADIENT) {
         float len = sqrt_(d.x * d.x + d.y * d.y + d.z * d.z);
-        if (len == 0.0f) return f3(c_scene.sky.horizon[0], c_scene.sky.horizon[1], c_scene.sky.horizon[2]);
+        if (len == 0.0f) return f3(sky.horizon[0], sky.horizon[1], sky.horizon[2]);
         float t = (d.y * rcp_(len) + 1.0f) * 0.5f;
         t = t < 0.0f ? 0.0f : t;
         t = t > 1.0f ? 1.0f : t;
-        return f3(c_scene.sky.horizon[0] * (1.0f - t) + c_scene.sky.zenith[0] * t,
-                  c_scene.sky.horizon[1] * (1.0f - t) + c_scene.sky.zenith[1] * t,
-                  c_scene.sky.horizon[2] * (1.0f - t) + c_scene.sky.zenith[2] * t);
+        return f3(sky.horizon[0] * (1.0f - t) + sky.zenith[0] * t,
+                  sky.horizon[1] * (1.0f - t) + sky.zenith[1] * t,
+                  sky.horizon[2] * (1.0f - t) + sky.zenith[2] * t);
     }
-    return f3(c_scene.sky.color[0], c_scene.sky.color[1], c_scene.sky.color[2]);
+    return f3(sky.color[0], sky.color[1], sky.color[2]);
 }
 
 // Pixel epilogue of renderer.go:189-221 in binary64 (one value per channel per pixel; cost is nil).
@@ -287,7 +294,9 @@ __device__ __forceinline__ uint8_t to_u8(float sum, double inv_spp) {
 
 template <bool STATS>
 __global__ void __launch_bounds__(PTB_BLOCK_THREADS, PTB_MIN_BLOCKS)
-integrate_kernel(const __grid_constant__ FrameParams fp) {
+integrate_kernel(const __grid_constant__ KernelArgs ka) {
+    const FrameParams& fp = ka.fp;
+    const SceneK& c_scene = ka.sc;
     extern __shared__ uint4 s_blob[];
     const int n_obj = c_scene.n_obj;
     {
@@ -365,10 +374,10 @@ integrate_kernel(const __grid_constant__ FrameParams fp) {
 #pragma unroll 2
         for (int i = 0; i < n_box; ++i) {
             float t;
-            if (hit_box(obj_lo(i), obj_hi(i), ray, 0.001f, best, t)) { best = t; bid = i; }
+            if (hit_box(obj_lo(s_obj, i), obj_hi(s_obj, i), ray, 0.001f, best, t)) { best = t; bid = i; }
         }
         for (int i = n_box; i < n_obj; ++i) {
-            const float4 lo = obj_lo(i), hi = obj_hi(i);
+            const float4 lo = obj_lo(s_obj, i), hi = obj_hi(s_obj, i);
             float t;
             const bool h = (__float_as_int(lo.w) & 3) == PTB_OBJ_SPHERE ? hit_sphere(lo, hi, ray, 0.001f, best, t) : hit_plane(lo, ray, 0.001f, best, t);
             if (h) { best = t; bid = i; }
@@ -378,7 +387,7 @@ integrate_kernel(const __grid_constant__ FrameParams fp) {
             if (STATS) st[ST_SEGMENTS]++;
             bool done = false;
             if (bid < 0) {                                    // renderer.go:304-306
-                F3 sk = sky_color(d);
+                F3 sk = sky_color(c_scene.sky, d);
                 L.x += beta.x * sk.x; L.y += beta.y * sk.y; L.z += beta.z * sk.z;
                 done = true;
                 if (STATS) st[ST_END_SKY]++;
@@ -464,11 +473,11 @@ integrate_kernel(const __grid_constant__ FrameParams fp) {
                         F3 ep = p;
                         const int n_diel = c_scene.n_diel;
                         for (int k = 0; k < n_diel; ++k) {    // only dielectric objects can be accepted (:335)
-                            const int ei = c_scene.diel_idx[k];
-                            const DevObj& eo = c_scene.obj[ei];
+                            const int ei = __ldg(c_scene.diel_idx + k);
+                            const DevObj& eo = s_obj[ei];
                             const int et = eo.meta & 3;
                             float t;
-                            if (!hit_any(obj_lo(ei), obj_hi(ei), et, er, 0.0001f, exit_t, t)) continue;
+                            if (!hit_any(obj_lo(s_obj, ei), obj_hi(s_obj, ei), et, er, 0.0001f, exit_t, t)) continue;
                             F3 q;
                             const bool qf = front_face_only(eo, et, p, sd, t, q);
                             if (!qf && t < exit_t) {
@@ -550,9 +559,6 @@ integrate_kernel(const __grid_constant__ FrameParams fp) {
 }  // namespace ptb
 #include "bvh.cuh"
 #include "wavefront.cuh"
-#ifdef PTB_ENABLE_WAVEQUEUE      // experimental queue-driven variant (slower than the phased kernel so far)
-#include "wavequeue.cuh"
-#endif
 namespace ptb {
 
 __global__ void finalize_kernel(const float* __restrict__ accum, int n_pix, double inv_spp, uchar4* __restrict__ rgba) {
@@ -560,6 +566,15 @@ __global__ void finalize_kernel(const float* __restrict__ accum, int n_pix, doub
     if (i >= n_pix) return;
     const float* a = accum + (size_t)i * 3;
     rgba[i] = make_uchar4(to_u8(a[0], inv_spp), to_u8(a[1], inv_spp), to_u8(a[2], inv_spp), 255);
+}
+
+// max_depth <= 0: rayColorOpt returns black at once (renderer.go:287-289) — every pixel is (0, 0, 0, 255) and the sums
+// do not change.
+__global__ void clear_frame_kernel(float* __restrict__ accum, int accum_resume, uchar4* __restrict__ rgba, int n_pix) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pix) return;
+    if (accum && !accum_resume) { accum[3 * (size_t)i] = 0.0f; accum[3 * (size_t)i + 1] = 0.0f; accum[3 * (size_t)i + 2] = 0.0f; }
+    if (rgba) rgba[i] = make_uchar4(0, 0, 0, 255);
 }
 
 // Split frames (FrameParams::split_k > 1): add the k partial-sum planes of every pixel in plane order, then accumulation
@@ -607,6 +622,39 @@ __global__ void finalize_peers_kernel(const float* const* __restrict__ bufs, int
     }
 }
 
+// The same reduce + epilogue for ONE SLICE of the frame, the multi-process arrangement (one rank per GPU): rank r sums pixels
+// [p_begin, p_end) of all ranks' buffers — its own from HBM, the others through NVLink peer loads (CUDA IPC mappings) — and
+// stores the finalised RGBA8 pixels straight into rank 0's image, again over NVLink: reduce-scatter, epilogue and gather in
+// one kernel, every link of the switch carrying 1/N of the traffic instead of everything converging on rank 0.
+// p_begin is a multiple of 4 (3 x 16-byte loads per 4 pixels and buffer).  Sum order: rank 0, 1, 2, ... on every rank.
+__global__ void reduce_finalize_slice_kernel(const float* const* __restrict__ bufs, int n_bufs, long long p_begin, long long p_end, double inv_spp,
+                                             uchar4* __restrict__ rgba_root) {
+    const long long p0 = p_begin + 4ll * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    if (p0 >= p_end) return;
+    if (p0 + 4 <= p_end) {
+        float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
+        for (int k = 0; k < n_bufs; ++k) {
+            const float4* src = reinterpret_cast<const float4*>(bufs[k] + 3 * p0);
+            const float4 x = src[0], y = src[1], z = src[2];
+            a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+            b.x += y.x; b.y += y.y; b.z += y.z; b.w += y.w;
+            c.x += z.x; c.y += z.y; c.z += z.z; c.w += z.w;
+        }
+        uint4 o;   // 4 pixels = one 16-byte store
+        o.x = (uint32_t)to_u8(a.x, inv_spp) | (uint32_t)to_u8(a.y, inv_spp) << 8 | (uint32_t)to_u8(a.z, inv_spp) << 16 | 0xFF000000u;
+        o.y = (uint32_t)to_u8(a.w, inv_spp) | (uint32_t)to_u8(b.x, inv_spp) << 8 | (uint32_t)to_u8(b.y, inv_spp) << 16 | 0xFF000000u;
+        o.z = (uint32_t)to_u8(b.z, inv_spp) | (uint32_t)to_u8(b.w, inv_spp) << 8 | (uint32_t)to_u8(c.x, inv_spp) << 16 | 0xFF000000u;
+        o.w = (uint32_t)to_u8(c.y, inv_spp) | (uint32_t)to_u8(c.z, inv_spp) << 8 | (uint32_t)to_u8(c.w, inv_spp) << 16 | 0xFF000000u;
+        *reinterpret_cast<uint4*>(rgba_root + p0) = o;
+    } else {
+        for (long long p = p0; p < p_end; ++p) {
+            float r = 0, g = 0, bb = 0;
+            for (int k = 0; k < n_bufs; ++k) { const float* s = bufs[k] + 3 * p; r += s[0]; g += s[1]; bb += s[2]; }
+            rgba_root[p] = make_uchar4(to_u8(r, inv_spp), to_u8(g, inv_spp), to_u8(bb, inv_spp), 255);
+        }
+    }
+}
+
 // FP32 FMA throughput probe: 8 independent chains per thread, 2 flop per FMA.
 __global__ void fma_peak_kernel(float* out, int iters) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f, a7 = a0 + 7.f;
@@ -622,86 +670,61 @@ __global__ void fma_peak_kernel(float* out, int iters) {
 }
 
 // ---------------------------------------------------------------- launchers
-int upload_scene_constants(const DevScene& h, void* stream) {
-    // header + diel_idx + obj: only the used prefix of each array is copied
-    cudaStream_t s = (cudaStream_t)stream;
-    cudaError_t e = cudaMemcpyToSymbolAsync(c_scene, &h, offsetof(DevScene, diel_idx), 0, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess && h.n_diel > 0)
-        e = cudaMemcpyToSymbolAsync(c_scene, h.diel_idx, sizeof(int32_t) * h.n_diel, offsetof(DevScene, diel_idx), cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess && h.n_obj > 0)
-        e = cudaMemcpyToSymbolAsync(c_scene, h.obj, sizeof(DevObj) * h.n_obj, offsetof(DevScene, obj), cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess && h.n_mat > 0)
-        e = cudaMemcpyToSymbolAsync(c_scene, h.mat, sizeof(DevMat) * h.n_mat, offsetof(DevScene, mat), cudaMemcpyHostToDevice, s);
-    return (int)e;
+int launch_integrator(const KernelArgs& ka, bool stats, void* stream) {
+    const FrameParams& fp = ka.fp;
+    dim3 grid((fp.width + 15) / 16, (fp.height + 7) / 8);
+    size_t smem = (size_t)(ka.sc.n_obj * 2 + ka.sc.n_mat * 3) * sizeof(uint4);     // <= kSmallBlobBytes (checked by the caller)
+    if (stats) integrate_kernel<true><<<grid, PTB_BLOCK_THREADS, smem, (cudaStream_t)stream>>>(ka);
+    else integrate_kernel<false><<<grid, PTB_BLOCK_THREADS, smem, (cudaStream_t)stream>>>(ka);
+    return (int)cudaGetLastError();
 }
 
-int launch_integrator(const FrameParams& fp, bool stats, int n_obj, int n_mat, void* stream) {
-    dim3 grid((fp.width + 15) / 16, (fp.height + 7) / 8);
-    size_t smem = (size_t)(n_obj * 2 + n_mat * 3) * sizeof(uint4);
-    if (stats) integrate_kernel<true><<<grid, PTB_BLOCK_THREADS, smem, (cudaStream_t)stream>>>(fp);
-    else integrate_kernel<false><<<grid, PTB_BLOCK_THREADS, smem, (cudaStream_t)stream>>>(fp);
+int launch_clear_frame(float* accum, int accum_resume, uint8_t* rgba, int n_pix, void* stream) {
+    clear_frame_kernel<<<(n_pix + 255) / 256, 256, 0, (cudaStream_t)stream>>>(accum, accum_resume, reinterpret_cast<uchar4*>(rgba), n_pix);
     return (int)cudaGetLastError();
 }
 
 constexpr int kMeshBlocksPerSm = PTB_WF_MIN_BLOCKS;
 size_t wf_trav_scratch_bytes(int sm_count) { return (size_t)sm_count * kMeshBlocksPerSm * WF_SLOTS * kTravStride * sizeof(int); }
 
-template <bool STATS, bool MESH>
-static int launch_wf_variant(const FrameParams& fp, size_t smem, int sm_count, cudaStream_t stream) {
-    static int blocks_per_sm = 0;
-    if (!blocks_per_sm) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(integrate_wf_kernel<STATS, MESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        int nb = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, integrate_wf_kernel<STATS, MESH>, WF_THREADS, smem);
+// The opt-in to more than 48 KB of dynamic shared memory is a per-DEVICE attribute of the kernel and the occupancy depends on
+// the shared-memory size of the scene at hand, so both are remembered per context (= per device) and per size: a small
+// scene rendered first, a large one later, or several devices in one process all get the right attribute and grid.
+template <bool STATS, bool MESH, bool BIG>
+static int launch_wf_variant(const KernelArgs& ka, size_t smem, int sm_count, LaunchCache::Entry& lc, cudaStream_t stream) {
+    const FrameParams& fp = ka.fp;
+    if (smem > 48 * 1024 && smem > lc.smem_optin) {
+        cudaError_t e = cudaFuncSetAttribute(integrate_wf_kernel<STATS, MESH, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        blocks_per_sm = nb > 0 ? nb : 1;
+        lc.smem_optin = smem;
+    }
+    if (lc.smem_occ != smem) {
+        int nb = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, integrate_wf_kernel<STATS, MESH, BIG>, WF_THREADS, smem);
+        if (e != cudaSuccess) return (int)e;
+        lc.blocks_per_sm = nb > 0 ? nb : 1;
+        lc.smem_occ = smem;
     }
     const long long n_pix = (long long)fp.width * fp.rows;
-    long long grid = (long long)sm_count * (MESH && blocks_per_sm > kMeshBlocksPerSm ? kMeshBlocksPerSm : blocks_per_sm);   // trav_scratch is sized for kMeshBlocksPerSm
+    long long grid = (long long)sm_count * (MESH && lc.blocks_per_sm > kMeshBlocksPerSm ? kMeshBlocksPerSm : lc.blocks_per_sm);   // trav_scratch is sized for kMeshBlocksPerSm
     const long long need = (n_pix * (fp.split_k > 1 ? fp.split_k : 1) + WF_SLOTS - 1) / WF_SLOTS;
     if (grid > need) grid = need;
-    integrate_wf_kernel<STATS, MESH><<<(unsigned)grid, WF_THREADS, smem, stream>>>(fp);
+    integrate_wf_kernel<STATS, MESH, BIG><<<(unsigned)grid, WF_THREADS, smem, stream>>>(ka);
     return (int)cudaGetLastError();
 }
 
-int launch_integrator_wf(const FrameParams& fp, bool stats, int n_obj, int n_mat, int sm_count, void* stream) {
-    const size_t smem = ((sizeof(WfState) + 15) / 16 + (size_t)(n_obj * 2 + n_mat * 3)) * sizeof(uint4);
+int launch_integrator_wf(const KernelArgs& ka, bool stats, bool big, int sm_count, LaunchCache* cache, void* stream) {
+    // BIG worlds read the object / material records in place (global memory): no shared-memory copy
+    const size_t smem = ((sizeof(WfState) + 15) / 16 + (big ? 0 : (size_t)(ka.sc.n_obj * 2 + ka.sc.n_mat * 3))) * sizeof(uint4);
     cudaStream_t st = (cudaStream_t)stream;
-    const bool mesh = fp.bvh_nodes != nullptr;      // the mesh-free instantiation carries no traversal code (it costs ~10 %)
-    if (stats) return mesh ? launch_wf_variant<true, true>(fp, smem, sm_count, st) : launch_wf_variant<true, false>(fp, smem, sm_count, st);
-    return mesh ? launch_wf_variant<false, true>(fp, smem, sm_count, st) : launch_wf_variant<false, false>(fp, smem, sm_count, st);
+    const bool mesh = ka.fp.bvh_nodes != nullptr;      // the mesh-free instantiation carries no traversal code (it costs ~10 %)
+    LaunchCache::Entry& lc = cache->wf[(stats ? 4 : 0) | (mesh ? 2 : 0) | (big ? 1 : 0)];
+#define PTB_WF_CASE(S, M, B) if (stats == S && mesh == M && big == B) return launch_wf_variant<S, M, B>(ka, smem, sm_count, lc, st);
+    PTB_WF_CASE(false, false, false) PTB_WF_CASE(false, false, true) PTB_WF_CASE(false, true, false) PTB_WF_CASE(false, true, true)
+    PTB_WF_CASE(true, false, false) PTB_WF_CASE(true, false, true) PTB_WF_CASE(true, true, false) PTB_WF_CASE(true, true, true)
+#undef PTB_WF_CASE
+    return (int)cudaErrorInvalidValue;
 }
-
-#ifdef PTB_ENABLE_WAVEQUEUE
-template <bool STATS, bool MESH>
-static int launch_wq_variant(const FrameParams& fp, size_t smem, int sm_count, cudaStream_t stream) {
-    static int blocks_per_sm = 0;
-    if (!blocks_per_sm) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(integrate_wq_kernel<STATS, MESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        int nb = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, integrate_wq_kernel<STATS, MESH>, WQ_THREADS, smem);
-        if (e != cudaSuccess) return (int)e;
-        blocks_per_sm = nb > 0 ? nb : 1;
-    }
-    const long long n_pix = (long long)fp.width * fp.height;
-    long long grid = (long long)sm_count * blocks_per_sm;
-    const long long need = (n_pix + WQ_SLOTS - 1) / WQ_SLOTS;
-    if (grid > need) grid = need;
-    integrate_wq_kernel<STATS, MESH><<<(unsigned)grid, WQ_THREADS, smem, stream>>>(fp);
-    return (int)cudaGetLastError();
-}
-
-int launch_integrator_wq(const FrameParams& fp, bool stats, int n_obj, int n_mat, int sm_count, void* stream) {
-    const size_t smem = ((sizeof(WqState) + 15) / 16 + (size_t)(n_obj * 2 + n_mat * 3)) * sizeof(uint4);
-    cudaStream_t st = (cudaStream_t)stream;
-    const bool mesh = fp.bvh_nodes != nullptr;
-    if (stats) return mesh ? launch_wq_variant<true, true>(fp, smem, sm_count, st) : launch_wq_variant<true, false>(fp, smem, sm_count, st);
-    return mesh ? launch_wq_variant<false, true>(fp, smem, sm_count, st) : launch_wq_variant<false, false>(fp, smem, sm_count, st);
-}
-
-#else
-int launch_integrator_wq(const FrameParams&, bool, int, int, int, void*) { return (int)cudaErrorNotSupported; }
-#endif
 
 int launch_finalize(const float* accum, int width, int height, int spp_total, uint8_t* rgba, void* stream) {
     int n = width * height;
@@ -732,6 +755,15 @@ int launch_finalize_peers(const float* const* d_bufs_on_dev0, int n_bufs, int wi
     const int n = width * height, threads = 256, groups = (n + 3) / 4;
     finalize_peers_kernel<<<(groups + threads - 1) / threads, threads, 0, (cudaStream_t)stream>>>(d_bufs_on_dev0, n_bufs, n, 1.0 / (double)spp_total,
                                                                                               reinterpret_cast<uchar4*>(rgba));
+    return (int)cudaGetLastError();
+}
+
+int launch_reduce_finalize_slice(const float* const* d_bufs, int n_bufs, long long p_begin, long long p_end, int spp_total, uint8_t* rgba_root, void* stream) {
+    if (p_end <= p_begin) return 0;
+    const long long groups = (p_end - p_begin + 3) / 4;
+    const int threads = 256;
+    reduce_finalize_slice_kernel<<<(unsigned)((groups + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(d_bufs, n_bufs, p_begin, p_end, 1.0 / (double)spp_total,
+                                                                                                                   reinterpret_cast<uchar4*>(rgba_root));
     return (int)cudaGetLastError();
 }
 

@@ -48,6 +48,9 @@ constexpr int WF_CHUNKS = WF_SLOTS / 32;
 // CL_DIEL..CL_SPEC match the class bits the host writes into DevObj::meta (api.cu).
 // Measured chunk costs on C3 (cycles, -DPTB_WF_TIMING): DIEL 5500, TERM 3450, REGEN 2740, DIFFUSE 2210, SPEC 1630.
 // CL_CONT (MESH only): the slot's BVH traversal ran out of its per-iteration step budget and continues next iteration.
+#ifndef PTB_MERGE_TERM_REGEN
+#define PTB_MERGE_TERM_REGEN 1        // sort slots that only need a new camera ray together with the terminating ones (one class boundary less)
+#endif
 enum : int { CL_DIEL = 0, CL_TERM = 1, CL_REGEN = 2, CL_DIFFUSE = 3, CL_SPEC = 4, CL_CONT = 5, CL_DEAD = 6, CL_COUNT = 7 };
 
 template <int N>
@@ -72,15 +75,20 @@ struct WfState : SlotState<WF_SLOTS> {
 
 // Finish the slot's current sample and give it its next camera ray: next sample of the same pixel, or — when the
 // pixel is complete — write the pixel out and take the next pixel from the global counter (renderer.go:171-221).
+// Sample sub-range of global plane g of a split frame (FrameParams::split_*): boundaries of the WHOLE render.
+__device__ __forceinline__ int plane_bound(const FrameParams& fp, int g) {
+    return fp.full_begin + (int)((unsigned)(fp.full_end - fp.full_begin) * (unsigned)g / (unsigned)fp.split_total);
+}
+
 template <bool STATS, class SS>
-__device__ __forceinline__ void path_regen(SS& S, const FrameParams& fp, int n_pix, int j, bool sample_done, unsigned long long* st) {
+__device__ __forceinline__ void path_regen(SS& S, const FrameParams& fp, const SceneK& sc, int n_pix, int j, bool sample_done, unsigned long long* st) {
     int w = S.pix[j];                                     // work item: the pixel, or plane * n_pix + pixel when the frame is split
     int s = S.smp[j] + (sample_done ? 1 : 0);
-    const bool split = fp.split_k > 1;
+    const bool split = fp.planes != nullptr;             // (a launch may cover a single plane of a split render)
     int pix = w, plane = 0, s_end = fp.s_end;
     if (split && w >= 0) {
         plane = w / n_pix; pix = w - plane * n_pix;
-        s_end = fp.s_begin + (int)((unsigned)(fp.s_end - fp.s_begin) * (unsigned)(plane + 1) / (unsigned)fp.split_k);
+        s_end = plane_bound(fp, fp.split_base + plane + 1);
     }
     if (w < 0 || s >= s_end) {
         if (w >= 0) {                                     // item complete: epilogue / accumulation buffer / partial-sum plane
@@ -102,7 +110,7 @@ __device__ __forceinline__ void path_regen(SS& S, const FrameParams& fp, int n_p
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
         if (split) {
             plane = w / n_pix; pix = w - plane * n_pix;
-            s = fp.s_begin + (int)((unsigned)(fp.s_end - fp.s_begin) * (unsigned)plane / (unsigned)fp.split_k);
+            s = plane_bound(fp, fp.split_base + plane);
         } else if (fp.accum_resume) { const float* a = fp.accum + (size_t)pix * 3; a0 = a[0]; a1 = a[1]; a2 = a[2]; }
         S.ax[j] = a0; S.ay[j] = a1; S.az[j] = a2;
     }
@@ -115,7 +123,7 @@ __device__ __forceinline__ void path_regen(SS& S, const FrameParams& fp, int n_p
     const float u = ((float)px + rng.peek(0)) * fp.inv_w;                       // renderer.go:182
     const float v = ((fp.h_minus_1 - (float)py) + rng.peek(1)) * fp.inv_h;      // renderer.go:174,183
     rng.ctr = 2u;
-    const DevCamera& cam = c_scene.cam;                                         // camera.go:60-74
+    const DevCamera& cam = sc.cam;                                              // camera.go:60-74
     F3 dir = f3(cam.llc[0] + cam.horizontal[0] * u + cam.vertical[0] * v - cam.origin[0],
                 cam.llc[1] + cam.horizontal[1] * u + cam.vertical[1] * v - cam.origin[1],
                 cam.llc[2] + cam.horizontal[2] * u + cam.vertical[2] * v - cam.origin[2]);
@@ -137,8 +145,20 @@ __device__ __forceinline__ void path_regen(SS& S, const FrameParams& fp, int n_p
 
 // One slot's work after a closest-hit scan, given its class c: scatter (+ exit search, Russian roulette), or add the
 // sky / emitted radiance; terminate-class and regenerate-class slots then get their next camera ray.
-template <bool STATS, bool MESH, class SS>
-__device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const DevObj* __restrict__ s_obj, const DevMat* __restrict__ s_mat,
+// The scan table: kernel parameter (constant bank, uniform datapath) or, for BIG worlds, global memory.
+template <bool BIG>
+__device__ __forceinline__ float4 tab_ld4(const SceneK& sc, int i4) {
+    if (BIG) return __ldg(sc.tab_global + i4);
+    return reinterpret_cast<const float4*>(sc.scan_tab)[i4];
+}
+template <bool BIG>
+__device__ __forceinline__ float tab_ld1(const SceneK& sc, int i) {
+    if (BIG) return __ldg(reinterpret_cast<const float*>(sc.tab_global) + i);
+    return sc.scan_tab[i];
+}
+
+template <bool STATS, bool MESH, bool BIG, class SS>
+__device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const SceneK& sc, const DevObj* __restrict__ s_obj, const DevMat* __restrict__ s_mat,
                                            int n_pix, int j, int c, unsigned long long* st) {
         if (c == CL_DIEL || c == CL_DIFFUSE || c == CL_SPEC) {
         const F3 ro = f3(S.ox[j], S.oy[j], S.oz[j]);
@@ -230,13 +250,11 @@ __device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const D
                         if (d2 > 1e-8f && d2 < 1000.0f) { hit_exit = true; exit_t = t; ep = q; }
                     }
                 };
-                if (c_scene.exit_typed) {                 // every dielectric object is a box or a sphere: typed records, no index loads
-                    const float4* tab4 = reinterpret_cast<const float4*>(c_scene.scan_tab);
-                    const int n_dbox = c_scene.n_dbox, n_dsph = c_scene.n_dsph;
-                    const float4* dbox = tab4 + c_scene.dbox_off4;
-                    const float4* dsph = tab4 + c_scene.dsph_off4;
+                if (sc.exit_typed) {                      // every dielectric object is a box or a sphere: typed records, no index loads
+                    const int n_dbox = sc.n_dbox, n_dsph = sc.n_dsph;
+                    const int dbox_off4 = sc.dbox_off4, dsph_off4 = sc.dsph_off4;
                     for (int k = 0; k < n_dbox; ++k) {
-                        const float4 bc = dbox[2 * k], bh = dbox[2 * k + 1];
+                        const float4 bc = tab_ld4<BIG>(sc, dbox_off4 + 2 * k), bh = tab_ld4<BIG>(sc, dbox_off4 + 2 * k + 1);
                         float t;
                         if (!hit_box(bc, bh, er, 0.0001f, exit_t, t)) continue;
                         DevObj eo;
@@ -246,7 +264,7 @@ __device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const D
                         consider(t, qf, q);
                     }
                     for (int k = 0; k < n_dsph; ++k) {
-                        const float4 sp = dsph[k];
+                        const float4 sp = tab_ld4<BIG>(sc, dsph_off4 + k);
                         float t;
                         if (!hit_sphere4(sp.x, sp.y, sp.z, sp.w, er, 0.0001f, exit_t, t)) continue;
                         DevObj eo;
@@ -256,13 +274,13 @@ __device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const D
                         consider(t, qf, q);
                     }
                 } else {
-                    const int n_diel = c_scene.n_diel;
+                    const int n_diel = sc.n_diel;
                     for (int k = 0; k < n_diel; ++k) {
-                        const int ei = c_scene.diel_idx[k];
-                        const DevObj& eo = c_scene.obj[ei];
+                        const int ei = __ldg(sc.diel_idx + k);
+                        const DevObj eo = s_obj[ei];
                         const int et = eo.meta & 3;
                         float t;
-                        if (!hit_any(obj_lo(ei), obj_hi(ei), et, er, 0.0001f, exit_t, t)) continue;
+                        if (!hit_any(obj_lo(s_obj, ei), obj_hi(s_obj, ei), et, er, 0.0001f, exit_t, t)) continue;
                         F3 q;
                         const bool qf = front_face_only(eo, et, p, sd, t, q);
                         consider(t, qf, q);
@@ -313,11 +331,11 @@ __device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const D
             S.ctr[j] = rng.ctr;
             S.depth[j] = depth;
         }
-    } else if (c == CL_TERM) {                            // sky (renderer.go:304-306) or emissive hit (:308-312)
-        F3 e;
+    } else if (c == CL_TERM && (!PTB_MERGE_TERM_REGEN || S.depth[j] > 0)) {   // sky (renderer.go:304-306) or emissive hit (:308-312)
+        F3 e;                                             // (merged classes: a slot without a live path only regenerates)
         const int hb = S.bid[j];
         if (hb < 0) {
-            e = sky_color(f3(S.dx[j], S.dy[j], S.dz[j]));
+            e = sky_color(sc.sky, f3(S.dx[j], S.dy[j], S.dz[j]));
             if (STATS) st[ST_END_SKY]++;
         } else {
             const bool is_tri = MESH && (hb & kTriBit) != 0;
@@ -328,22 +346,25 @@ __device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const D
         }
         S.ax[j] += S.bx[j] * e.x; S.ay[j] += S.by[j] * e.y; S.az[j] += S.bz[j] * e.z;
     }
-    if (c == CL_TERM || c == CL_REGEN) path_regen<STATS>(S, fp, n_pix, j, true, st);
+    if (c == CL_TERM || c == CL_REGEN) path_regen<STATS>(S, fp, sc, n_pix, j, true, st);
 }
 
-template <bool STATS, bool MESH>
+template <bool STATS, bool MESH, bool BIG>
 __global__ void __launch_bounds__(WF_THREADS, PTB_WF_MIN_BLOCKS)
-integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
+integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
+    const FrameParams& fp = ka.fp;
+    const SceneK& c_scene = ka.sc;
     extern __shared__ uint4 s_raw[];
     WfState& S = *reinterpret_cast<WfState*>(s_raw);
     uint4* s_blob = s_raw + (sizeof(WfState) + 15) / 16;
     const int n_obj = c_scene.n_obj;
-    {
+    if (!BIG) {
         const int n_words = n_obj * 2 + c_scene.n_mat * 3;
         for (int i = threadIdx.x; i < n_words; i += blockDim.x) s_blob[i] = fp.scene_blob[i];
     }
-    const DevObj* __restrict__ s_obj = reinterpret_cast<const DevObj*>(s_blob);
-    const DevMat* __restrict__ s_mat = reinterpret_cast<const DevMat*>(s_blob + 2 * n_obj);
+    // object / material records for the divergent look-ups: the CTA's shared-memory copy, or (BIG) global memory in place
+    const DevObj* __restrict__ s_obj = BIG ? reinterpret_cast<const DevObj*>(fp.scene_blob) : reinterpret_cast<const DevObj*>(s_blob);
+    const DevMat* __restrict__ s_mat = BIG ? reinterpret_cast<const DevMat*>(fp.scene_blob + 2 * n_obj) : reinterpret_cast<const DevMat*>(s_blob + 2 * n_obj);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_pix = fp.width * fp.rows;
@@ -357,7 +378,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
         const int j = tid + k * WF_THREADS;
         S.pix[j] = -1; S.smp[j] = 0; S.depth[j] = 0; S.trav[j] = 0;
         S.ox[j] = 0.f; S.oy[j] = 0.f; S.oz[j] = 0.f; S.dx[j] = 0.f; S.dy[j] = 0.f; S.dz[j] = 1.f;
-        if (fp.max_depth > 0) path_regen<STATS>(S, fp, n_pix, j, false, st);
+        if (fp.max_depth > 0) path_regen<STATS>(S, fp, c_scene, n_pix, j, false, st);
     }
     if (tid == 0) { S.n_list = 0; S.next_chunk = 0; }
     __syncthreads();
@@ -388,12 +409,11 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
                 ray[k] = make_ray(f3(S.ox[j], S.oy[j], S.oz[j]), f3(S.dx[j], S.dy[j], S.dz[j]));
                 best[k] = FLT_MAX; bid[k] = -1;
             }
-            const float4* tab4 = reinterpret_cast<const float4*>(c_scene.scan_tab);
             for (int gi = 0; gi < n_box_groups; ++gi) {              // kBoxGroup boxes per trip, 6 floats each (scene_dev.h)
-                const float4* q = tab4 + gi * (kBoxGroup * 6 / 4);
+                const int q = gi * (kBoxGroup * 6 / 4);
                 float bx[kBoxGroup * 6];
 #pragma unroll
-                for (int v = 0; v < kBoxGroup * 6 / 4; ++v) { const float4 w = q[v]; bx[4 * v] = w.x; bx[4 * v + 1] = w.y; bx[4 * v + 2] = w.z; bx[4 * v + 3] = w.w; }
+                for (int v = 0; v < kBoxGroup * 6 / 4; ++v) { const float4 w = tab_ld4<BIG>(c_scene, q + v); bx[4 * v] = w.x; bx[4 * v + 1] = w.y; bx[4 * v + 2] = w.z; bx[4 * v + 3] = w.w; }
 #pragma unroll
                 for (int u = 0; u < kBoxGroup; ++u) {
                     const float4 lo = make_float4(bx[6 * u], bx[6 * u + 1], bx[6 * u + 2], 0.0f);
@@ -406,7 +426,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
                 }
             }
             for (int i = 0; i < n_plane_run; ++i) {
-                const float py = c_scene.scan_tab[plane_off4 * 4 + i];
+                const float py = tab_ld1<BIG>(c_scene, plane_off4 * 4 + i);
 #pragma unroll
                 for (int k = 0; k < WF_SG; ++k) {
                     float t;
@@ -416,7 +436,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
             for (int gi = 0; gi < n_sphere_groups; ++gi) {
 #pragma unroll
                 for (int u = 0; u < kSphereGroup; ++u) {
-                    const float4 sp = tab4[sphere_off4 + gi * kSphereGroup + u];
+                    const float4 sp = tab_ld4<BIG>(c_scene, sphere_off4 + gi * kSphereGroup + u);
 #pragma unroll
                     for (int k = 0; k < WF_SG; ++k) {
                         float t;
@@ -425,7 +445,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
                 }
             }
             for (int i = n_typed; i < n_obj; ++i) {                  // whatever follows the typed runs in world order
-                const float4 lo = obj_lo(i), hi = obj_hi(i);
+                const float4 lo = obj_lo(s_obj, i), hi = obj_hi(s_obj, i);
                 const bool is_sphere = (__float_as_int(lo.w) & 3) == PTB_OBJ_SPHERE;
 #pragma unroll
                 for (int k = 0; k < WF_SG; ++k) {
@@ -503,14 +523,14 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
                 const int j = tid + (g + k) * WF_THREADS;
                 int c;
                 if (S.pix[j] < 0) c = CL_DEAD;
-                else if (S.depth[j] <= 0) c = CL_REGEN;
+                else if (S.depth[j] <= 0) c = PTB_MERGE_TERM_REGEN ? CL_TERM : CL_REGEN;
                 else if (MESH && S.trav[j] != 0) c = CL_CONT;
                 else if (bid[k] < 0) c = CL_TERM;
                 else if (MESH && (bid[k] & kTriBit)) c = (__float_as_int(__ldg(fp.bvh_tris + 3 * (bid[k] & ~kTriBit) + 1).w) >> 3) & 7;
                 else c = (s_obj[bid[k]].meta >> 3) & 7;
                 cls[g + k] = c;
                 S.best[j] = best[k]; S.bid[j] = bid[k];
-                if (STATS) { st[ST_LANE_TOTAL]++; if (c != CL_DEAD && c != CL_REGEN) { st[ST_LANE_ACTIVE]++; if (c != CL_CONT) st[ST_SEGMENTS]++; } }
+                if (STATS) { st[ST_LANE_TOTAL]++; if (c != CL_DEAD && S.depth[j] > 0) { st[ST_LANE_ACTIVE]++; if (c != CL_CONT) st[ST_SEGMENTS]++; } }
             }
         }
 
@@ -592,7 +612,7 @@ integrate_wf_kernel(const __grid_constant__ FrameParams fp) {
         const long long tc0 = clock64();
         const int c_lane0 = __shfl_sync(0xffffffffu, c, 0), c_lane31 = __shfl_sync(0xffffffffu, c, 31);
 #endif
-        path_shade<STATS, MESH>(S, fp, s_obj, s_mat, n_pix, j, c, st);
+        path_shade<STATS, MESH, BIG>(S, fp, c_scene, s_obj, s_mat, n_pix, j, c, st);
 #ifdef PTB_WF_TIMING
         if (lane == 0 && fp.stats && c_lane0 == c_lane31) {      // homogeneous chunks only
             atomicAdd(fp.stats + kStatsWords + 8 + 2 * c_lane0, (unsigned long long)(clock64() - tc0));

@@ -106,3 +106,135 @@ def render_rows_distributed(ctx, cfg_full, group=None):
     gathered = torch.empty((world * rows_max, W, 4), dtype=torch.uint8, device=dev)      # rank-major concatenation
     dist.all_gather_into_tensor(gathered, mine, group=group)
     return assemble_rows(list(gathered.view(world, rows_max, W, 4)), H)
+
+
+# ---- the fused exchange (default on GPUs): ONE kernel per rank does reduce-scatter + pixel epilogue + gather over NVLink peer
+# memory (ptb_peer_*, include/ptb200.h).  torch.distributed is the plumbing only: it carries the 64-byte CUDA IPC handles once
+# and provides the stream-ordered barriers (4-byte all-reduces) around the kernel.
+
+class _DevPtr:
+    """A raw device pointer dressed up for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr, "version": 3}
+
+
+class PeerGroup:
+    """One rank's end of the multi-process peer group: its fp32 sum buffer, rank 0's image, and the fused kernel."""
+
+    def __init__(self, ctx, max_width: int, max_height: int, group=None):
+        import ctypes as C
+
+        from . import _lib
+        self._L, self._ctx, self._group = _lib.lib(), ctx, group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.max_width, self.max_height = int(max_width), int(max_height)
+        h = C.c_void_p()
+        ctx._check(self._L.ptb_peer_create(ctx._h, self.rank, self.world, self.max_width, self.max_height, C.byref(h)))
+        self._h = h
+        dev = torch.device("cuda", ctx.device)
+        self._token = torch.zeros(1, dtype=torch.int32, device=dev)
+        if self.world > 1:
+            mine = (C.c_ubyte * 128)()
+            ctx._check(self._L.ptb_peer_handles(self._h, mine, C.byref(mine, 64)))
+            t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
+            allh = torch.empty(self.world * 128, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(allh, t, group=group)
+            allh = allh.cpu().numpy().reshape(self.world, 128)
+            accum = (C.c_ubyte * (64 * self.world))(*allh[:, :64].reshape(-1).tolist())
+            image = (C.c_ubyte * 64)(*allh[0, 64:].tolist())
+            ctx._check(self._L.ptb_peer_connect(self._h, accum, image))
+            dist.barrier(group=group)                      # nobody renders before every mapping exists
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            if self.world > 1 and dist.is_initialized():
+                torch.cuda.synchronize()
+                dist.barrier(group=self._group)            # no rank unmaps while another still reads its buffer
+            self._L.ptb_peer_destroy(h)
+
+    @property
+    def accum_ptr(self) -> int:
+        return int(self._L.ptb_peer_accum(self._h))
+
+    def accum_tensor(self, height: int, width: int) -> torch.Tensor:
+        return torch.as_tensor(_DevPtr(self.accum_ptr, (height, width, 3), "<f4"), device=torch.device("cuda", self._ctx.device))
+
+    def image_tensor(self, height: int, width: int):
+        """Rank 0: the assembled RGBA8 frame (a view of the peer image buffer); None on the other ranks."""
+        p = self._L.ptb_peer_image(self._h)
+        if not p:
+            return None
+        return torch.as_tensor(_DevPtr(int(p), (height, width, 4), "|u1"), device=torch.device("cuda", self._ctx.device))
+
+    def _barrier(self):
+        if self.world > 1:
+            dist.all_reduce(self._token, group=self._group)   # stream-ordered: completes when every rank's stream got here
+
+    def reduce_finalize(self, width: int, height: int, spp_total: int, stream: int = 0):
+        """Every rank's sums are complete on its stream -> barrier -> fused slice kernel -> barrier (rank 0 owns the image)."""
+        self._barrier()
+        self._ctx._check(self._L.ptb_peer_reduce_finalize(self._h, int(width), int(height), int(spp_total), stream))
+        self._barrier()
+
+
+def render_distributed_peer(ctx, cfg_full, peers: PeerGroup):
+    """Whole multi-GPU frame with the fused exchange: partition -> render into the peer buffer -> reduce_finalize.
+    Returns the CUDA uint8 (H, W, 4) image on rank 0 (a view of the peer image buffer), None elsewhere."""
+    from ._lib import PtbCfg
+    H, W = cfg_full.height, cfg_full.width
+    stream = torch.cuda.current_stream(torch.device("cuda", ctx.device)).cuda_stream
+    b, e = sample_range(cfg_full.samples_per_px, peers.rank, peers.world)
+    if e > b:
+        cfg = PtbCfg(W, H, cfg_full.samples_per_px, cfg_full.max_depth, cfg_full.seed, b, e - b, cfg_full.flags, 0, 0)
+        ctx.render_accum_device(cfg, peers.accum_ptr, stream)
+    else:
+        peers.accum_tensor(H, W).zero_()
+    peers.reduce_finalize(W, H, cfg_full.samples_per_px, stream)
+    return peers.image_tensor(H, W)
+
+
+# ---- the same data movement with NCCL collectives only (reduce_scatter -> per-rank epilogue of its slice -> gather of RGBA8):
+# the library-call baseline of the fused kernel above, and the path for groups without CUDA IPC (e.g. ranks on several hosts).
+
+def slice_pixels(n_pix: int, world: int) -> int:
+    """Pixels per rank slice: ceil(n_pix / world) rounded up to a multiple of 4 (the slices tile [0, world * chunk) >= n_pix)."""
+    return ((n_pix + world - 1) // world + 3) // 4 * 4
+
+
+def exchange_scatter(accum_padded: torch.Tensor, rgba_padded, n_pix: int, finalize, group=None):
+    """reduce_scatter of the padded sums -> finalize(slice sums (chunk, 3)) -> (chunk, 4) uint8 on every rank -> gather into rank 0's
+    rgba_padded (world * chunk, 4).  Returns rank 0's first n_pix pixels (a view), None elsewhere."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    chunk = slice_pixels(n_pix, world)
+    assert accum_padded.shape == (world * chunk, 3)
+    if world == 1:
+        return finalize(accum_padded)[:n_pix]
+    mine = torch.empty((chunk, 3), dtype=accum_padded.dtype, device=accum_padded.device)
+    dist.reduce_scatter_tensor(mine, accum_padded, op=dist.ReduceOp.SUM, group=group)
+    my_rgba = finalize(mine)
+    dist.gather(my_rgba, list(rgba_padded.view(world, chunk, 4)) if rank == 0 else None, dst=0, group=group)
+    return rgba_padded[:n_pix] if rank == 0 else None
+
+
+def render_distributed_scatter(ctx, cfg_full, accum_padded: torch.Tensor, rgba_padded: torch.Tensor | None, group=None):
+    """accum_padded: CUDA fp32 (world * chunk, 3) with chunk = slice_pixels(H * W, world), zero beyond H * W; rgba_padded: rank 0's
+    CUDA uint8 (world * chunk, 4).  Returns rank 0's (H, W, 4) view of rgba_padded, None elsewhere."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    H, W = cfg_full.height, cfg_full.width
+    n_pix = H * W
+    dev = torch.device("cuda", ctx.device)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    render_partition(ctx, cfg_full, rank, world, accum_padded[:n_pix].view(H, W, 3), stream)
+
+    def finalize(sums):
+        out = torch.empty((sums.shape[0], 4), dtype=torch.uint8, device=dev)
+        ctx.finalize_device(sums.data_ptr(), sums.shape[0], 1, cfg_full.samples_per_px, out.data_ptr(), stream)
+        return out
+
+    img = exchange_scatter(accum_padded, rgba_padded, n_pix, finalize, group)
+    return img.view(H, W, 4) if img is not None else None

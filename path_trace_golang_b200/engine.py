@@ -90,11 +90,8 @@ class Context:
 
     @staticmethod
     def cfg(width, height, spp, max_depth, seed=1, sample_begin=0, sample_count=0, stats=False, megakernel=False,
-            wavequeue=None, row_offset=0, row_step=0) -> PtbCfg:
-        import os
-        if wavequeue is None:
-            wavequeue = bool(os.environ.get("PTB_WAVEQUEUE"))
-        flags = (PTB_FLAG_STATS if stats else 0) | (PTB_FLAG_MEGAKERNEL if megakernel else 0) | (4 if wavequeue and not megakernel else 0)
+            row_offset=0, row_step=0) -> PtbCfg:
+        flags = (PTB_FLAG_STATS if stats else 0) | (PTB_FLAG_MEGAKERNEL if megakernel else 0)
         return PtbCfg(int(width), int(height), int(spp), int(max_depth), int(seed) & 0xFFFFFFFF, int(sample_begin),
                       int(sample_count), flags, int(row_offset), int(row_step))
 
@@ -119,6 +116,29 @@ class Context:
         self._check(self._L.ptb_render_accum(self._h, C.byref(cfg), out.ctypes.data))
         return out
 
+    def render_resume(self, cfg: PtbCfg, sums: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """ptb_render_resume: continue the fp32 sums (H, W, 3) over cfg's sample range, in place; returns them."""
+        assert sums.dtype == np.float32 and sums.flags.c_contiguous and sums.shape == (cfg.height, cfg.width, 3)
+        if out is not None:
+            assert out.dtype == np.uint8 and out.shape == (cfg.height, cfg.width, 4) and out.strides[1] == 4
+        self._check(self._L.ptb_render_resume(self._h, C.byref(cfg), sums.ctypes.data, out.ctypes.data if out is not None else None,
+                                              out.strides[0] if out is not None else 0))
+        return sums
+
+    def finalize_host(self, sums: np.ndarray, spp_total: int) -> np.ndarray:
+        """ptb_finalize_host: pixel epilogue (on the device) of host fp32 sums (H, W, 3) -> RGBA8 (H, W, 4)."""
+        sums = np.ascontiguousarray(sums, dtype=np.float32)
+        out = np.empty(sums.shape[:2] + (4,), dtype=np.uint8)
+        self._check(self._L.ptb_finalize_host(self._h, sums.ctypes.data, sums.shape[1], sums.shape[0], int(spp_total), out.ctypes.data, out.strides[0]))
+        return out
+
+    def pin(self, arr: np.ndarray):
+        """ptb_host_buffer_pin: page-lock a caller-owned image so that renders copy straight into it."""
+        self._check(self._L.ptb_host_buffer_pin(self._h, arr.ctypes.data, arr.nbytes))
+
+    def unpin(self, arr: np.ndarray):
+        self._check(self._L.ptb_host_buffer_unpin(self._h, arr.ctypes.data))
+
     def render_accum_device(self, cfg: PtbCfg, d_ptr: int, stream: int = 0):
         self._check(self._L.ptb_render_accum_device(self._h, C.byref(cfg), C.c_void_p(d_ptr), C.c_void_p(stream)))
 
@@ -140,6 +160,10 @@ class Context:
         s = PtbStats()
         self._check(self._L.ptb_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def last_kernel(self) -> str:
+        """Symbol of the integrator instantiation the last render launched (as ncu prints it)."""
+        return self._L.ptb_last_kernel(self._h).decode()
 
     def bvh_info(self) -> dict:
         """EXTENSION: the BVH ptb_scene_upload built over the mesh triangles (zeros without meshes)."""
@@ -224,6 +248,22 @@ def RenderInto(sc: Scene, cfg: RenderConfig, img: np.ndarray, progress=None, *, 
                                   C.cast(cb, C.c_void_p) if cb else None, None)
     if rc:
         raise PtbError(rc, L.ptb_host_last_error().decode())
+
+
+def RenderCheckpointed(sc: Scene, cfg: RenderConfig, img: np.ndarray, path, samples_per_call: int, max_calls: int = 0, progress=None, *,
+                       ctx: Context | None = None, seed: int = 1) -> int:
+    """RenderInto with an accumulation checkpoint at `path` (ptb_engine_render_checkpointed): continues a matching checkpoint,
+    rewrites it after every call of samples_per_call samples; max_calls > 0 stops early.  Returns the samples per pixel done."""
+    ctx = ctx or default_context()
+    L = _lib.lib()
+    cb = PROGRESS_FN(lambda _u: progress()) if progress is not None else None
+    done = C.c_int32()
+    rc = L.ptb_engine_render_checkpointed(ctx._h, sc._h, cfg.Width, cfg.Height, cfg.SamplesPerPx, cfg.MaxDepth, int(seed) & 0xFFFFFFFF,
+                                          img.ctypes.data, img.strides[0], img.shape[1], img.shape[0], str(path).encode(),
+                                          int(samples_per_call), int(max_calls), C.byref(done), C.cast(cb, C.c_void_p) if cb else None, None)
+    if rc:
+        raise PtbError(rc, L.ptb_host_last_error().decode())
+    return done.value
 
 
 def Render(sc: Scene, cfg: RenderConfig, **kw) -> np.ndarray:

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_abi_version():
     from path_trace_golang_b200 import _lib
-    assert _lib.lib().ptb_abi_version() == 4
+    assert _lib.lib().ptb_abi_version() == 5
 
 
 def test_create_fails_loudly_without_gpu():
