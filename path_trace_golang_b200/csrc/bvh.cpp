@@ -1,4 +1,5 @@
-// bvh.cpp — binned-SAH BVH2 builder (host, C++, multi-threaded over subtrees).  See bvh.h for the layout.
+// bvh.cpp — binned-SAH BVH builder (host, C++, multi-threaded over subtrees): a binary tree by binned SAH, collapsed to the
+// 4-wide nodes of bvh.h when it is flattened.
 #include "bvh.h"
 
 #include <algorithm>
@@ -143,15 +144,16 @@ void build_bvh(const BvhBuildInput& in, BvhBuildOutput& out, int threads) {
         o.q[4] = v[3] - v[0]; o.q[5] = v[4] - v[1]; o.q[6] = v[5] - v[2]; o.q[7] = i2f(in.tri_meta[t]);
         o.q[8] = v[6] - v[0]; o.q[9] = v[7] - v[1]; o.q[10] = v[8] - v[2]; o.q[11] = i2f(in.tri_world[t]);
     }
-    struct Item { const BuildNode* n; int32_t slot; int depth; };
+    struct Item { const BuildNode* n; int32_t slot; int depth; int pending; };
     std::vector<Item> stack;
-    out.nodes.reserve((size_t)(n / 2 + 16));
+    out.nodes.reserve((size_t)(n / 4 + 16));
     const double root_area = std::max(root->box.area(), 1e-30);
-    auto child_link = [&](const BuildNode* c, int depth) -> int32_t {
+    out.max_stack = 0;
+    auto child_link = [&](const BuildNode* c, int depth, int pending) -> int32_t {
         if (c->child[0]) {                                   // inner: allocate its node now, fill it later
             out.nodes.emplace_back();
             int32_t id = (int32_t)out.nodes.size() - 1;
-            stack.push_back({c, id, depth});
+            stack.push_back({c, id, depth, pending});
             return id;
         }
         out.sah_cost += c->box.area() / root_area * (double)c->count;
@@ -167,28 +169,50 @@ void build_bvh(const BvhBuildInput& in, BvhBuildOutput& out, int threads) {
             const double need = std::max(hi - (double)c[k], (double)c[k] - lo);
             h[k] = std::nextafter((float)need, INFINITY);
         }
-        float* q = nd.q + (which == 0 ? 0 : 6);
+        float* q = nd.q + 6 * which;
         q[0] = c[0]; q[1] = c[1]; q[2] = c[2]; q[3] = h[0]; q[4] = h[1]; q[5] = h[2];
+    };
+    // the (up to) kBvhWidth children of the wide node made from binary node b: its two children, then repeatedly the inner
+    // one with the largest box replaced by ITS two children
+    auto wide_children = [&](const BuildNode* b, const BuildNode* kids[kBvhWidth]) -> int {
+        int nk = 2;
+        kids[0] = b->child[0].get(); kids[1] = b->child[1].get();
+        while (nk < kBvhWidth) {
+            int pick = -1;
+            double best = -1.0;
+            for (int k = 0; k < nk; k++) if (kids[k]->child[0] && kids[k]->box.area() > best) { best = kids[k]->box.area(); pick = k; }
+            if (pick < 0) break;
+            const BuildNode* p = kids[pick];
+            kids[pick] = p->child[0].get();
+            kids[nk++] = p->child[1].get();
+        }
+        return nk;
     };
     out.nodes.emplace_back();
     if (!root->child[0]) {                                   // <= kMaxLeafTris triangles: root with one leaf child
         BvhNode& nd = out.nodes[0];
         std::memset(&nd, 0, sizeof nd);
-        put_box(nd, 0, &root->box); put_box(nd, 1, nullptr);
-        nd.q[12] = i2f(~(int32_t)((root->first << 2) | (root->count - 1))); nd.q[13] = i2f(kEmptyLeaf);
+        put_box(nd, 0, &root->box);
+        nd.q[24] = i2f(~(int32_t)((root->first << 2) | (root->count - 1)));
+        for (int k = 1; k < kBvhWidth; k++) { put_box(nd, k, nullptr); nd.q[24 + k] = i2f(kEmptyLeaf); }
         out.max_depth = 1;
     } else {
-        stack.push_back({root.get(), 0, 1});
+        stack.push_back({root.get(), 0, 1, 0});
         while (!stack.empty()) {
             Item it = stack.back(); stack.pop_back();
             out.max_depth = std::max(out.max_depth, it.depth);
             out.sah_cost += it.n->box.area() / root_area;
-            const int32_t c0 = child_link(it.n->child[0].get(), it.depth + 1);
-            const int32_t c1 = child_link(it.n->child[1].get(), it.depth + 1);
+            const BuildNode* kids[kBvhWidth];
+            const int nk = wide_children(it.n, kids);
+            out.max_stack = std::max(out.max_stack, it.pending + nk - 1);
+            int32_t link[kBvhWidth];
+            for (int k = 0; k < nk; k++) link[k] = child_link(kids[k], it.depth + 1, it.pending + nk - 1);
             BvhNode& nd = out.nodes[it.slot];                // (re-fetch: emplace_back may have moved the array)
             std::memset(&nd, 0, sizeof nd);
-            put_box(nd, 0, &it.n->child[0]->box); put_box(nd, 1, &it.n->child[1]->box);
-            nd.q[12] = i2f(c0); nd.q[13] = i2f(c1);
+            for (int k = 0; k < kBvhWidth; k++) {
+                put_box(nd, k, k < nk ? &kids[k]->box : nullptr);
+                nd.q[24 + k] = i2f(k < nk ? link[k] : kEmptyLeaf);
+            }
         }
     }
     out.build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();

@@ -1,6 +1,6 @@
 // bvh.cuh — binary32 BVH traversal for the integrators (EXTENSION: triangle meshes; layout in bvh.h).
-// Stack-based while-while traversal: one 64-byte node fetch (4 x 16-byte read-only loads) decides both children,
-// the nearer child is followed first and the farther one pushed.  Triangles: Moeller-Trumbore, two-sided,
+// Stack-based while-while traversal of the 4-wide tree: one 128-byte node fetch (7 x 16-byte read-only loads) decides four
+// children; they are sorted by entry distance, the nearest is followed, the others pushed farthest first.  Triangles: Moeller-Trumbore, two-sided,
 // t in [tmin, best); among triangles of equal t the lowest triangle id wins (so the result does not depend on the
 // traversal order and equals a brute-force scan).
 #pragma once
@@ -53,28 +53,45 @@ __device__ __forceinline__ int trav_round(const float4* __restrict__ nodes, cons
     int cur = T.cur, sp = T.sp;
     while (cur >= 0 && max_nodes > 0 && T.budget > 0) {
         --max_nodes; --T.budget;
-        const float4 q0 = __ldg(nodes + 4 * cur), q1 = __ldg(nodes + 4 * cur + 1), q2 = __ldg(nodes + 4 * cur + 2),
-                     q3 = __ldg(nodes + 4 * cur + 3);
+        const float4* nd = nodes + 8 * cur;                 // 128-byte node: 7 read-only 16-byte loads (the 8th quad is padding)
+        const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3), q4 = __ldg(nd + 4), q5 = __ldg(nd + 5),
+                     q6 = __ldg(nd + 6);
         if (STATS) st[ST_BVH_NODES]++;
-        // children as (centre, half extent): near/far of an axis are (c - o)/d -+ h/|d| (see hit_box)
-        float cx = fmaf(q0.x, r.inv.x, -r.oi.x), cy = fmaf(q0.y, r.inv.y, -r.oi.y), cz = fmaf(q0.z, r.inv.z, -r.oi.z);
-        const float n0 = fmaxf(fmaxf(fmaxf(fmaf(-q0.w, r.ainv.x, cx), fmaf(-q1.x, r.ainv.y, cy)), fmaf(-q1.y, r.ainv.z, cz)), tmin);
-        const float f0 = fminf(fminf(fminf(fmaf(q0.w, r.ainv.x, cx), fmaf(q1.x, r.ainv.y, cy)), fmaf(q1.y, r.ainv.z, cz)), best);
-        cx = fmaf(q1.z, r.inv.x, -r.oi.x); cy = fmaf(q1.w, r.inv.y, -r.oi.y); cz = fmaf(q2.x, r.inv.z, -r.oi.z);
-        const float n1 = fmaxf(fmaxf(fmaxf(fmaf(-q2.y, r.ainv.x, cx), fmaf(-q2.z, r.ainv.y, cy)), fmaf(-q2.w, r.ainv.z, cz)), tmin);
-        const float f1 = fminf(fminf(fminf(fmaf(q2.y, r.ainv.x, cx), fmaf(q2.z, r.ainv.y, cy)), fmaf(q2.w, r.ainv.z, cz)), best);
-        const bool h0 = f0 >= n0, h1 = f1 >= n1;
-        const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-        if (h0 && h1) {
-            const bool first0 = n0 <= n1;
-            // the builder bounds the depth (bvh.cpp: depth + log2(count) <= 35 < kTravStack), so the stack cannot overflow;
-            // should that bound ever regress, the dropped subtree is counted (ptb_stats.bvh_stack_overflows, STATS builds)
-            if (sp < kTravStack) T.stack[sp++] = first0 ? c1 : c0;
-            else if (STATS) st[ST_BVH_STACK_OVERFLOW]++;
-            cur = first0 ? c0 : c1;
-        } else if (h0) cur = c0;
-        else if (h1) cur = c1;
-        else cur = sp ? T.stack[--sp] : kTravDone;
+        // children as (centre, half extent): near/far of an axis are (c - o)/d -+ h/|d| (see hit_box); a child that is missed
+        // (or unused: h = -1) gets the distance +inf
+        float d[4];
+        int l[4] = {__float_as_int(q6.x), __float_as_int(q6.y), __float_as_int(q6.z), __float_as_int(q6.w)};
+        {
+            float cx = fmaf(q0.x, r.inv.x, -r.oi.x), cy = fmaf(q0.y, r.inv.y, -r.oi.y), cz = fmaf(q0.z, r.inv.z, -r.oi.z);
+            float n = fmaxf(fmaxf(fmaxf(fmaf(-q0.w, r.ainv.x, cx), fmaf(-q1.x, r.ainv.y, cy)), fmaf(-q1.y, r.ainv.z, cz)), tmin);
+            float f = fminf(fminf(fminf(fmaf(q0.w, r.ainv.x, cx), fmaf(q1.x, r.ainv.y, cy)), fmaf(q1.y, r.ainv.z, cz)), best);
+            d[0] = f >= n ? n : __int_as_float(0x7f800000);
+            cx = fmaf(q1.z, r.inv.x, -r.oi.x); cy = fmaf(q1.w, r.inv.y, -r.oi.y); cz = fmaf(q2.x, r.inv.z, -r.oi.z);
+            n = fmaxf(fmaxf(fmaxf(fmaf(-q2.y, r.ainv.x, cx), fmaf(-q2.z, r.ainv.y, cy)), fmaf(-q2.w, r.ainv.z, cz)), tmin);
+            f = fminf(fminf(fminf(fmaf(q2.y, r.ainv.x, cx), fmaf(q2.z, r.ainv.y, cy)), fmaf(q2.w, r.ainv.z, cz)), best);
+            d[1] = f >= n ? n : __int_as_float(0x7f800000);
+            cx = fmaf(q3.x, r.inv.x, -r.oi.x); cy = fmaf(q3.y, r.inv.y, -r.oi.y); cz = fmaf(q3.z, r.inv.z, -r.oi.z);
+            n = fmaxf(fmaxf(fmaxf(fmaf(-q3.w, r.ainv.x, cx), fmaf(-q4.x, r.ainv.y, cy)), fmaf(-q4.y, r.ainv.z, cz)), tmin);
+            f = fminf(fminf(fminf(fmaf(q3.w, r.ainv.x, cx), fmaf(q4.x, r.ainv.y, cy)), fmaf(q4.y, r.ainv.z, cz)), best);
+            d[2] = f >= n ? n : __int_as_float(0x7f800000);
+            cx = fmaf(q4.z, r.inv.x, -r.oi.x); cy = fmaf(q4.w, r.inv.y, -r.oi.y); cz = fmaf(q5.x, r.inv.z, -r.oi.z);
+            n = fmaxf(fmaxf(fmaxf(fmaf(-q5.y, r.ainv.x, cx), fmaf(-q5.z, r.ainv.y, cy)), fmaf(-q5.w, r.ainv.z, cz)), tmin);
+            f = fminf(fminf(fminf(fmaf(q5.y, r.ainv.x, cx), fmaf(q5.z, r.ainv.y, cy)), fmaf(q5.w, r.ainv.z, cz)), best);
+            d[3] = f >= n ? n : __int_as_float(0x7f800000);
+        }
+        // sort the four (distance, link) pairs by distance (5 compare-exchanges): the nearest child is visited next, the others are
+        // pushed farthest first, so the nearer ones are popped — and shrink `best` — before the farther ones are looked at
+#define PTB_CE(a, b) { const bool sw = d[b] < d[a]; const float da = sw ? d[b] : d[a], db = sw ? d[a] : d[b]; \
+                       const int la = sw ? l[b] : l[a], lb = sw ? l[a] : l[b]; d[a] = da; d[b] = db; l[a] = la; l[b] = lb; }
+        PTB_CE(0, 1) PTB_CE(2, 3) PTB_CE(0, 2) PTB_CE(1, 3) PTB_CE(1, 2)
+#undef PTB_CE
+        const float inf = __int_as_float(0x7f800000);
+        // the builder bounds the pending entries (BvhBuildOutput::max_stack < kTravStack, checked at upload), so the stack
+        // cannot overflow; should that bound ever regress, dropped subtrees are counted (ptb_stats.bvh_stack_overflows, STATS builds)
+        if (d[3] < inf) { if (sp < kTravStack) T.stack[sp++] = l[3]; else if (STATS) st[ST_BVH_STACK_OVERFLOW]++; }
+        if (d[2] < inf) { if (sp < kTravStack) T.stack[sp++] = l[2]; else if (STATS) st[ST_BVH_STACK_OVERFLOW]++; }
+        if (d[1] < inf) { if (sp < kTravStack) T.stack[sp++] = l[1]; else if (STATS) st[ST_BVH_STACK_OVERFLOW]++; }
+        cur = d[0] < inf ? l[0] : (sp ? T.stack[--sp] : kTravDone);
     }
     if (cur < 0 && cur != kTravDone) {
         const int link = ~cur, first = link >> 2, cnt = (link & 3) + 1;

@@ -2,12 +2,16 @@
 // north-star: "internal/scene gains a BVH builder that emits a flattened, cache-line-aligned node array").
 //
 // Layout (device, global memory, fetched with 16-byte loads):
-//   node  = 64 bytes = 4 x float4, cache-line aligned:  both children's boxes + both child links, so ONE node fetch
-//           decides both children ("Aila-Laine" BVH2 layout)
-//             boxes as (centre c, half extent h), the form whose slab test needs no per-axis min/max (integrator.cu hit_box):
-//             q0 = (c0.x, c0.y, c0.z, h0.x)   q1 = (h0.y, h0.z, c1.x, c1.y)   q2 = (c1.z, h1.x, h1.y, h1.z)
-//             q3 = (bits l0, bits l1, 0, 0)   link l >= 0: inner node index;  l < 0: leaf, ~l = first_tri << 2 | (count - 1)
-//           an empty child has h = -1 (never hit) and link kEmptyLeaf
+//   node  = 128 bytes = 8 x float4, aligned to the 128-byte L2 line: a 4-WIDE node — the boxes of up to four children and
+//           their links, so ONE node fetch decides four subtrees and a ray needs about half the DEPENDENT fetches of a binary
+//           tree (the traversal is bound by the latency of those fetches).  Built by collapsing the binned-SAH
+//           binary tree: a node adopts its grandchildren, largest box first, until it has four children.
+//             floats 6k .. 6k+5  (k = 0..3): child k's box as (centre c.xyz, half extent h.xyz) — the form whose slab test
+//                                            needs no per-axis min/max (integrator.cu hit_box)
+//             floats 24 .. 27              : bits of link k;  link >= 0: inner node index;  link < 0: leaf,
+//                                            ~link = first_tri << 2 | (count - 1)
+//             floats 28 .. 31              : 0 (pad)
+//           an unused child has h = -1 (never hit) and link kEmptyLeaf
 //   tri   = 48 bytes = 3 x float4, in leaf order:  (v0.xyz, bits tri_id)  (e1.xyz, bits meta)  (e2.xyz, bits world_idx)
 //           e1 = v1 - v0, e2 = v2 - v0 (binary32);  meta = the DevObj::meta of the mesh's material
 // Boxes are padded by 1e-5 x (largest absolute coordinate of the scene, at least 1) so that the fp32 slab test with
@@ -18,7 +22,8 @@
 
 namespace ptb {
 
-struct alignas(64) BvhNode { float q[16]; };
+constexpr int kBvhWidth = 4;
+struct alignas(128) BvhNode { float q[32]; };
 struct alignas(16) BvhTri { float q[12]; };
 constexpr int32_t kEmptyLeaf = 0x7fffffff;   // never followed (its box has a negative half extent)
 constexpr int kMaxLeafTris = 4;
@@ -32,7 +37,8 @@ struct BvhBuildInput {
 struct BvhBuildOutput {
     std::vector<BvhNode> nodes;  // nodes[0] = root (always an inner node when n_tri > 0)
     std::vector<BvhTri> tris;    // leaf order
-    int max_depth = 0;
+    int max_depth = 0;           // depth of the 4-wide tree (root = 1)
+    int max_stack = 0;           // entries a depth-first traversal can have pending: sum over a root-to-leaf path of (children - 1)
     double sah_cost = 0;         // sum over inner nodes of area(node)/area(root) (+ leaves weighted by count)
     double build_ms = 0;
 };

@@ -94,6 +94,16 @@ struct Rng {
 struct F3 { float x, y, z; };
 __device__ __forceinline__ F3 f3(float x, float y, float z) { return F3{x, y, z}; }
 __device__ __forceinline__ float dot3(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }   // math.go:19
+// unit vector by one reciprocal square root (callers whose input cannot be the zero vector)
+__device__ __forceinline__ F3 unit3_nz(F3 a) {
+#if PTB_FAST_MATH
+    float inv; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(inv) : "f"(dot3(a, a)));
+    return f3(a.x * inv, a.y * inv, a.z * inv);
+#else
+    const float inv = 1.0f / sqrtf(dot3(a, a));
+    return f3(a.x * inv, a.y * inv, a.z * inv);
+#endif
+}
 __device__ __forceinline__ F3 unit3(F3 a) {                                                       // math.go:31-37, 14-17
     float l = sqrt_(dot3(a, a));
     if (l == 0.0f) return a;
@@ -117,7 +127,7 @@ __device__ __forceinline__ F3 cosine_direction(F3 n, float r1, float r2) {
     float st = sqrt_(1.0f - r2);
     // v = unit(n x helper), u = v x n with helper = (0,1,0) if |n.x| > 0.9 else (1,0,0)
     F3 v = (fabsf(n.x) > 0.9f) ? f3(-n.z, 0.0f, n.x) : f3(0.0f, n.z, -n.y);
-    v = unit3(v);
+    v = unit3_nz(v);                   // n x helper is never zero: the helper axis is chosen away from the unit vector n
     F3 u = f3(v.y * n.z - v.z * n.y, v.z * n.x - v.x * n.z, v.x * n.y - v.y * n.x);
     float sp, cp;
     sincos_(phi, &sp, &cp);
@@ -128,18 +138,21 @@ __device__ __forceinline__ F3 cosine_direction(F3 n, float r1, float r2) {
 // Per-ray constants of the closest-hit tests: a = d.d (objects.go:43), inv = 1/d (objects.go:149-161),
 // oi = o*inv (so a slab distance (b - o)*inv is one FFMA: b*inv - oi), inv_a = 1/a (the divisions of
 // objects.go:55,57 become multiplications).
-struct RayK { F3 o, d, inv, oi, ainv; float a, inv_a; };
-__device__ __forceinline__ RayK make_ray(F3 o, F3 d) {
-    RayK r;
-    // A direction component that is exactly 0 would make the (centre, half extent) slab form below compute inf - inf = NaN
-    // and silently drop that axis from the box test (the reference misses such a box when the origin is outside the
-    // slab: tNear, tFar = -+inf, objects.go:149-165).  Such components (about 2^-24 of all) become +-1e-30: 1/d = +-1e30
-    // stays finite, every slab distance keeps its sign, hit points and normals are unchanged in binary32.
+// A direction component that is exactly 0 would make the (centre, half extent) slab form of hit_box compute inf - inf = NaN and
+// silently drop that axis from the box test (the reference misses such a box when the origin is outside the slab: tNear, tFar
+// = -+inf, objects.go:149-165).  Such components (about 2^-24 of all) become +-1e-30 WHERE A DIRECTION IS MADE (camera ray,
+// scatter): 1/d = +-1e30 stays finite, every slab distance keeps its sign, hit points and normals are unchanged in binary32 —
+// and the closest-hit scan itself stays free of the check.
+__device__ __forceinline__ void sanitize_dir(F3& d) {
     if (fminf(fminf(fabsf(d.x), fabsf(d.y)), fabsf(d.z)) == 0.0f) {
         if (d.x == 0.0f) d.x = copysignf(1e-30f, d.x);
         if (d.y == 0.0f) d.y = copysignf(1e-30f, d.y);
         if (d.z == 0.0f) d.z = copysignf(1e-30f, d.z);
     }
+}
+struct RayK { F3 o, d, inv, oi, ainv; float a, inv_a; };
+__device__ __forceinline__ RayK make_ray(F3 o, F3 d) {
+    RayK r;
     r.o = o; r.d = d;
     r.a = d.x * d.x + d.y * d.y + d.z * d.z;
     r.inv = f3(rcp_(d.x), rcp_(d.y), rcp_(d.z));
@@ -349,6 +362,7 @@ integrate_kernel(const __grid_constant__ KernelArgs ka) {
             org = f3(org.x + off.x, org.y + off.y, org.z + off.z);
             dir = f3(dir.x - off.x, dir.y - off.y, dir.z - off.z);
         }
+        sanitize_dir(dir);
         o = org; d = dir;
         beta = f3(1.0f, 1.0f, 1.0f);
         L = f3(0.0f, 0.0f, 0.0f);
@@ -465,6 +479,7 @@ integrate_kernel(const __grid_constant__ KernelArgs ka) {
                         const float par = -sqrt_(fabsf(1.0f - (qx * qx + qy * qy + qz * qz)));
                         sd = f3(qx + n.x * par, qy + n.y * par, qz + n.z * par);
                     }
+                    sanitize_dir(sd);
                     if (front) {                              // exit search, renderer.go:316-371
                         if (STATS) st[ST_EXIT_SCANS]++;
                         const RayK er = make_ray(p, sd);
@@ -519,6 +534,7 @@ integrate_kernel(const __grid_constant__ KernelArgs ka) {
                     rng.ctr += used;
                     if (!done) {                              // renderer.go:398-403
                         beta.x *= att.x; beta.y *= att.y; beta.z *= att.z;
+                        sanitize_dir(sd);
                         o = so; d = sd;
                         if (--depth <= 0) {                   // renderer.go:287-289
                             done = true;

@@ -81,15 +81,22 @@ __device__ void bvh_closest64(const float4* __restrict__ nodes, const float4* __
     int sp = 0, cur = 0, best_tri = -1;
     for (;;) {
         if (cur >= 0) {
-            const float4 q0 = __ldg(nodes + 4 * cur), q1 = __ldg(nodes + 4 * cur + 1), q2 = __ldg(nodes + 4 * cur + 2), q3 = __ldg(nodes + 4 * cur + 3);
-            // nodes store (centre, half extent) in binary32; c -+ h is exact in binary64
-            const double lo0[3] = {(double)q0.x - q0.w, (double)q0.y - q1.x, (double)q0.z - q1.y}, hi0[3] = {(double)q0.x + q0.w, (double)q0.y + q1.x, (double)q0.z + q1.y};
-            const double lo1[3] = {(double)q1.z - q2.y, (double)q1.w - q2.z, (double)q2.x - q2.w}, hi1[3] = {(double)q1.z + q2.y, (double)q1.w + q2.z, (double)q2.x + q2.w};
-            const bool h0 = slab64(lo0, hi0, o, d, tMin, closest), h1 = slab64(lo1, hi1, o, d, tMin, closest);
-            const int c0 = __float_as_int(q3.x), c1 = __float_as_int(q3.y);
-            if (h0 && h1) { if (sp < 48) stack[sp++] = c1; cur = c0; }
-            else if (h0) cur = c0;
-            else if (h1) cur = c1;
+            // 4-wide node (bvh.h): floats 6k..6k+5 = child k's (centre, half extent) in binary32 — c -+ h is exact in binary64 —
+            // floats 24..27 = links.  The result does not depend on the visiting order: every hit child is pushed.
+            float q[28];
+#pragma unroll
+            for (int v = 0; v < 7; ++v) { const float4 w = __ldg(nodes + 8 * cur + v); q[4 * v] = w.x; q[4 * v + 1] = w.y; q[4 * v + 2] = w.z; q[4 * v + 3] = w.w; }
+            int next = 0x7fffffff;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float* b = q + 6 * k;
+                const double lo[3] = {(double)b[0] - b[3], (double)b[1] - b[4], (double)b[2] - b[5]}, hi[3] = {(double)b[0] + b[3], (double)b[1] + b[4], (double)b[2] + b[5]};
+                if (b[3] < 0.0f || !slab64(lo, hi, o, d, tMin, closest)) continue;
+                const int link = __float_as_int(q[24 + k]);
+                if (next == 0x7fffffff) next = link;
+                else if (sp < 48) stack[sp++] = link;
+            }
+            if (next != 0x7fffffff) cur = next;
             else { if (sp == 0) break; cur = stack[--sp]; }
         } else {
             const int link = ~cur, first = link >> 2, cnt = (link & 3) + 1;

@@ -48,6 +48,9 @@ constexpr int WF_CHUNKS = WF_SLOTS / 32;
 // CL_DIEL..CL_SPEC match the class bits the host writes into DevObj::meta (api.cu).
 // Measured chunk costs on C3 (cycles, -DPTB_WF_TIMING): DIEL 5500, TERM 3450, REGEN 2740, DIFFUSE 2210, SPEC 1630.
 // CL_CONT (MESH only): the slot's BVH traversal ran out of its per-iteration step budget and continues next iteration.
+#ifndef PTB_WF_DYNAMIC
+#define PTB_WF_DYNAMIC 1              // SHADE phase: dynamic (1) or static serpentine (0) assignment of chunks to warps
+#endif
 #ifndef PTB_MERGE_TERM_REGEN
 #define PTB_MERGE_TERM_REGEN 1        // sort slots that only need a new camera ray together with the terminating ones (one class boundary less)
 #endif
@@ -71,6 +74,7 @@ struct WfState : SlotState<WF_SLOTS> {
     alignas(4) unsigned short cnt[CL_COUNT * WF_WARPS];
     unsigned char trav[WF_SLOTS];      // MESH: 1 = the slot's traversal is suspended (state in FrameParams::trav_scratch)
     int n_list, next_chunk;            // MESH: compacted list of slots to traverse (in perm[]) and its chunk dispenser
+    int shade_next;                    // PTB_WF_DYNAMIC: next unassigned 32-slot chunk of the SHADE phase
 };
 
 // Finish the slot's current sample and give it its next camera ray: next sample of the same pixel, or — when the
@@ -135,6 +139,7 @@ __device__ __forceinline__ void path_regen(SS& S, const FrameParams& fp, const S
         org = f3(org.x + off.x, org.y + off.y, org.z + off.z);
         dir = f3(dir.x - off.x, dir.y - off.y, dir.z - off.z);
     }
+    sanitize_dir(dir);
     S.ox[j] = org.x; S.oy[j] = org.y; S.oz[j] = org.z;
     S.dx[j] = dir.x; S.dy[j] = dir.y; S.dz[j] = dir.z;
     S.bx[j] = 1.0f; S.by[j] = 1.0f; S.bz[j] = 1.0f;
@@ -181,12 +186,18 @@ __device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const S
         int depth = S.depth[j];
 
         uint32_t used = 0u;                               // draws consumed by this bounce (classes are warp-coherent: draw lazily)
-        const float a = rd.x * rd.x + rd.y * rd.y + rd.z * rd.z;
-        const float len = sqrt_(a);
-        const float il = rcp_(len);
-        const F3 ud = f3(rd.x * il, rd.y * il, rd.z * il);
-        const float udn = ud.x * n.x + ud.y * n.y + ud.z * n.z;
-        const F3 refl = f3(ud.x - n.x * 2.0f * udn, ud.y - n.y * 2.0f * udn, ud.z - n.z * 2.0f * udn);   // math.go:39-46
+        // unit incoming direction and its mirror image (math.go:39-46): every material but lambert needs them (a chunk of
+        // lambert hits — most diffuse chunks — skips the block)
+        float len = 1.0f, udn = 0.0f;
+        F3 ud = rd, refl = rd;
+        if (m.type != PTB_MAT_LAMBERT) {
+            const float a = rd.x * rd.x + rd.y * rd.y + rd.z * rd.z;
+            len = sqrt_(a);
+            const float il = rcp_(len);
+            ud = f3(rd.x * il, rd.y * il, rd.z * il);
+            udn = ud.x * n.x + ud.y * n.y + ud.z * n.z;
+            refl = f3(ud.x - n.x * 2.0f * udn, ud.y - n.y * 2.0f * udn, ud.z - n.z * 2.0f * udn);
+        }
 
         F3 att = f3(m.albedo[0], m.albedo[1], m.albedo[2]), sd = refl, so = p;
         bool ok = true;
@@ -235,6 +246,7 @@ __device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const S
                 const float par = -sqrt_(fabsf(1.0f - (qx * qx + qy * qy + qz * qz)));
                 sd = f3(qx + n.x * par, qy + n.y * par, qz + n.z * par);
             }
+            sanitize_dir(sd);
             if (front) {                                  // exit search, renderer.go:316-371
                 if (STATS) st[ST_EXIT_SCANS]++;
                 const RayK er = make_ray(p, sd);
@@ -326,6 +338,7 @@ __device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const S
             S.depth[j] = 0;                               // regenerated next iteration, together with the other finished slots
         } else {
             S.bx[j] *= att.x; S.by[j] *= att.y; S.bz[j] *= att.z;
+            if (c != CL_DIEL) sanitize_dir(sd);           // (dielectric: done before the exit search)
             S.ox[j] = so.x; S.oy[j] = so.y; S.oz[j] = so.z;
             S.dx[j] = sd.x; S.dy[j] = sd.y; S.dz[j] = sd.z;
             S.ctr[j] = rng.ctr;
@@ -592,6 +605,9 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
 #pragma unroll
         for (int k = 0; k < WF_SPT; ++k)
             S.perm[base[k] + (int)before[k]] = (unsigned short)((tid + k * WF_THREADS) | (cls[k] << 12));
+#if PTB_WF_DYNAMIC
+        if (tid == 0) S.shade_next = WF_WARPS;      // (the previous SHADE phase ended behind a barrier; the next starts behind the one below)
+#endif
         PTB_TICK(1)
         __syncthreads();
         PTB_MARK()
@@ -602,10 +618,18 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
         // Static, serpentine chunk assignment: perm[] is sorted heaviest class first, so warp w takes chunks w,
         // 2W-1-w, 2W+w, ... and pairs a heavy chunk with a light one (keeps the phase balanced without atomics,
         // and keeps the loop structure provably uniform so the scan above stays on the uniform datapath).
+#if PTB_WF_DYNAMIC
+        // Dynamic chunk assignment: perm[] is sorted heaviest class first; every warp starts with chunk `warp` and then takes
+        // the next unassigned chunk (one shared-memory atomic by lane 0, broadcast by shuffle — a warp-uniform value, so the
+        // loop structure stays provably uniform): longest-processing-time-first list scheduling instead of a fixed pairing.
+#pragma unroll 1
+        for (int chunk = warp; chunk < live_chunks;) {
+#else
 #pragma unroll 1
         for (int q = 0; q < WF_SPT; ++q) {
         const int chunk = (q & 1) ? (q + 1) * WF_WARPS - 1 - warp : q * WF_WARPS + warp;
         if (chunk >= live_chunks) continue;
+#endif
         const unsigned pv = S.perm[chunk * 32 + lane];
         const int j = pv & 0xFFF, c = pv >> 12;
 #ifdef PTB_WF_TIMING
@@ -618,6 +642,9 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
             atomicAdd(fp.stats + kStatsWords + 8 + 2 * c_lane0, (unsigned long long)(clock64() - tc0));
             atomicAdd(fp.stats + kStatsWords + 8 + 2 * c_lane0 + 1, 1ull);
         }
+#endif
+#if PTB_WF_DYNAMIC
+        { int nx = 0; if (lane == 0) nx = atomicAdd(&S.shade_next, 1); chunk = __shfl_sync(0xffffffffu, nx, 0); }
 #endif
         }   // chunk loop
 #ifdef PTB_WF_TIMING
