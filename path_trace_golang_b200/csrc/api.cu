@@ -205,6 +205,7 @@ int check_cfg(ptb_ctx* c, const ptb_cfg* cfg, int& s0, int& s1) {
         return fail(c, PTB_ERR_INVALID, "width and height must be >= 2 (got %dx%d)", cfg->width, cfg->height);
     if ((long long)cfg->width * cfg->height > (1ll << 30)) return fail(c, PTB_ERR_LIMIT, "frame too large");
     if (cfg->samples_per_px < 1) return fail(c, PTB_ERR_INVALID, "samples_per_px must be >= 1");
+    if (cfg->max_depth > 65534) return fail(c, PTB_ERR_LIMIT, "max_depth %d > 65534 (the remaining depth of a path is kept in 16 bits)", cfg->max_depth);
     s0 = 0; s1 = cfg->samples_per_px;
     if (cfg->sample_count > 0) {
         s0 = cfg->sample_begin; s1 = cfg->sample_begin + cfg->sample_count;
@@ -707,7 +708,7 @@ int build_mesh_accel(ptb_ctx* c, const ptb_scene* s, const WorldBuild& wb, MeshS
     BvhBuildInput in{tri_v.data(), (int64_t)tri_world.size(), tri_meta.data(), tri_world.data()};
     BvhBuildOutput out;
     build_bvh(in, out, threads);
-    if (out.max_depth > 38) return fail(c, PTB_ERR_LIMIT, "BVH depth %d exceeds the traversal stack", out.max_depth);
+    if (out.max_stack >= 40) return fail(c, PTB_ERR_LIMIT, "BVH needs %d pending traversal entries: more than the traversal stack holds", out.max_stack);
     cudaError_t e = cudaMalloc((void**)&st.fresh_nodes, out.nodes.size() * sizeof(BvhNode));
     if (e == cudaSuccess) e = cudaMalloc((void**)&st.fresh_tris, out.tris.size() * sizeof(BvhTri));
     if (e == cudaSuccess) e = cudaMemcpy(st.fresh_nodes, out.nodes.data(), out.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice);
@@ -1395,8 +1396,8 @@ int64_t ptb_bvh_selfcheck(const float* tri_vertices, int64_t n_tri, int64_t* n_n
         if (it.link >= 0) {
             if (it.link >= (int32_t)out.nodes.size()) { bad++; continue; }
             const BvhNode& nd = out.nodes[it.link];
-            for (int ch = 0; ch < 2; ch++) {
-                const int32_t l = f2i(nd.q[12 + ch]);
+            for (int ch = 0; ch < kBvhWidth; ch++) {
+                const int32_t l = f2i(nd.q[24 + ch]);
                 if (l == kEmptyLeaf) { if (!(nd.q[6 * ch + 3] < 0.0f)) bad++; continue; }
                 Item nx{l, {nd.q[6 * ch], nd.q[6 * ch + 1], nd.q[6 * ch + 2]}, {nd.q[6 * ch + 3], nd.q[6 * ch + 4], nd.q[6 * ch + 5]}, true};
                 auto chain = chains[my_chain];

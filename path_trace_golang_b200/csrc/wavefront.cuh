@@ -56,18 +56,20 @@ constexpr int WF_CHUNKS = WF_SLOTS / 32;
 #endif
 enum : int { CL_DIEL = 0, CL_TERM = 1, CL_REGEN = 2, CL_DIFFUSE = 3, CL_SPEC = 4, CL_CONT = 5, CL_DEAD = 6, CL_COUNT = 7 };
 
+// Path state, one entry per slot.  The SHADE phase reads and writes a slot through an arbitrary index (perm[]), so the state is
+// packed into 16-byte vectors — one LDS.128 / STS.128 moves a whole vector and its rider — while the scalars the SCAN phase
+// touches through its own index (stride 1: conflict-free) stay in arrays of their own.
+constexpr unsigned short kDepDead = 0xFFFFu;   // dep[]: slot retired;  0 = no live path (needs a new camera ray);  else remaining depth
+constexpr int kMaxDepth = 0xFFFE;
 template <int N>
-struct SlotState {                     // path state, SoA, one entry per slot
-    float ox[N], oy[N], oz[N];
-    float dx[N], dy[N], dz[N];
-    float bx[N], by[N], bz[N];         // throughput beta
-    float ax[N], ay[N], az[N];         // pixel sum
-    float best[N];
-    int bid[N];
-    uint32_t key[N], ctr[N];
-    int depth[N];                      // remaining depth of the live path; 0 = no live path (needs regeneration)
-    int smp[N];                        // sample index being traced
-    int pix[N];                        // pixel index, -1 = slot retired
+struct SlotState {
+    float4 O[N];                       // ray origin            | RNG key (bits)
+    float4 D[N];                       // ray direction         | RNG counter (bits)
+    float4 B[N];                       // throughput beta       | sample index being traced (bits)
+    float4 A[N];                       // pixel sum             | work item (pixel index, or plane * n_pix + pixel) (bits), -1 = none
+    float best[N];                     // closest hit of the last scan ...
+    int bid[N];                        // ... and its device object index (or kTriBit | triangle slot), -1 = miss
+    unsigned short dep[N];             // remaining depth of the live path (renderer.go:287-289), 0 / kDepDead see above
 };
 struct WfState : SlotState<WF_SLOTS> {
     unsigned short perm[WF_SLOTS];     // slot | class << 12
@@ -86,8 +88,9 @@ __device__ __forceinline__ int plane_bound(const FrameParams& fp, int g) {
 
 template <bool STATS, class SS>
 __device__ __forceinline__ void path_regen(SS& S, const FrameParams& fp, const SceneK& sc, int n_pix, int j, bool sample_done, unsigned long long* st) {
-    int w = S.pix[j];                                     // work item: the pixel, or plane * n_pix + pixel when the frame is split
-    int s = S.smp[j] + (sample_done ? 1 : 0);
+    float4 av = S.A[j];
+    int w = __float_as_int(av.w);                         // work item: the pixel, or plane * n_pix + pixel when the frame is split
+    int s = __float_as_int(S.B[j].w) + (sample_done ? 1 : 0);
     const bool split = fp.planes != nullptr;             // (a launch may cover a single plane of a split render)
     int pix = w, plane = 0, s_end = fp.s_end;
     if (split && w >= 0) {
@@ -96,7 +99,7 @@ __device__ __forceinline__ void path_regen(SS& S, const FrameParams& fp, const S
     }
     if (w < 0 || s >= s_end) {
         if (w >= 0) {                                     // item complete: epilogue / accumulation buffer / partial-sum plane
-            const float sx = S.ax[j], sy = S.ay[j], sz = S.az[j];
+            const float sx = av.x, sy = av.y, sz = av.z;
             if (split) {
                 float* a = fp.planes + (size_t)w * 3; a[0] = sx; a[1] = sy; a[2] = sz;
             } else {
@@ -108,17 +111,15 @@ __device__ __forceinline__ void path_regen(SS& S, const FrameParams& fp, const S
             }
         }
         w = (int)atomicAdd(fp.work_counter, 1u);
-        if (w >= n_pix * fp.split_k) { S.pix[j] = -1; S.depth[j] = 0; return; }
-        S.pix[j] = w;
+        if (w >= n_pix * fp.split_k) { S.A[j] = make_float4(0.0f, 0.0f, 0.0f, __int_as_float(-1)); S.dep[j] = kDepDead; return; }
         pix = w; s = fp.s_begin;
         float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
         if (split) {
             plane = w / n_pix; pix = w - plane * n_pix;
             s = plane_bound(fp, fp.split_base + plane);
         } else if (fp.accum_resume) { const float* a = fp.accum + (size_t)pix * 3; a0 = a[0]; a1 = a[1]; a2 = a[2]; }
-        S.ax[j] = a0; S.ay[j] = a1; S.az[j] = a2;
+        S.A[j] = make_float4(a0, a1, a2, __int_as_float(w));
     }
-    S.smp[j] = s;
     const int ly = pix / fp.width, px = pix - ly * fp.width;
     const int py = ly * fp.row_step + fp.row_offset;         // row partition: compact row ly is row py of the frame
     Rng rng;
@@ -140,11 +141,10 @@ __device__ __forceinline__ void path_regen(SS& S, const FrameParams& fp, const S
         dir = f3(dir.x - off.x, dir.y - off.y, dir.z - off.z);
     }
     sanitize_dir(dir);
-    S.ox[j] = org.x; S.oy[j] = org.y; S.oz[j] = org.z;
-    S.dx[j] = dir.x; S.dy[j] = dir.y; S.dz[j] = dir.z;
-    S.bx[j] = 1.0f; S.by[j] = 1.0f; S.bz[j] = 1.0f;
-    S.key[j] = rng.key; S.ctr[j] = rng.ctr;
-    S.depth[j] = fp.max_depth;
+    S.O[j] = make_float4(org.x, org.y, org.z, __uint_as_float(rng.key));
+    S.D[j] = make_float4(dir.x, dir.y, dir.z, __uint_as_float(rng.ctr));
+    S.B[j] = make_float4(1.0f, 1.0f, 1.0f, __int_as_float(s));
+    S.dep[j] = (unsigned short)fp.max_depth;
     if (STATS) st[ST_SAMPLES]++;
 }
 
@@ -166,8 +166,9 @@ template <bool STATS, bool MESH, bool BIG, class SS>
 __device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const SceneK& sc, const DevObj* __restrict__ s_obj, const DevMat* __restrict__ s_mat,
                                            int n_pix, int j, int c, unsigned long long* st) {
         if (c == CL_DIEL || c == CL_DIFFUSE || c == CL_SPEC) {
-        const F3 ro = f3(S.ox[j], S.oy[j], S.oz[j]);
-        const F3 rd = f3(S.dx[j], S.dy[j], S.dz[j]);
+        const float4 ov = S.O[j], dv = S.D[j];
+        const F3 ro = f3(ov.x, ov.y, ov.z);
+        const F3 rd = f3(dv.x, dv.y, dv.z);
         const float t_hit = S.best[j];
         const int hid = S.bid[j];
         F3 p, n; bool front;
@@ -182,8 +183,8 @@ __device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const S
             surface(ob, meta & 3, ro, rd, t_hit, p, n, front);
         }
         const DevMat m = s_mat[meta >> 6];
-        Rng rng{S.key[j], S.ctr[j]};
-        int depth = S.depth[j];
+        Rng rng{__float_as_uint(ov.w), __float_as_uint(dv.w)};
+        int depth = S.dep[j];
 
         uint32_t used = 0u;                               // draws consumed by this bounce (classes are warp-coherent: draw lazily)
         // unit incoming direction and its mirror image (math.go:39-46): every material but lambert needs them (a chunk of
@@ -335,20 +336,22 @@ __device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const S
             }
         }
         if (done) {
-            S.depth[j] = 0;                               // regenerated next iteration, together with the other finished slots
+            S.dep[j] = 0;                                 // regenerated next iteration, together with the other finished slots
         } else {
-            S.bx[j] *= att.x; S.by[j] *= att.y; S.bz[j] *= att.z;
+            float4 bv = S.B[j];
+            bv.x *= att.x; bv.y *= att.y; bv.z *= att.z;
+            S.B[j] = bv;
             if (c != CL_DIEL) sanitize_dir(sd);           // (dielectric: done before the exit search)
-            S.ox[j] = so.x; S.oy[j] = so.y; S.oz[j] = so.z;
-            S.dx[j] = sd.x; S.dy[j] = sd.y; S.dz[j] = sd.z;
-            S.ctr[j] = rng.ctr;
-            S.depth[j] = depth;
+            S.O[j] = make_float4(so.x, so.y, so.z, ov.w);
+            S.D[j] = make_float4(sd.x, sd.y, sd.z, __uint_as_float(rng.ctr));
+            S.dep[j] = (unsigned short)depth;
         }
-    } else if (c == CL_TERM && (!PTB_MERGE_TERM_REGEN || S.depth[j] > 0)) {   // sky (renderer.go:304-306) or emissive hit (:308-312)
+    } else if (c == CL_TERM && (!PTB_MERGE_TERM_REGEN || S.dep[j] != 0)) {     // sky (renderer.go:304-306) or emissive hit (:308-312)
         F3 e;                                             // (merged classes: a slot without a live path only regenerates)
         const int hb = S.bid[j];
         if (hb < 0) {
-            e = sky_color(sc.sky, f3(S.dx[j], S.dy[j], S.dz[j]));
+            const float4 dv = S.D[j];
+            e = sky_color(sc.sky, f3(dv.x, dv.y, dv.z));
             if (STATS) st[ST_END_SKY]++;
         } else {
             const bool is_tri = MESH && (hb & kTriBit) != 0;
@@ -357,7 +360,10 @@ __device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const S
             e = f3(m.emit[0], m.emit[1], m.emit[2]);
             if (STATS) { st[ST_END_EMISSIVE]++; st[is_tri ? ST_ACC_MESH : ST_ACC_SPHERE + (meta & 3)]++; }
         }
-        S.ax[j] += S.bx[j] * e.x; S.ay[j] += S.by[j] * e.y; S.az[j] += S.bz[j] * e.z;
+        const float4 bv = S.B[j];
+        float4 av = S.A[j];
+        av.x += bv.x * e.x; av.y += bv.y * e.y; av.z += bv.z * e.z;
+        S.A[j] = av;
     }
     if (c == CL_TERM || c == CL_REGEN) path_regen<STATS>(S, fp, sc, n_pix, j, true, st);
 }
@@ -389,8 +395,9 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
 #pragma unroll
     for (int k = 0; k < WF_SPT; ++k) {
         const int j = tid + k * WF_THREADS;
-        S.pix[j] = -1; S.smp[j] = 0; S.depth[j] = 0; S.trav[j] = 0;
-        S.ox[j] = 0.f; S.oy[j] = 0.f; S.oz[j] = 0.f; S.dx[j] = 0.f; S.dy[j] = 0.f; S.dz[j] = 1.f;
+        S.A[j] = make_float4(0.f, 0.f, 0.f, __int_as_float(-1)); S.B[j] = make_float4(1.f, 1.f, 1.f, __int_as_float(0));
+        S.O[j] = make_float4(0.f, 0.f, 0.f, 0.f); S.D[j] = make_float4(0.f, 0.f, 1.f, 0.f);
+        S.dep[j] = kDepDead; S.trav[j] = 0;
         if (fp.max_depth > 0) path_regen<STATS>(S, fp, c_scene, n_pix, j, false, st);
     }
     if (tid == 0) { S.n_list = 0; S.next_chunk = 0; }
@@ -419,7 +426,8 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
 #pragma unroll
             for (int k = 0; k < WF_SG; ++k) {
                 const int j = tid + (g + k) * WF_THREADS;
-                ray[k] = make_ray(f3(S.ox[j], S.oy[j], S.oz[j]), f3(S.dx[j], S.dy[j], S.dz[j]));
+                const float4 ov = S.O[j], dv = S.D[j];
+                ray[k] = make_ray(f3(ov.x, ov.y, ov.z), f3(dv.x, dv.y, dv.z));
                 best[k] = FLT_MAX; bid[k] = -1;
             }
             for (int gi = 0; gi < n_box_groups; ++gi) {              // kBoxGroup boxes per trip, 6 floats each (scene_dev.h)
@@ -477,7 +485,7 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
 #pragma unroll
                 for (int k = 0; k < WF_SG; ++k) {
                     const int j = tid + (g + k) * WF_THREADS;
-                    const bool live = S.pix[j] >= 0 && S.depth[j] > 0;
+                    const bool live = S.dep[j] != 0 && S.dep[j] != kDepDead;
                     const bool resume = live && S.trav[j] != 0;
                     float tb;
                     const bool need = resume || (live && hit_box(mc, mh, ray[k], 0.001f, best[k], tb));
@@ -507,7 +515,8 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
                             const int idx = base + __popc(idle & ((1u << lane) - 1u));
                             if (tj < 0 && idx < n_list) {
                                 tj = S.perm[idx];
-                                tr = make_ray(f3(S.ox[tj], S.oy[tj], S.oz[tj]), f3(S.dx[tj], S.dy[tj], S.dz[tj]));
+                                const float4 ov = S.O[tj], dv = S.D[tj];
+                                tr = make_ray(f3(ov.x, ov.y, ov.z), f3(dv.x, dv.y, dv.z));
                                 tbest = S.best[tj]; tbid = S.bid[tj];
                                 trav_begin(T, fp.trav_scratch + ((size_t)blockIdx.x * WF_SLOTS + tj) * kTravStride, S.trav[tj] != 0, PTB_BVH_STEP_BUDGET);
                             }
@@ -535,15 +544,16 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
             for (int k = 0; k < WF_SG; ++k) {
                 const int j = tid + (g + k) * WF_THREADS;
                 int c;
-                if (S.pix[j] < 0) c = CL_DEAD;
-                else if (S.depth[j] <= 0) c = PTB_MERGE_TERM_REGEN ? CL_TERM : CL_REGEN;
+                const unsigned dp = S.dep[j];
+                if (dp == kDepDead) c = CL_DEAD;
+                else if (dp == 0u) c = PTB_MERGE_TERM_REGEN ? CL_TERM : CL_REGEN;
                 else if (MESH && S.trav[j] != 0) c = CL_CONT;
                 else if (bid[k] < 0) c = CL_TERM;
                 else if (MESH && (bid[k] & kTriBit)) c = (__float_as_int(__ldg(fp.bvh_tris + 3 * (bid[k] & ~kTriBit) + 1).w) >> 3) & 7;
                 else c = (s_obj[bid[k]].meta >> 3) & 7;
                 cls[g + k] = c;
                 S.best[j] = best[k]; S.bid[j] = bid[k];
-                if (STATS) { st[ST_LANE_TOTAL]++; if (c != CL_DEAD && S.depth[j] > 0) { st[ST_LANE_ACTIVE]++; if (c != CL_CONT) st[ST_SEGMENTS]++; } }
+                if (STATS) { st[ST_LANE_TOTAL]++; if (c != CL_DEAD && dp != 0u) { st[ST_LANE_ACTIVE]++; if (c != CL_CONT) st[ST_SEGMENTS]++; } }
             }
         }
 

@@ -101,6 +101,45 @@ def test_oracle_bvh_equals_bruteforce(oracle_mod):
     assert (a[0] == len(doc["objects"]) - 1).mean() > 0.05
 
 
+def test_bvh_build_service_emits_aligned_wide_nodes():
+    """ptb_bvh_build (host only): the flattened arrays the device traverses — 128-byte aligned 4-wide nodes whose links cover every
+    triangle exactly once in leaves of at most 4, triangle records carrying the original index, depth about half a binary tree's."""
+    import ctypes as C
+    from path_trace_golang_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(3)
+    n = 5000
+    base = rng.random((n, 1, 3)).astype(np.float32) * 10
+    tris = (base + rng.random((n, 3, 3)).astype(np.float32) * 0.3).reshape(n, 9)
+    tris = np.ascontiguousarray(tris)
+    b = _lib.PtbBvh()
+    assert L.ptb_bvh_build(tris.ctypes.data_as(C.POINTER(C.c_float)), n, C.byref(b)) == 0
+    try:
+        assert b.info.n_triangles == n and b.info.node_bytes == 128 and b.info.triangle_bytes == 48
+        assert C.addressof(b.nodes.contents) % 64 == 0
+        nodes = np.ctypeslib.as_array(b.nodes, shape=(b.info.n_nodes, 32)).copy()
+        tr = np.ctypeslib.as_array(b.triangles, shape=(n, 12)).copy()
+        links = nodes[:, 24:28].view(np.int32)
+        half = nodes[:, [3, 9, 15, 21]]
+        used = half >= 0
+        assert (links[~used] == 0x7fffffff).all() and (nodes[:, 28:] == 0).all()
+        inner = links[used & (links >= 0)]
+        assert sorted(inner.tolist()) == list(range(1, b.info.n_nodes))          # every node but the root has exactly one parent
+        leaf = ~links[used & (links < 0)]
+        first, cnt = leaf >> 2, (leaf & 3) + 1
+        covered = np.zeros(n, dtype=np.int32)
+        for f, c in zip(first, cnt):
+            covered[f:f + c] += 1
+        assert (covered == 1).all()
+        ids = tr[:, 3].view(np.int32)
+        assert sorted(ids.tolist()) == list(range(n))
+        np.testing.assert_array_equal(tr[:, 0:3], tris[ids, 0:3])
+        assert 4 <= b.info.max_depth <= 14 and used.sum(axis=1).mean() > 2.5       # log4(5000 / 4) ~ 5; inner levels are full, nodes over two leaves stay 2-wide
+    finally:
+        L.ptb_bvh_free(C.byref(b))
+    assert L.ptb_bvh_selfcheck(tris.ctypes.data_as(C.POINTER(C.c_float)), n, None, None) == 0
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,nx,nz,res", [("example_simple", 40, 30, (1280, 720)), ("test_comprehensive", 300, 200, (1920, 1080))])
@@ -111,7 +150,7 @@ def test_gpu_primary_hits_with_mesh_bit_exact(name, nx, nz, res, ctx, oracle_mod
     sc = scene.Parse(json.dumps(doc))
     ctx.upload(sc)
     info = ctx.bvh_info()
-    assert info["n_triangles"] == nx * nz * 2 and info["node_bytes"] == 64 and info["triangle_bytes"] == 48 and info["max_depth"] < 38
+    assert info["n_triangles"] == nx * nz * 2 and info["node_bytes"] == 128 and info["triangle_bytes"] == 48 and info["max_depth"] < 38
     ids, t = ctx.primary_hits(*res)
     oids, ot = oracle_mod.OracleScene(doc, mesh_triangles=sc.mesh_triangles()).primary_hits(*res)
     assert (ids == oids).all(), f"{(ids != oids).sum()} id mismatches"
