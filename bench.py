@@ -134,11 +134,11 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm)}
 
 
-def traffic_record():
+def traffic_record(workload):
     """DRAM bytes per launch of the dominant kernel from the newest committed ncu --set full capture (profiles/traffic.json,
     written by tools/ncu_traffic.py from the .ncu-rep: dram__bytes_read.sum + dram__bytes_write.sum of one launch)."""
     try:
-        return json.load(open(ROOT / "profiles" / "traffic.json"))
+        return json.load(open(ROOT / "profiles" / "traffic.json")).get(workload)
     except Exception:
         return None
 
@@ -271,7 +271,7 @@ def main():
     mesh_note = f" + {C4_MESH[args.workload][0] * C4_MESH[args.workload][1] * 2} triangle heightfield" if args.workload in C4_MESH else ""
     config = {"workload": f"{args.workload}: scenes/{name}.json{mesh_note} {W}x{H}, {spp} spp, max depth {depth}", "scene": name,
               "width": W, "height": H, "samples_per_px": spp, "max_depth": depth,
-              "partition": ("single GPU" if world == 1 else "interleaved rows per rank + all_gather of RGBA8" if args.partition == "rows"
+              "partition": ("single GPU" if world == 1 else "image tiles (interleaved rows) per rank with the epilogue fused + NCCL gather of RGBA8 rows to rank 0" if args.partition == "rows"
                             else {"peer": "sample ranges per rank; one kernel per rank: reduce-scatter + epilogue + gather over NVLink peer memory (CUDA IPC)",
                                   "scatter": "sample ranges per rank; NCCL reduce_scatter + per-rank epilogue + gather of RGBA8 to rank 0",
                                   "reduce": "sample ranges per rank + NCCL reduce to rank 0 + epilogue on rank 0"}[args.exchange]),
@@ -338,7 +338,7 @@ def main():
             ctx.render_device(cfg, rgba.data_ptr(), stream)      # 1 launch: integrate + epilogue
             return rgba
         if args.partition == "rows":
-            return pdist.render_rows_distributed(ctx, cfg)       # interleaved rows, fused epilogue, all_gather of RGBA8
+            return pdist.render_rows_distributed(ctx, cfg)       # interleaved rows, fused epilogue, gather of RGBA8 rows to rank 0
         if peers is not None:
             return pdist.render_distributed_peer(ctx, cfg, peers)    # 2 launches per rank: integrate, reduce+epilogue+gather slice
         if accum_padded is not None:
@@ -440,7 +440,7 @@ def main():
         achieved = fps * (samples / world) / (kernel_ms * 1e-3) / 1e12
         flat = sc.flat()
         h2d = 8 * (flat.n_obj * 8 + flat.n_mat * 12) + 512          # flattened SoA + camera/sky structs (bytes, approx. exact)
-        tr = traffic_record()
+        tr = traffic_record(args.workload)
         split_k = 1                                                 # (frames of >= 1.2 M pixels are not split: 1 launch per frame)
         per_rank_launches = 1 if (world == 1 or args.partition == "rows") else 2
         out = {
@@ -450,9 +450,10 @@ def main():
             "mrays_per_s": value * rays_per_sample, "rays_per_sample": rays_per_sample,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak if fp32_peak else None,
-                         "traffic": (tr["dram_bytes_read"] + tr["dram_bytes_write"]) if tr and tr.get("workload") == args.workload else None,
+                         "traffic": (tr["dram_bytes_read"] + tr["dram_bytes_write"]) if tr else None,
                          "traffic_note": (f"dram__bytes_read.sum + dram__bytes_write.sum of one {tr['kernel']} launch, ncu --set full capture "
-                                          f"{tr['source']} ({tr['what']}); read from profiles/traffic.json at run time") if tr else
+                                          f"{tr['source']} ({tr['what']}; that launch traced {tr.get('spp_captured')} spp — the scene is on chip, so the bytes do not grow with "
+                                          f"spp); read from profiles/traffic.json at run time") if tr else
                                          "no ncu capture recorded in profiles/traffic.json",
                          "kernel": kernel_name, "kernel_ms": kernel_ms,
                          "flops_per_sample": fps, "simt_lane_utilisation": simt_util,
@@ -484,7 +485,7 @@ def main():
             out["roofline_fp32"] = out["roofline"]
             out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak or 6650.0, "unit": "GB/s",
                                "frac": ach / (hbm_peak or 6650.0),
-                               "traffic": (tr["dram_bytes_read"] + tr["dram_bytes_write"]) if tr and tr.get("workload") == args.workload else None,
+                               "traffic": (tr["dram_bytes_read"] + tr["dram_bytes_write"]) if tr else None,
                                "kernel": kernel_name,
                                "kernel_ms": kernel_ms, "bytes_per_sample": bytes_per_sample,
                                "nodes_per_ray": st["bvh_nodes_visited"] / st["segments"], "tris_per_ray": st["bvh_tris_tested"] / st["segments"],

@@ -12,10 +12,10 @@ constexpr int kTriBit = 0x40000000;        // hit id = kTriBit | slot in the lea
 constexpr int kTravStack = 40;
 constexpr int kTravStride = kTravStack + 4;     // ints of global scratch per path slot: sp, cur, best_tri, -, stack[]
 #ifndef PTB_BVH_STEP_BUDGET
-#define PTB_BVH_STEP_BUDGET 24                 // inner-node visits per ray and wavefront iteration
+#define PTB_BVH_STEP_BUDGET 16                 // inner-node visits per ray and wavefront iteration
 #endif
 #ifndef PTB_BVH_ROUND_NODES
-#define PTB_BVH_ROUND_NODES 8                  // inner-node visits between two refills of a warp's idle lanes
+#define PTB_BVH_ROUND_NODES 4                  // inner-node visits between two refills of a warp's idle lanes
 #endif
 
 // a*b - c*d and a 3-term dot product with a fixed rounding sequence.

@@ -33,9 +33,17 @@ bool parse(int argc, char** argv, Flags& f) {
             return nullptr;
         };
         const char* v = nullptr;
-        if (a == "-gpu") f.gpu = true;
-        else if (a == "-headless") f.headless = true;
-        else if (a == "-settings") f.settings = true;
+        // Go's flag package: a boolean flag is `-flag` or `-flag=value` (strconv.ParseBool values); `-flag value` is NOT its argument
+        auto boolean = [&](bool& dst) -> bool {
+            if (!has_val) { dst = true; return true; }
+            if (val == "1" || val == "t" || val == "T" || val == "true" || val == "TRUE" || val == "True") { dst = true; return true; }
+            if (val == "0" || val == "f" || val == "F" || val == "false" || val == "FALSE" || val == "False") { dst = false; return true; }
+            std::fprintf(stderr, "invalid boolean value \"%s\" for %s: parse error\n", val.c_str(), a.c_str());
+            return false;
+        };
+        if (a == "-gpu") { if (!boolean(f.gpu)) return false; }
+        else if (a == "-headless") { if (!boolean(f.headless)) return false; }
+        else if (a == "-settings") { if (!boolean(f.settings)) return false; }
         else if (a == "-scene") { if (!(v = next())) return false; f.scene = v; }
         else if (a == "-mode") { if (!(v = next())) return false; f.mode = v; }
         else if (a == "-out") { if (!(v = next())) return false; f.out = v; }

@@ -76,6 +76,7 @@ struct WfState : SlotState<WF_SLOTS> {
     alignas(4) unsigned short cnt[CL_COUNT * WF_WARPS];
     unsigned char trav[WF_SLOTS];      // MESH: 1 = the slot's traversal is suspended (state in FrameParams::trav_scratch)
     int n_list, next_chunk;            // MESH: compacted list of slots to traverse (in perm[]) and its chunk dispenser
+    int n_back;                        // MESH: rays starting their traversal are listed from the END of perm[] (resumed ones from the front)
     int shade_next;                    // PTB_WF_DYNAMIC: next unassigned 32-slot chunk of the SHADE phase
 };
 
@@ -400,7 +401,7 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
         S.dep[j] = kDepDead; S.trav[j] = 0;
         if (fp.max_depth > 0) path_regen<STATS>(S, fp, c_scene, n_pix, j, false, st);
     }
-    if (tid == 0) { S.n_list = 0; S.next_chunk = 0; }
+    if (tid == 0) { S.n_list = 0; S.next_chunk = 0; S.n_back = 0; }
     __syncthreads();
 
 #ifdef PTB_WF_TIMING
@@ -490,14 +491,21 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
                     float tb;
                     const bool need = resume || (live && hit_box(mc, mh, ray[k], 0.001f, best[k], tb));
                     if (!resume) { S.best[j] = best[k]; S.bid[j] = bid[k]; }     // a suspended slot keeps its partial result
-                    const unsigned m = __ballot_sync(0xffffffffu, need);
-                    int base = 0;
-                    if (lane == 0 && m) base = atomicAdd(&S.n_list, __popc(m));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (need) S.perm[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)j;   // perm[] is free until the sort
+                    // Longest-processing-time-first: a ray whose traversal was suspended has already used up one step budget, so it
+                    // is likely to be long — it goes to the FRONT of the list (perm[0..)), rays that start now to the back
+                    // (perm[WF_SLOTS-1] downwards), and the lanes take the list front to back: the long rays start first and the
+                    // phase does not end on a late, long straggler.
+                    const unsigned mr = __ballot_sync(0xffffffffu, resume), mn = __ballot_sync(0xffffffffu, need && !resume);
+                    int base_r = 0, base_n = 0;
+                    if (lane == 0 && mr) base_r = atomicAdd(&S.n_list, __popc(mr));
+                    if (lane == 0 && mn) base_n = atomicAdd(&S.n_back, __popc(mn));
+                    base_r = __shfl_sync(0xffffffffu, base_r, 0); base_n = __shfl_sync(0xffffffffu, base_n, 0);
+                    const unsigned lt = (1u << lane) - 1u;
+                    if (resume) S.perm[base_r + __popc(mr & lt)] = (unsigned short)j;                // perm[] is free until the sort
+                    else if (need) S.perm[WF_SLOTS - 1 - (base_n + __popc(mn & lt))] = (unsigned short)j;
                 }
                 __syncthreads();
-                const int n_list = S.n_list;
+                const int n_front = S.n_list, n_list = n_front + S.n_back;
                 {   // persistent lanes: a lane whose ray finished (or ran out of budget) takes the next ray of the list
                     int tj = -1;                     // slot this lane is traversing, -1 = none
                     RayK tr;
@@ -514,7 +522,7 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
                             more = base + __popc(idle) < n_list;
                             const int idx = base + __popc(idle & ((1u << lane) - 1u));
                             if (tj < 0 && idx < n_list) {
-                                tj = S.perm[idx];
+                                tj = S.perm[idx < n_front ? idx : WF_SLOTS - 1 - (idx - n_front)];
                                 const float4 ov = S.O[tj], dv = S.D[tj];
                                 tr = make_ray(f3(ov.x, ov.y, ov.z), f3(dv.x, dv.y, dv.z));
                                 tbest = S.best[tj]; tbid = S.bid[tj];
@@ -522,6 +530,9 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
                             }
                         }
                         if (__ballot_sync(0xffffffffu, tj >= 0) == 0u) break;
+#ifdef PTB_BVH_TAIL_BUDGET
+                        if (!more && T.budget > PTB_BVH_TAIL_BUDGET) T.budget = PTB_BVH_TAIL_BUDGET;   // list exhausted: do not let the CTA wait for stragglers
+#endif
                         if (tj >= 0) {
                             const int status = trav_round<STATS>(fp.bvh_nodes, fp.bvh_tris, tr, 0.001f, tbest, tbid, st, T, PTB_BVH_ROUND_NODES);
                             if (status != 0) {
@@ -533,7 +544,7 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
                     }
                 }
                 __syncthreads();
-                if (tid == 0) { S.n_list = 0; S.next_chunk = 0; }                 // next use is behind the sort's barriers
+                if (tid == 0) { S.n_list = 0; S.next_chunk = 0; S.n_back = 0; }  // next use is behind the sort's barriers
 #pragma unroll
                 for (int k = 0; k < WF_SG; ++k) {
                     const int j = tid + (g + k) * WF_THREADS;
@@ -654,7 +665,11 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
         }
 #endif
 #if PTB_WF_DYNAMIC
-        { int nx = 0; if (lane == 0) nx = atomicAdd(&S.shade_next, 1); chunk = __shfl_sync(0xffffffffu, nx, 0); }
+        {   // (inline PTX: the atomicAdd intrinsic wraps a one-lane atomic in ~10 instructions of warp aggregation)
+            int nx = 0;
+            if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(nx) : "r"((unsigned)__cvta_generic_to_shared(&S.shade_next)) : "memory");
+            chunk = __shfl_sync(0xffffffffu, nx, 0);
+        }
 #endif
         }   // chunk loop
 #ifdef PTB_WF_TIMING

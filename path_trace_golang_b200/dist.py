@@ -85,10 +85,10 @@ def assemble_rows(parts, height: int) -> torch.Tensor:
     return out
 
 
-def render_rows_distributed(ctx, cfg_full, group=None):
-    """Whole multi-GPU frame by interleaved rows: render (fused epilogue) -> all_gather -> assemble on every rank.
-
-    Returns the CUDA uint8 (H, W, 4) image.  Everything is enqueued on torch's current stream."""
+def render_rows_distributed(ctx, cfg_full, group=None, to_all: bool = False):
+    """Whole multi-GPU frame by interleaved rows (image tiles): render (fused epilogue) -> gather of the ranks' compact RGBA8 row
+    sets to rank 0 -> assemble there.  4 bytes per pixel cross the links in total.  Returns the CUDA uint8 (H, W, 4) image on rank
+    0 and None elsewhere (to_all=True: all_gather, every rank assembles the frame).  Everything is enqueued on torch's current stream."""
     from ._lib import PtbCfg
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -103,9 +103,13 @@ def render_rows_distributed(ctx, cfg_full, group=None):
         ctx.render_device(cfg, mine.data_ptr(), stream)
     if world == 1:
         return mine
-    gathered = torch.empty((world * rows_max, W, 4), dtype=torch.uint8, device=dev)      # rank-major concatenation
-    dist.all_gather_into_tensor(gathered, mine, group=group)
-    return assemble_rows(list(gathered.view(world, rows_max, W, 4)), H)
+    if to_all:
+        gathered = torch.empty((world * rows_max, W, 4), dtype=torch.uint8, device=dev)      # rank-major concatenation
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+        return assemble_rows(list(gathered.view(world, rows_max, W, 4)), H)
+    parts = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+    dist.gather(mine, parts, dst=0, group=group)
+    return assemble_rows(parts, H) if rank == 0 else None
 
 
 # ---- the fused exchange (default on GPUs): ONE kernel per rank does reduce-scatter + pixel epilogue + gather over NVLink peer

@@ -53,6 +53,11 @@ def test_cpp_driver_flags_and_errors():
     assert r.returncode == 2 and "flag provided but not defined: -bogus" in r.stderr
     r = subprocess.run([str(exe), "-scene", "/nonexistent.json", "-headless"], capture_output=True, text=True)
     assert r.returncode == 1 and "open scene" in r.stderr
+    # boolean flags follow Go's flag package: -flag=false is false (it used to read as true), junk is an error
+    r = subprocess.run([str(exe), "-scene", "/nonexistent.json", "-headless=false", "-gpu=false"], capture_output=True, text=True)
+    assert r.returncode == 1 and "headless=0" in r.stderr
+    r = subprocess.run([str(exe), "-headless=maybe"], capture_output=True, text=True)
+    assert r.returncode == 2 and "invalid boolean value" in r.stderr
 
 
 @pytest.mark.gpu

@@ -9,7 +9,7 @@ mi=[("rng",find(srcI,"struct Rng")-8),("vec helpers",find(srcI,"struct F3")),("i
 ("surface",find(srcI,"void surface")-1),("sky",find(srcI,"F3 sky_color")),("to_u8",find(srcI,"uint8_t to_u8")-1),("megakernel",find(srcI,"integrate_kernel(const __grid_constant__")-2)]
 mw=[("wf prologue",1),("wf regen",find(srcW,"void path_regen")-1),("wf shade: load+surface",find(srcW,"void path_shade")-1),("wf shade: common",find(srcW,"draws consumed by this bounce")),
 ("wf shade: diffuse",find(srcW,"} else if (c == CL_DIFFUSE)")),("wf shade: dielectric",find(srcW,"} else if (c == CL_DIEL)")),("wf exit search",find(srcW,"if (front) {")),
-("wf RR/update",find(srcW,"bool done = !ok;")),("wf term",find(srcW,"} else if (c == CL_TERM)")),("wf kernel prologue",find(srcW,"integrate_wf_kernel(const __grid_constant__")-2),("wf scan",find(srcW,"SCAN (thread")),("wf sort",find(srcW,"SORT (stable")),("wf shade loop+barrier",find(srcW,"SHADE (one class per")),("wf epilogue",find(srcW,"if (STATS) {",find(srcW,"SHADE (one class per")))]
+("wf RR/update",find(srcW,"bool done = !ok;")),("wf term",find(srcW,"} else if (c == CL_TERM")),("wf kernel prologue",find(srcW,"integrate_wf_kernel(const __grid_constant__")-2),("wf scan",find(srcW,"SCAN (thread")),("wf sort",find(srcW,"SORT (stable")),("wf shade loop+barrier",find(srcW,"SHADE (one class per")),("wf epilogue",find(srcW,"if (STATS) {",find(srcW,"SHADE (one class per")))]
 def region(f,line):
     marks = mi if f=="integrator.cu" else mw if f=="wavefront.cuh" else None
     if marks is None: return "other:"+f
