@@ -14,9 +14,10 @@ import (
 // emits a flattened, cache-line-aligned node array").  The builder itself is the library's (binned SAH, ptb_bvh_build — the
 // same code ptb_scene_upload runs), so the Go side and the device can never disagree about the layout:
 //
-//	Nodes      16 float32 per node (64 bytes): both children's boxes as centre / half extent, then the two child links as bit
-//	           patterns (link >= 0: inner node index; link < 0: leaf, ^link = firstTriangle<<2 | count-1)
-//	Triangles  12 float32 per triangle (48 bytes), leaf order: v0 + bits(original index), e1 = v1-v0, e2 = v2-v0
+//	Nodes      32 float32 per node (128 bytes, 4-wide): floats 6k..6k+5 = child k's box as centre / half extent (half < 0: unused),
+//	           floats 24..27 = the child links as bit patterns (link >= 0: inner node index; link < 0: leaf,
+//	           ^link = firstTriangle<<2 | count-1), floats 28..31 = 0
+//	Triangles  16 float32 per triangle (64 bytes), leaf order: v0 + bits(original index), e1 = v1-v0, e2 = v2-v0, padding
 type BVH struct {
 	Nodes, Triangles []float32
 	MaxDepth         int
@@ -36,7 +37,7 @@ func BuildBVH(tris []float32) (*BVH, error) {
 	}
 	defer C.ptb_bvh_free(&b)
 	out := &BVH{MaxDepth: int(b.info.max_depth), SAHCost: float64(b.info.sah_cost), BuildMs: float64(b.info.build_ms)}
-	out.Nodes = append(out.Nodes, unsafe.Slice((*float32)(unsafe.Pointer(b.nodes)), int(b.info.n_nodes)*16)...)
-	out.Triangles = append(out.Triangles, unsafe.Slice((*float32)(unsafe.Pointer(b.triangles)), int(b.info.n_triangles)*12)...)
+	out.Nodes = append(out.Nodes, unsafe.Slice((*float32)(unsafe.Pointer(b.nodes)), int(b.info.n_nodes)*32)...)
+	out.Triangles = append(out.Triangles, unsafe.Slice((*float32)(unsafe.Pointer(b.triangles)), int(b.info.n_triangles)*16)...)
 	return out, nil
 }

@@ -111,7 +111,7 @@ typedef struct {
     /* EXTENSION — triangle meshes (the reference has none; north-star: "internal/scene gains a BVH builder that emits
      * a flattened, cache-line-aligned node array").  An object of type PTB_OBJ_MESH is ONE world entry; obj_mesh[i]
      * names its mesh; triangles are given in world space, binary32, 9 floats each (v0, v1, v2).  The library builds
-     * the BVH (binned SAH, 64-byte nodes).  Hit rule: Moeller-Trumbore, two-sided, t in [tMin, closest); among
+     * the BVH (binned SAH collapsed to 4-wide 128-byte nodes).  Hit rule: Moeller-Trumbore, two-sided, t in [tMin, closest); among
      * triangles of equal t the lowest triangle index wins; geometric normal.  n_mesh == 0: all three may be NULL. */
     int32_t n_mesh;
     const int32_t* obj_mesh;         /* [n_obj] mesh index for PTB_OBJ_MESH objects, -1 otherwise */
@@ -163,8 +163,8 @@ typedef struct {
     uint64_t lane_iters_total;  /* 32 x warp loop iterations (SIMT utilisation denominator) */
     double last_render_ms;      /* device time of the last render call (CUDA events) */
     uint64_t accepts_mesh;      /* EXTENSION: winning hits on mesh triangles */
-    uint64_t bvh_nodes_visited; /* 64-byte node fetches */
-    uint64_t bvh_tris_tested;   /* 48-byte triangle fetches */
+    uint64_t bvh_nodes_visited; /* 128-byte (4-wide) node fetches */
+    uint64_t bvh_tris_tested;   /* 64-byte triangle fetches */
     uint64_t bvh_stack_overflows; /* subtrees dropped because the traversal stack was full: must be 0 (the builder bounds the depth) */
 } ptb_stats;
 
@@ -302,14 +302,14 @@ int ptb_scene_device_order(const ptb_scene* scene, int32_t* order, int32_t cap, 
 int64_t ptb_bvh_selfcheck(const float* tri_vertices, int64_t n_tri, int64_t* n_nodes, int32_t* max_depth);
 
 /* Host only (no CUDA call): the BVH builder on its own — binned SAH over n_tri world-space triangles (9 floats each), output
- * as the flattened arrays the device traverses: 64-byte cache-line-aligned nodes (both children's boxes as centre / half
- * extent + links; layout in path_trace_golang_b200/csrc/bvh.h) and 48-byte triangles (v0, e1, e2) in leaf order carrying the
+ * as the flattened arrays the device traverses: 128-byte cache-line-aligned 4-wide nodes (the children's boxes as centre / half
+ * extent + links; layout in path_trace_golang_b200/csrc/bvh.h) and 64-byte triangles (v0, e1, e2, pad) in leaf order carrying the
  * original triangle index.  ptb_scene_upload calls the same builder; this entry point lets the host inspect, cache or
  * serialise the structure (north-star: "internal/scene gains a BVH builder that emits a flattened, cache-line-aligned node
  * array").  Free with ptb_bvh_free. */
 typedef struct {
-    const float* nodes;       /* info.n_nodes x 16 floats, 64-byte aligned */
-    const float* triangles;   /* info.n_triangles x 12 floats */
+    const float* nodes;       /* info.n_nodes x 32 floats (128-byte nodes), 64-byte aligned */
+    const float* triangles;   /* info.n_triangles x 16 floats */
     ptb_bvh_info info;
 } ptb_bvh;
 int ptb_bvh_build(const float* tri_vertices, int64_t n_tri, ptb_bvh* out);

@@ -61,7 +61,8 @@ struct ptb_ctx {
     BvhNode* d_bvh_nodes = nullptr;      // EXTENSION: mesh BVH
     BvhTri* d_bvh_tris = nullptr;
     float* d_planes = nullptr; size_t planes_cap = 0;   // partial-sum planes of split (small) frames
-    int* d_trav = nullptr; size_t trav_cap = 0;   // suspended-traversal scratch (wavefront kernel, mesh scenes)
+    int* d_trav = nullptr; size_t trav_cap = 0;   // suspended-traversal scratch (persistent kernel with in-kernel traversal: PTB_MESH_PERSISTENT)
+    MeshPipe mesh_pipe;                           // mesh scenes: global path state + ray queue of the wavefront across kernels
     BvhNode* d_bvh_nodes_keep = nullptr; // last built BVH, reused when the same triangles are uploaded again
     BvhTri* d_bvh_tris_keep = nullptr;
     ptb_bvh_info bvh_keep{};
@@ -281,7 +282,9 @@ int render_launch(ptb_ctx* c, const ptb_cfg* cfg, const SplitPlan& plan, float* 
         if (e) return fail(c, PTB_ERR_CUDA, "clear launch: %s", cudaGetErrorString((cudaError_t)e));
         return PTB_OK;
     }
-    if (c->d_bvh_nodes) {
+    // mesh scenes: in-kernel traversal (wavefront.cuh), or — experiment, PTB_MESH_PIPELINE=1 — the wavefront across kernels (mesh_pipeline.cuh)
+    const bool mesh_pipeline = c->d_bvh_nodes && !(cfg->flags & PTB_FLAG_MEGAKERNEL) && std::getenv("PTB_MESH_PIPELINE") != nullptr;
+    if (c->d_bvh_nodes && !mesh_pipeline) {
         int rc = ensure(c, (void**)&c->d_trav, &c->trav_cap, wf_trav_scratch_bytes(c->prop.multiProcessorCount));
         if (rc) return rc;
         fp.trav_scratch = c->d_trav;
@@ -302,6 +305,25 @@ int render_launch(ptb_ctx* c, const ptb_cfg* cfg, const SplitPlan& plan, float* 
             fp.split_k = k; fp.planes = c->d_planes;
         }
         c->last_kernel = std::string("integrate_wf_kernel<") + (stats ? "1, " : "0, ") + (c->d_bvh_nodes ? "1, " : "0, ") + (hs.big ? "1>" : "0>");
+        if (mesh_pipeline) {
+            MeshPipe& mp = c->mesh_pipe;
+            const int n_slots = mesh_pool_slots(c->prop.multiProcessorCount, (long long)W * R * k);
+            const size_t need = mesh_pool_bytes(n_slots);
+            if (mp.d_bytes < need) {
+                cudaFree(mp.d_mem); mp.d_mem = nullptr; mp.d_bytes = 0;
+                CK(c, cudaMalloc(&mp.d_mem, need));
+                mp.d_bytes = need;
+            }
+            mesh_pool_bind(mp.pool, mp.d_mem, n_slots);
+            if (!mp.h_flags) CK(c, cudaMallocHost((void**)&mp.h_flags, 4 * sizeof(unsigned int)));
+            for (void*& ev : mp.events) if (!ev) { cudaEvent_t x; CK(c, cudaEventCreateWithFlags(&x, cudaEventDisableTiming)); ev = x; }
+            c->last_kernel = std::string("mp_shade_scan_kernel<") + (stats ? "1, " : "0, ") + (hs.big ? "1>" : "0>") + " + mp_traverse_kernel<" + (stats ? "1>" : "0>");
+            // the pipeline replays a CUDA graph, which the legacy default stream cannot capture: it runs on the context's own
+            // stream, ordered behind the caller's stream, and has finished when the call returns
+            CK(c, cudaEventRecord(c->ev_batch[0], stream));
+            CK(c, cudaStreamWaitEvent(c->stream, c->ev_batch[0], 0));
+            e = launch_mesh_pipeline(ka, stats, hs.big, c->prop.multiProcessorCount, &c->launch_cache, mp, c->stream);
+        } else
         e = launch_integrator_wf(ka, stats, hs.big, c->prop.multiProcessorCount, &c->launch_cache, stream);
         if (!e && plan.total > 1) e = launch_finalize_planes(c->d_planes, k, W, R, cfg->samples_per_px, d_accum, resume ? 1 : 0, d_rgba, stream);
     }
@@ -388,6 +410,9 @@ void ptb_destroy(ptb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();            // frames queued on caller streams may still read this context's buffers
+    cudaFree(c->mesh_pipe.d_mem);
+    if (c->mesh_pipe.h_flags) cudaFreeHost(c->mesh_pipe.h_flags);
+    for (void* e : c->mesh_pipe.events) if (e) cudaEventDestroy((cudaEvent_t)e);
     cudaFree(c->d_planes); cudaFree(c->d_trav); cudaFree(c->d_blob); cudaFree(c->d_tab); cudaFree(c->d_diel); cudaFree(c->d_world64);
     cudaFree(c->d_bvh_nodes_keep); cudaFree(c->d_bvh_tris_keep); cudaFree(c->d_accum); cudaFree(c->d_rgba); cudaFree(c->d_rgba2);
     cudaFree(c->d_stats); cudaFree(c->d_work);
@@ -1178,8 +1203,11 @@ int ptb_multi_render(ptb_multi* m, const ptb_cfg* cfg, uint8_t* rgba, size_t str
         if (e != cudaSuccess) { drop_all(); return mfail(m, PTB_ERR_CUDA, std::string("cudaMemcpy: ") + cudaGetErrorString(e)); }
         m->accum_cap = bytes;
     }
-    // every device traces its sample range (asynchronous launches: the devices run concurrently)
-    for (int k = 0; k < n; k++) {
+    // every device traces its sample range.  The analytic integrator is one asynchronous launch per device, so issuing them
+    // one after the other already runs the devices concurrently; the mesh pipeline drives its device from the host until the
+    // frame is done, so mesh scenes get one host thread per device.
+    std::vector<int> rcs(n, PTB_OK);
+    auto work = [&](int k) {
         const int base = spp / n, rem = spp % n;
         const int b = k * base + (k < rem ? k : rem), cnt = base + (k < rem ? 1 : 0);
         ptb_ctx* c = m->ctx[k];
@@ -1189,13 +1217,20 @@ int ptb_multi_render(ptb_multi* m, const ptb_cfg* cfg, uint8_t* rgba, size_t str
             ptb_cfg sub = *cfg;
             sub.sample_begin = b; sub.sample_count = cnt;
             sub.flags &= ~PTB_FLAG_STATS;
-            int rc = ptb_render_accum_device(c, &sub, m->d_accum[k], c->stream);
-            if (rc != PTB_OK) return mfail(m, rc, ptb_last_error(c));
+            rcs[k] = ptb_render_accum_device(c, &sub, m->d_accum[k], c->stream);
         } else {
             cudaMemsetAsync(m->d_accum[k], 0, bytes, c->stream);
         }
         cudaEventRecord(m->done[k], c->stream);
+    };
+    if (n > 1 && m->ctx[0]->d_bvh_nodes) {
+        std::vector<std::thread> pool;
+        for (int k = 0; k < n; k++) pool.emplace_back(work, k);
+        for (auto& t : pool) t.join();
+    } else {
+        for (int k = 0; k < n; k++) work(k);
     }
+    for (int k = 0; k < n; k++) if (rcs[k] != PTB_OK) return mfail(m, rcs[k], ptb_last_error(m->ctx[k]));
     // device 0: wait for everybody, then the fused reduce + epilogue over peer memory, then read back
     ptb_ctx* c0 = m->ctx[0];
     cudaSetDevice(c0->device);

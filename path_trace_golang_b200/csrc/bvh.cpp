@@ -143,6 +143,7 @@ void build_bvh(const BvhBuildInput& in, BvhBuildOutput& out, int threads) {
         o.q[0] = v[0]; o.q[1] = v[1]; o.q[2] = v[2]; o.q[3] = i2f((int32_t)t);
         o.q[4] = v[3] - v[0]; o.q[5] = v[4] - v[1]; o.q[6] = v[5] - v[2]; o.q[7] = i2f(in.tri_meta[t]);
         o.q[8] = v[6] - v[0]; o.q[9] = v[7] - v[1]; o.q[10] = v[8] - v[2]; o.q[11] = i2f(in.tri_world[t]);
+        o.q[12] = o.q[13] = o.q[14] = o.q[15] = 0.0f;
     }
     struct Item { const BuildNode* n; int32_t slot; int depth; int pending; };
     std::vector<Item> stack;

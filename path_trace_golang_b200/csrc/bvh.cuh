@@ -7,6 +7,13 @@
 
 namespace ptb {
 
+// One 256-bit read-only load (LDG.E.256.CONSTANT, sm_100): two adjacent float4 at a 32-byte aligned address.
+__device__ __forceinline__ void ld256(const float4* __restrict__ p, float4& a, float4& b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+constexpr int kTriQuads = 4;               // float4 per triangle record (bvh.h)
+
 constexpr int kTriBit = 0x40000000;        // hit id = kTriBit | slot in the leaf-ordered triangle array
 
 constexpr int kTravStack = 40;
@@ -45,17 +52,23 @@ __device__ __forceinline__ void trav_save(const TravState& T, int* __restrict__ 
 }
 
 // One round: up to max_nodes inner-node visits (while-while: the warp reconverges behind the node loop, so the triangle
-// tests run with all the lanes that reached a leaf), then the leaf the ray stands on, if any.
+// tests run with all the lanes that reached a leaf), then the triangles of the leaf the ray set aside on the way, if any.
 // Returns 0 = in progress, 1 = finished, 2 = out of budget (T.cur is an inner node; trav_save it to continue later).
 template <bool STATS>
 __device__ __forceinline__ int trav_round(const float4* __restrict__ nodes, const float4* __restrict__ tris, const RayK& r, float tmin,
                                           float& best, int& bid, unsigned long long* st, TravState& T, int max_nodes) {
     int cur = T.cur, sp = T.sp;
-    while (cur >= 0 && max_nodes > 0 && T.budget > 0) {
+    // Postponed leaf: the first leaf a ray reaches in a round is set aside and the ray goes on with its next node, so the lanes
+    // of a warp stay together in the node loop instead of idling from their first leaf to the end of the round (ncu r02g: the
+    // traversal ran with 9.8 of 32 lanes); the triangle tests of all the lanes' postponed leaves then run together.
+    int pend = 0;                              // 0 = none (node 0 is the root, never a leaf link)
+    for (;;) {
+        if (cur < 0 && cur != kTravDone && pend == 0) { pend = cur; cur = sp ? T.stack[--sp] : kTravDone; }
+        if (cur < 0 || max_nodes <= 0 || T.budget <= 0) break;
         --max_nodes; --T.budget;
-        const float4* nd = nodes + 8 * cur;                 // 128-byte node: 7 read-only 16-byte loads (the 8th quad is padding)
-        const float4 q0 = __ldg(nd), q1 = __ldg(nd + 1), q2 = __ldg(nd + 2), q3 = __ldg(nd + 3), q4 = __ldg(nd + 4), q5 = __ldg(nd + 5),
-                     q6 = __ldg(nd + 6);
+        const float4* nd = nodes + 8 * cur;                 // 128-byte node: four 256-bit read-only loads
+        float4 q0, q1, q2, q3, q4, q5, q6, q7;
+        ld256(nd, q0, q1); ld256(nd + 2, q2, q3); ld256(nd + 4, q4, q5); ld256(nd + 6, q6, q7);
         if (STATS) st[ST_BVH_NODES]++;
         // children as (centre, half extent): near/far of an axis are (c - o)/d -+ h/|d| (see hit_box); a child that is missed
         // (or unused: h = -1) gets the distance +inf
@@ -93,10 +106,11 @@ __device__ __forceinline__ int trav_round(const float4* __restrict__ nodes, cons
         if (d[1] < inf) { if (sp < kTravStack) T.stack[sp++] = l[1]; else if (STATS) st[ST_BVH_STACK_OVERFLOW]++; }
         cur = d[0] < inf ? l[0] : (sp ? T.stack[--sp] : kTravDone);
     }
-    if (cur < 0 && cur != kTravDone) {
-        const int link = ~cur, first = link >> 2, cnt = (link & 3) + 1;
+    if (pend != 0) {
+        const int link = ~pend, first = link >> 2, cnt = (link & 3) + 1;
         for (int k = 0; k < cnt; ++k) {
-            const float4 a = __ldg(tris + 3 * (first + k)), b = __ldg(tris + 3 * (first + k) + 1), c = __ldg(tris + 3 * (first + k) + 2);
+            float4 a, b, c, pad_;
+            ld256(tris + kTriQuads * (first + k), a, b); ld256(tris + kTriQuads * (first + k) + 2, c, pad_);
             if (STATS) st[ST_BVH_TRIS]++;
             // (products and sums spelled out: the contraction ptxas would pick for a*b - c*d is not the same in every
             // instantiation of the kernel, and the STATS build must trace exactly the paths of the plain one)
@@ -115,8 +129,8 @@ __device__ __forceinline__ int trav_round(const float4* __restrict__ nodes, cons
             const int id = __float_as_int(a.w);
             if (t < best || (T.best_tri >= 0 && id < T.best_tri)) { best = t; bid = kTriBit | (first + k); T.best_tri = id; }
         }
-        cur = sp ? T.stack[--sp] : kTravDone;
     }
+    // (cur may be a second leaf reached in this round: it is postponed first thing in the next one)
     T.cur = cur; T.sp = sp;
     if (cur == kTravDone) return 1;
     if (cur >= 0 && T.budget <= 0) return 2;
@@ -134,7 +148,7 @@ __device__ __forceinline__ void bvh_closest(const float4* __restrict__ nodes, co
 
 // Surface of a triangle hit: point, geometric normal flipped against the ray (setFaceNormal, objects.go:17-24), frontFace.
 __device__ __forceinline__ void tri_surface(const float4* __restrict__ tris, int slot, F3 o, F3 d, float t, F3& p, F3& n, bool& front, int& meta) {
-    const float4 b = __ldg(tris + 3 * slot + 1), c = __ldg(tris + 3 * slot + 2);
+    const float4 b = __ldg(tris + kTriQuads * slot + 1), c = __ldg(tris + kTriQuads * slot + 2);
     p = f3(fmaf(d.x, t, o.x), fmaf(d.y, t, o.y), fmaf(d.z, t, o.z));
     F3 g = f3(xmy(b.y, c.z, b.z, c.y), xmy(b.z, c.x, b.x, c.z), xmy(b.x, c.y, b.y, c.x));    // e1 x e2
     {   // unit3 and dot3 with the rounding sequence fixed (see trav_round)

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <float.h>
 #include <stdint.h>
+#include <cstdlib>
 
 #include "scene_dev.h"
 
@@ -575,6 +576,7 @@ integrate_kernel(const __grid_constant__ KernelArgs ka) {
 }  // namespace ptb
 #include "bvh.cuh"
 #include "wavefront.cuh"
+#include "mesh_pipeline.cuh"
 namespace ptb {
 
 __global__ void finalize_kernel(const float* __restrict__ accum, int n_pix, double inv_spp, uchar4* __restrict__ rgba) {
@@ -740,6 +742,95 @@ int launch_integrator_wf(const KernelArgs& ka, bool stats, bool big, int sm_coun
     PTB_WF_CASE(true, false, false) PTB_WF_CASE(true, false, true) PTB_WF_CASE(true, true, false) PTB_WF_CASE(true, true, true)
 #undef PTB_WF_CASE
     return (int)cudaErrorInvalidValue;
+}
+
+// ---- mesh pipeline (mesh_pipeline.cuh)
+size_t mesh_pool_bytes(int n_slots) {
+    return (size_t)n_slots * (4 * sizeof(float4) + sizeof(float) + sizeof(int) + sizeof(int) + sizeof(unsigned short)) + kMpCtlWords * sizeof(unsigned int) + 1024;
+}
+void mesh_pool_bind(MeshPool& pool, void* d_mem, int n_slots) {
+    char* p = (char*)d_mem;
+    auto take = [&](size_t bytes) { void* r = p; p += (bytes + 255) / 256 * 256; return r; };
+    pool.n_slots = n_slots;
+    pool.O = (float4*)take((size_t)n_slots * sizeof(float4)); pool.D = (float4*)take((size_t)n_slots * sizeof(float4));
+    pool.B = (float4*)take((size_t)n_slots * sizeof(float4)); pool.A = (float4*)take((size_t)n_slots * sizeof(float4));
+    pool.best = (float*)take((size_t)n_slots * sizeof(float)); pool.bid = (int*)take((size_t)n_slots * sizeof(int));
+    pool.queue = (int*)take((size_t)n_slots * sizeof(int)); pool.dep = (unsigned short*)take((size_t)n_slots * sizeof(unsigned short));
+    pool.ctl = (unsigned int*)take(kMpCtlWords * sizeof(unsigned int));
+}
+int mesh_pool_slots(int sm_count, long long n_items) {
+    long long want = (long long)sm_count * PTB_MP_CTAS_PER_SM * WF_SLOTS;
+    if (const char* e = std::getenv("PTB_MP_CTAS_PER_SM")) { int k = std::atoi(e); if (k >= 1 && k <= 64) want = (long long)sm_count * k * WF_SLOTS; }
+    const long long need = (n_items + WF_SLOTS - 1) / WF_SLOTS * WF_SLOTS;
+    return (int)(want < need ? want : need);
+}
+
+template <bool STATS, bool BIG>
+static int mp_prepare(size_t smem, LaunchCache::Entry& lc) {       // (outside the stream capture)
+    if (smem > 48 * 1024 && smem > lc.smem_optin) {
+        cudaError_t e = cudaFuncSetAttribute(mp_shade_scan_kernel<STATS, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        lc.smem_optin = smem;
+    }
+    return 0;
+}
+template <bool STATS, bool BIG>
+static int launch_mp_iteration(const KernelArgs& ka, const MeshPool& pool, size_t smem, int traverse_blocks, cudaStream_t stream) {
+    mp_shade_scan_kernel<STATS, BIG><<<pool.n_slots / WF_SLOTS, WF_THREADS, smem, stream>>>(ka, pool);
+    mp_traverse_kernel<STATS><<<traverse_blocks, 256, 0, stream>>>(ka.fp.bvh_nodes, ka.fp.bvh_tris, pool, ka.fp.stats);
+    return (int)cudaGetLastError();
+}
+
+int launch_mesh_pipeline(const KernelArgs& ka, bool stats, bool big, int sm_count, LaunchCache* cache, MeshPipe& mp, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const MeshPool& pool = mp.pool;
+    const size_t smem = ((sizeof(WfState) + 15) / 16 + (big ? 0 : (size_t)(ka.sc.n_obj * 2 + ka.sc.n_mat * 3))) * sizeof(uint4);
+    if (!mp.traverse_blocks) {
+        int nb = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, mp_traverse_kernel<false>, 256, 0);
+        if (e != cudaSuccess) return (int)e;
+        mp.traverse_blocks = sm_count * (nb > 0 ? nb : 1);
+    }
+    LaunchCache::Entry& lc = cache->mp[(stats ? 2 : 0) | (big ? 1 : 0)];
+    {
+        const int pe = stats ? (big ? mp_prepare<true, true>(smem, lc) : mp_prepare<true, false>(smem, lc)) : (big ? mp_prepare<false, true>(smem, lc) : mp_prepare<false, false>(smem, lc));
+        if (pe) return pe;
+    }
+    auto iteration = [&]() -> int {
+        if (stats) return big ? launch_mp_iteration<true, true>(ka, pool, smem, mp.traverse_blocks, stream) : launch_mp_iteration<true, false>(ka, pool, smem, mp.traverse_blocks, stream);
+        return big ? launch_mp_iteration<false, true>(ka, pool, smem, mp.traverse_blocks, stream) : launch_mp_iteration<false, false>(ka, pool, smem, mp.traverse_blocks, stream);
+    };
+    // One period = kCheck iterations + a copy of the newest "a path is alive" flag to pinned memory, captured ONCE as a CUDA
+    // graph and replayed: the kernels take the iteration number from device memory, so every period is the same graph except
+    // for the flag word copied, which is why the copy and the event stay outside the graph.
+    constexpr int kCheck = 8;
+    mp_init_kernel<<<(pool.n_slots + 255) / 256, 256, 0, stream>>>(pool);
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
+    if (ce != cudaSuccess) return (int)ce;
+    int e = 0;
+    for (int k = 0; k < kCheck && !e; ++k) e = iteration();
+    ce = cudaStreamEndCapture(stream, &graph);
+    if (e) { if (graph) cudaGraphDestroy(graph); return e; }
+    if (ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+    if (ce != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return (int)ce; }
+    int pending = -1;                    // event slot of the flag copy not yet looked at
+    for (int period = 0; ce == cudaSuccess; ++period) {
+        ce = cudaGraphLaunch(exec, stream);
+        if (ce != cudaSuccess) break;
+        if (pending >= 0) {              // the host runs one period ahead of the flag it reads: no bubble on the device
+            ce = cudaEventSynchronize((cudaEvent_t)mp.events[pending]);
+            if (ce != cudaSuccess || mp.h_flags[pending] == 0u) break;     // no path was alive at the end of the previous period
+        }
+        const int slot = period & 1, last_iter = period * kCheck + kCheck - 1;
+        ce = cudaMemcpyAsync(&mp.h_flags[slot], pool.ctl + 8 + (last_iter & 15), sizeof(unsigned int), cudaMemcpyDeviceToHost, stream);
+        if (ce == cudaSuccess) ce = cudaEventRecord((cudaEvent_t)mp.events[slot], stream);
+        pending = slot;
+    }
+    cudaError_t se = cudaStreamSynchronize(stream);
+    cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+    return (int)(ce != cudaSuccess ? ce : se);
 }
 
 int launch_finalize(const float* accum, int width, int height, int spp_total, uint8_t* rgba, void* stream) {

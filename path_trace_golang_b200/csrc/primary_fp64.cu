@@ -101,7 +101,7 @@ __device__ void bvh_closest64(const float4* __restrict__ nodes, const float4* __
         } else {
             const int link = ~cur, first = link >> 2, cnt = (link & 3) + 1;
             for (int k = 0; k < cnt; ++k) {
-                const float4 a = __ldg(tris + 3 * (first + k)), b = __ldg(tris + 3 * (first + k) + 1), c = __ldg(tris + 3 * (first + k) + 2);
+                const float4 a = __ldg(tris + 4 * (first + k)), b = __ldg(tris + 4 * (first + k) + 1), c = __ldg(tris + 4 * (first + k) + 2);   // 64-byte records
                 const double e1x = b.x, e1y = b.y, e1z = b.z, e2x = c.x, e2y = c.y, e2z = c.z;
                 const double px = d[1] * e2z - d[2] * e2y, py = d[2] * e2x - d[0] * e2z, pz = d[0] * e2y - d[1] * e2x;
                 const double det = e1x * px + e1y * py + e1z * pz;

@@ -138,6 +138,26 @@ struct KernelArgs {              // the one __grid_constant__ parameter of the i
 };
 static_assert(sizeof(KernelArgs) <= 16 * 1024, "kernel parameters: keep well below the 32,764-byte limit");
 
+// Mesh scenes (mesh_pipeline.cuh): path state in global memory between the kernels of the pipeline, the ray queue of the
+// traversal kernel and its control words.  One pool per context, sized for SMs x PTB_MP_CTAS_PER_SM x 512 path slots.
+struct MeshPool {
+    float4 *O, *D, *B, *A;       // per slot, as SlotState (wavefront.cuh)
+    float* best; int* bid; unsigned short* dep;
+    int* queue;                  // slots whose ray must be traversed this iteration
+    unsigned int* ctl;           // control words (mesh_pipeline.cuh)
+    int n_slots;
+};
+struct MeshPipe {                // host side of the pool
+    MeshPool pool{};
+    void* d_mem = nullptr; size_t d_bytes = 0;
+    unsigned int* h_flags = nullptr;     // pinned: copies of the "alive" flags
+    void* events[4] = {nullptr, nullptr, nullptr, nullptr};
+    int traverse_blocks = 0;             // persistent grid of the traversal kernel (per device)
+};
+size_t mesh_pool_bytes(int n_slots);
+void mesh_pool_bind(MeshPool& pool, void* d_mem, int n_slots);
+int mesh_pool_slots(int sm_count, long long n_items);
+
 enum StatWord {
     ST_SAMPLES = 0, ST_SEGMENTS, ST_EXIT_SCANS, ST_ACC_SPHERE, ST_ACC_PLANE, ST_ACC_BOX, ST_SCATTERS,
     ST_END_SKY, ST_END_EMISSIVE, ST_END_RR, ST_END_DEPTH, ST_END_NOSCATTER, ST_LANE_ACTIVE, ST_LANE_TOTAL,
@@ -150,11 +170,15 @@ enum StatWord {
 struct LaunchCache {
     struct Entry { size_t smem_optin = 0, smem_occ = ~(size_t)0; int blocks_per_sm = 0; };
     Entry wf[8];                 // integrate_wf_kernel<STATS, MESH, BIG>
+    Entry mp[4];                 // mp_shade_scan_kernel<STATS, BIG>
 };
 
 // launchers (integrator.cu / primary_fp64.cu)
 int launch_integrator(const KernelArgs& ka, bool stats, void* stream);          // pixel-per-lane megakernel (small worlds only)
 int launch_integrator_wf(const KernelArgs& ka, bool stats, bool big, int sm_count, LaunchCache* cache, void* stream);
+// mesh scenes: the wavefront across kernels.  Launches iteration after iteration on `stream` and WAITS for completion in
+// steps (the host reads an "alive" flag a few iterations behind): returns when the frame is complete.
+int launch_mesh_pipeline(const KernelArgs& ka, bool stats, bool big, int sm_count, LaunchCache* cache, MeshPipe& mp, void* stream);
 int launch_clear_frame(float* accum, int accum_resume, uint8_t* rgba, int n_pix, void* stream);   // max_depth <= 0: black frame
 size_t wf_trav_scratch_bytes(int sm_count);      // size of FrameParams::trav_scratch the mesh instantiation needs
 int launch_finalize(const float* accum, int width, int height, int spp_total, uint8_t* rgba, void* stream);

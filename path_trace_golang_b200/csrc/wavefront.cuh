@@ -356,7 +356,7 @@ __device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const S
             if (STATS) st[ST_END_SKY]++;
         } else {
             const bool is_tri = MESH && (hb & kTriBit) != 0;
-            const int meta = is_tri ? __float_as_int(__ldg(fp.bvh_tris + 3 * (hb & ~kTriBit) + 1).w) : s_obj[hb].meta;
+            const int meta = is_tri ? __float_as_int(__ldg(fp.bvh_tris + kTriQuads * (hb & ~kTriBit) + 1).w) : s_obj[hb].meta;
             const DevMat& m = s_mat[meta >> 6];
             e = f3(m.emit[0], m.emit[1], m.emit[2]);
             if (STATS) { st[ST_END_EMISSIVE]++; st[is_tri ? ST_ACC_MESH : ST_ACC_SPHERE + (meta & 3)]++; }
@@ -367,6 +367,66 @@ __device__ __forceinline__ void path_shade(SS& S, const FrameParams& fp, const S
         S.A[j] = av;
     }
     if (c == CL_TERM || c == CL_REGEN) path_regen<STATS>(S, fp, sc, n_pix, j, true, st);
+}
+
+// Loop bounds and table offsets of the closest-hit scan, read once per kernel from the scene header (warp-uniform values).
+struct ScanK {
+    int n_obj, n_box, n_box_groups, n_plane_run, n_sphere_groups, plane_off4, sphere_off4, n_typed, sphere_base;
+    __device__ __forceinline__ explicit ScanK(const SceneK& sc)
+        : n_obj(sc.n_obj), n_box(sc.n_box), n_box_groups(sc.n_box_groups), n_plane_run(sc.n_plane_run), n_sphere_groups(sc.n_sphere_groups),
+          plane_off4(sc.plane_off4), sphere_off4(sc.sphere_off4), n_typed(sc.n_typed), sphere_base(sc.n_box + sc.n_plane_run) {}
+};
+
+// Closest hit of WF_SG rays over the analytic world (renderer.go:292-302): every record of the per-type scan tables is tested
+// against all the rays as it is loaded (warp-uniform loops; operands from the constant bank via LDCU unless BIG).
+template <bool BIG>
+__device__ __forceinline__ void scan_analytic(const SceneK& sc, const ScanK& k_, const DevObj* __restrict__ s_obj, const RayK (&ray)[WF_SG],
+                                              float (&best)[WF_SG], int (&bid)[WF_SG]) {
+    for (int gi = 0; gi < k_.n_box_groups; ++gi) {              // kBoxGroup boxes per trip, 6 floats each (scene_dev.h)
+        const int q = gi * (kBoxGroup * 6 / 4);
+        float bx[kBoxGroup * 6];
+#pragma unroll
+        for (int v = 0; v < kBoxGroup * 6 / 4; ++v) { const float4 w = tab_ld4<BIG>(sc, q + v); bx[4 * v] = w.x; bx[4 * v + 1] = w.y; bx[4 * v + 2] = w.z; bx[4 * v + 3] = w.w; }
+#pragma unroll
+        for (int u = 0; u < kBoxGroup; ++u) {
+            const float4 lo = make_float4(bx[6 * u], bx[6 * u + 1], bx[6 * u + 2], 0.0f);
+            const float4 hi = make_float4(bx[6 * u + 3], bx[6 * u + 4], bx[6 * u + 5], 0.0f);
+#pragma unroll
+            for (int k = 0; k < WF_SG; ++k) {
+                float t;
+                if (hit_box(lo, hi, ray[k], 0.001f, best[k], t)) { best[k] = t; bid[k] = gi * kBoxGroup + u; }
+            }
+        }
+    }
+    for (int i = 0; i < k_.n_plane_run; ++i) {
+        const float py = tab_ld1<BIG>(sc, k_.plane_off4 * 4 + i);
+#pragma unroll
+        for (int k = 0; k < WF_SG; ++k) {
+            float t;
+            if (hit_plane1(py, ray[k], 0.001f, best[k], t)) { best[k] = t; bid[k] = k_.n_box + i; }
+        }
+    }
+    for (int gi = 0; gi < k_.n_sphere_groups; ++gi) {
+#pragma unroll
+        for (int u = 0; u < kSphereGroup; ++u) {
+            const float4 sp = tab_ld4<BIG>(sc, k_.sphere_off4 + gi * kSphereGroup + u);
+#pragma unroll
+            for (int k = 0; k < WF_SG; ++k) {
+                float t;
+                if (hit_sphere4(sp.x, sp.y, sp.z, sp.w, ray[k], 0.001f, best[k], t)) { best[k] = t; bid[k] = k_.sphere_base + gi * kSphereGroup + u; }
+            }
+        }
+    }
+    for (int i = k_.n_typed; i < k_.n_obj; ++i) {                  // whatever follows the typed runs in world order
+        const float4 lo = obj_lo(s_obj, i), hi = obj_hi(s_obj, i);
+        const bool is_sphere = (__float_as_int(lo.w) & 3) == PTB_OBJ_SPHERE;
+#pragma unroll
+        for (int k = 0; k < WF_SG; ++k) {
+            float t;
+            const bool h = is_sphere ? hit_sphere(lo, hi, ray[k], 0.001f, best[k], t) : hit_plane(lo, ray[k], 0.001f, best[k], t);
+            if (h) { best[k] = t; bid[k] = i; }
+        }
+    }
 }
 
 template <bool STATS, bool MESH, bool BIG>
@@ -388,9 +448,7 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n_pix = fp.width * fp.rows;
-    const int n_box = c_scene.n_box;
-    const int n_box_groups = c_scene.n_box_groups, n_plane_run = c_scene.n_plane_run, n_sphere_groups = c_scene.n_sphere_groups;
-    const int plane_off4 = c_scene.plane_off4, sphere_off4 = c_scene.sphere_off4, n_typed = c_scene.n_typed, sphere_base = n_box + n_plane_run;
+    const ScanK sk(c_scene);
     unsigned long long st[STATS ? kStatsWords : 1] = {0};
 
 #pragma unroll
@@ -431,51 +489,7 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
                 ray[k] = make_ray(f3(ov.x, ov.y, ov.z), f3(dv.x, dv.y, dv.z));
                 best[k] = FLT_MAX; bid[k] = -1;
             }
-            for (int gi = 0; gi < n_box_groups; ++gi) {              // kBoxGroup boxes per trip, 6 floats each (scene_dev.h)
-                const int q = gi * (kBoxGroup * 6 / 4);
-                float bx[kBoxGroup * 6];
-#pragma unroll
-                for (int v = 0; v < kBoxGroup * 6 / 4; ++v) { const float4 w = tab_ld4<BIG>(c_scene, q + v); bx[4 * v] = w.x; bx[4 * v + 1] = w.y; bx[4 * v + 2] = w.z; bx[4 * v + 3] = w.w; }
-#pragma unroll
-                for (int u = 0; u < kBoxGroup; ++u) {
-                    const float4 lo = make_float4(bx[6 * u], bx[6 * u + 1], bx[6 * u + 2], 0.0f);
-                    const float4 hi = make_float4(bx[6 * u + 3], bx[6 * u + 4], bx[6 * u + 5], 0.0f);
-#pragma unroll
-                    for (int k = 0; k < WF_SG; ++k) {
-                        float t;
-                        if (hit_box(lo, hi, ray[k], 0.001f, best[k], t)) { best[k] = t; bid[k] = gi * kBoxGroup + u; }
-                    }
-                }
-            }
-            for (int i = 0; i < n_plane_run; ++i) {
-                const float py = tab_ld1<BIG>(c_scene, plane_off4 * 4 + i);
-#pragma unroll
-                for (int k = 0; k < WF_SG; ++k) {
-                    float t;
-                    if (hit_plane1(py, ray[k], 0.001f, best[k], t)) { best[k] = t; bid[k] = n_box + i; }
-                }
-            }
-            for (int gi = 0; gi < n_sphere_groups; ++gi) {
-#pragma unroll
-                for (int u = 0; u < kSphereGroup; ++u) {
-                    const float4 sp = tab_ld4<BIG>(c_scene, sphere_off4 + gi * kSphereGroup + u);
-#pragma unroll
-                    for (int k = 0; k < WF_SG; ++k) {
-                        float t;
-                        if (hit_sphere4(sp.x, sp.y, sp.z, sp.w, ray[k], 0.001f, best[k], t)) { best[k] = t; bid[k] = sphere_base + gi * kSphereGroup + u; }
-                    }
-                }
-            }
-            for (int i = n_typed; i < n_obj; ++i) {                  // whatever follows the typed runs in world order
-                const float4 lo = obj_lo(s_obj, i), hi = obj_hi(s_obj, i);
-                const bool is_sphere = (__float_as_int(lo.w) & 3) == PTB_OBJ_SPHERE;
-#pragma unroll
-                for (int k = 0; k < WF_SG; ++k) {
-                    float t;
-                    const bool h = is_sphere ? hit_sphere(lo, hi, ray[k], 0.001f, best[k], t) : hit_plane(lo, ray[k], 0.001f, best[k], t);
-                    if (h) { best[k] = t; bid[k] = i; }
-                }
-            }
+            scan_analytic<BIG>(c_scene, sk, s_obj, ray, best, bid);
             if (MESH) {
                 // EXTENSION: triangle meshes, tested after the analytic objects (bvh.cuh).  Only rays that reach the meshes'
                 // bounds before their analytic hit (or whose traversal was suspended) are traversed, and they are compacted
@@ -560,7 +574,7 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
                 else if (dp == 0u) c = PTB_MERGE_TERM_REGEN ? CL_TERM : CL_REGEN;
                 else if (MESH && S.trav[j] != 0) c = CL_CONT;
                 else if (bid[k] < 0) c = CL_TERM;
-                else if (MESH && (bid[k] & kTriBit)) c = (__float_as_int(__ldg(fp.bvh_tris + 3 * (bid[k] & ~kTriBit) + 1).w) >> 3) & 7;
+                else if (MESH && (bid[k] & kTriBit)) c = (__float_as_int(__ldg(fp.bvh_tris + kTriQuads * (bid[k] & ~kTriBit) + 1).w) >> 3) & 7;
                 else c = (s_obj[bid[k]].meta >> 3) & 7;
                 cls[g + k] = c;
                 S.best[j] = best[k]; S.bid[j] = bid[k];

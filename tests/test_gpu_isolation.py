@@ -92,19 +92,40 @@ def test_parameter_table_boundary_matches_global_tables(ctx, oracle_mod, monkeyp
 
 def test_small_scene_then_large_scene_same_process(host_scenes):
     """the >48 KB shared-memory opt-in used to be taken once per process on the first scene's size.  A fresh
-    context renders a 10-object scene, then one whose records need the opt-in (about 250 objects, 28 materials)."""
+    context renders a 10-object scene, then one whose records need the opt-in (320 objects, 28 materials: the largest world that
+    still takes the kernel-parameter path)."""
     from path_trace_golang_b200 import engine, scene
     c = engine.Context(0)
     try:
         c.upload(host_scenes["example_simple"])
         a = c.render(c.cfg(160, 90, 2, 8, seed=1))
-        c.upload(scene.Parse(json.dumps(sphere_field(250, box_every=4))))
+        c.upload(scene.Parse(json.dumps(sphere_field(320, box_every=4))))      # 38.7 KB of path state + 11.6 KB of records > 48 KB
         b = c.render(c.cfg(160, 90, 2, 6, seed=1))
         c.upload(host_scenes["example_simple"])
         a2 = c.render(c.cfg(160, 90, 2, 8, seed=1))
         assert b[..., :3].any() and (a == a2).all()
     finally:
         c.close()
+
+
+def test_rejected_upload_keeps_the_previous_scene(ctx, host_scenes):
+    """a failed ptb_scene_upload used to leave the context half-updated.  The upload is staged now: a scene that is
+    rejected (material index out of range) changes nothing, and the next render equals the one before."""
+    import ctypes as C
+    from path_trace_golang_b200 import _lib, engine
+    sc = host_scenes["test_scene"]
+    ctx.upload(sc)
+    cfg = ctx.cfg(200, 120, 3, 10, seed=4)
+    before = ctx.render(cfg)
+    flat = sc.flat()
+    bad = _lib.PtbScene()
+    C.memmove(C.byref(bad), C.byref(flat), C.sizeof(flat))
+    mats = (C.c_int32 * flat.n_obj)(*[flat.obj_mat[i] for i in range(flat.n_obj)])
+    mats[flat.n_obj - 1] = flat.n_mat + 5                       # out of range: build_world rejects the scene
+    bad.obj_mat = mats
+    rc = _lib.lib().ptb_scene_upload(ctx._h, C.byref(bad))
+    assert rc == _lib.PTB_ERR_INVALID and b"out of range" in _lib.lib().ptb_last_error(ctx._h)
+    assert len(ctx.world()) > 0 and (ctx.render(cfg) == before).all()
 
 
 def test_two_contexts_render_concurrently_on_one_device(host_scenes):

@@ -115,10 +115,10 @@ def test_bvh_build_service_emits_aligned_wide_nodes():
     b = _lib.PtbBvh()
     assert L.ptb_bvh_build(tris.ctypes.data_as(C.POINTER(C.c_float)), n, C.byref(b)) == 0
     try:
-        assert b.info.n_triangles == n and b.info.node_bytes == 128 and b.info.triangle_bytes == 48
+        assert b.info.n_triangles == n and b.info.node_bytes == 128 and b.info.triangle_bytes == 64
         assert C.addressof(b.nodes.contents) % 64 == 0
         nodes = np.ctypeslib.as_array(b.nodes, shape=(b.info.n_nodes, 32)).copy()
-        tr = np.ctypeslib.as_array(b.triangles, shape=(n, 12)).copy()
+        tr = np.ctypeslib.as_array(b.triangles, shape=(n, 16)).copy()
         links = nodes[:, 24:28].view(np.int32)
         half = nodes[:, [3, 9, 15, 21]]
         used = half >= 0
@@ -150,7 +150,7 @@ def test_gpu_primary_hits_with_mesh_bit_exact(name, nx, nz, res, ctx, oracle_mod
     sc = scene.Parse(json.dumps(doc))
     ctx.upload(sc)
     info = ctx.bvh_info()
-    assert info["n_triangles"] == nx * nz * 2 and info["node_bytes"] == 128 and info["triangle_bytes"] == 48 and info["max_depth"] < 38
+    assert info["n_triangles"] == nx * nz * 2 and info["node_bytes"] == 128 and info["triangle_bytes"] == 64 and info["max_depth"] < 38
     ids, t = ctx.primary_hits(*res)
     oids, ot = oracle_mod.OracleScene(doc, mesh_triangles=sc.mesh_triangles()).primary_hits(*res)
     assert (ids == oids).all(), f"{(ids != oids).sum()} id mismatches"
