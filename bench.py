@@ -517,6 +517,7 @@ def main():
                                    "note": "C++ restatement of the Go CPU path (Go toolchain unavailable)"}
         print(json.dumps(out))
     if peers is not None:
+        peers.check()              # raises if a wait of the exchange ever timed out
         peers.close()
     if world > 1:
         dist.destroy_process_group()

@@ -271,19 +271,27 @@ int ptb_multi_last_timing(ptb_multi* m, double* render_ms, double* reduce_ms);
  * 1/world slice of the pixels over all ranks' buffers (NVLink peer loads) and stores the finalised RGBA8 pixels directly into
  * rank 0's image (NVLink peer stores).  Against "NCCL reduce to rank 0, then finalise" this moves 12 B/pixel * (world-1)/world
  * spread over all links plus 4 B/pixel into rank 0, instead of 12 B/pixel * (world-1) into rank 0 alone.
+ * The cross-rank ordering is part of the same kernel — flag words in peer memory: "my sums of frame seq are complete" /
+ * "my slice of frame seq is written" — so no collective-library call is made per frame at all.
  * Protocol: every rank ptb_peer_create -> ptb_peer_handles -> exchange the handles with the host's own communicator
- * (all-gather of 64 bytes) -> ptb_peer_connect.  Per frame: render into ptb_peer_accum() (ptb_render_accum_device), make sure
- * every rank's render has finished (a stream-ordered barrier of the host's communicator, e.g. a 4-byte NCCL all-reduce),
- * ptb_peer_reduce_finalize on every rank, barrier again; rank 0 then owns the image at ptb_peer_image().
+ * (all-gather of 3 x 64 bytes, once) -> ptb_peer_connect.  Per frame, on every rank, on one stream: render into
+ * ptb_peer_accum() (ptb_render_accum_device), then ptb_peer_reduce_finalize — when it has run on the stream, every rank has
+ * finished the frame: rank 0 owns the image at ptb_peer_image() and every rank may render the next frame into its buffer.
+ * Every rank must call ptb_peer_reduce_finalize the same number of times (frames are matched by a sequence number); a rank
+ * that never arrives makes the others give up after a few seconds (ptb_peer_status reports it) instead of hanging the device.
  * Sum order is rank 0, 1, 2, ... on every rank: the image does not depend on which rank finalises which slice. */
 #define PTB_IPC_HANDLE_BYTES 64
 typedef struct ptb_peer ptb_peer;
 int ptb_peer_create(ptb_ctx* ctx, int rank, int world, int32_t max_width, int32_t max_height, ptb_peer** out);
 void ptb_peer_destroy(ptb_peer* p);
-int ptb_peer_handles(ptb_peer* p, unsigned char accum_handle[PTB_IPC_HANDLE_BYTES], unsigned char image_handle[PTB_IPC_HANDLE_BYTES]);
+int ptb_peer_handles(ptb_peer* p, unsigned char accum_handle[PTB_IPC_HANDLE_BYTES], unsigned char image_handle[PTB_IPC_HANDLE_BYTES],
+                     unsigned char flags_handle[PTB_IPC_HANDLE_BYTES]);
 int ptb_peer_connect(ptb_peer* p, const unsigned char* accum_handles /* world x 64 bytes, in rank order */,
-                     const unsigned char* root_image_handle /* rank 0's image handle */);
-void* ptb_peer_accum(ptb_peer* p);                 /* device pointer: this rank's width*height*3 float sums */
+                     const unsigned char* root_image_handle /* rank 0's image handle */,
+                     const unsigned char* flags_handles /* world x 64 bytes, in rank order */);
+int ptb_peer_status(ptb_peer* p);                  /* PTB_OK, or PTB_ERR_CUDA when a wait of the exchange timed out */
+void* ptb_peer_accum(ptb_peer* p);                 /* device pointer: this rank's width*height*3 float sums of the NEXT frame (two buffers
+                                                      alternate, so ranks may run a frame apart): ask again before every frame */
 void* ptb_peer_image(ptb_peer* p);                 /* device pointer on rank 0 (NULL elsewhere): width*height*4 bytes */
 int ptb_peer_slice(const ptb_peer* p, int32_t width, int32_t height, int64_t* begin, int64_t* end);   /* pixel range this rank finalises */
 int ptb_peer_reduce_finalize(ptb_peer* p, int32_t width, int32_t height, int32_t spp_total, void* stream);

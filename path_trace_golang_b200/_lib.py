@@ -122,8 +122,9 @@ SYMBOLS = {
     "ptb_multi_last_timing": (C.c_int, [C.c_void_p, _dp, _dp]),
     "ptb_peer_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]),
     "ptb_peer_destroy": (None, [C.c_void_p]),
-    "ptb_peer_handles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "ptb_peer_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ptb_peer_handles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ptb_peer_connect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "ptb_peer_status": (C.c_int, [C.c_void_p]),
     "ptb_peer_accum": (C.c_void_p, [C.c_void_p]),
     "ptb_peer_image": (C.c_void_p, [C.c_void_p]),
     "ptb_peer_slice": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),

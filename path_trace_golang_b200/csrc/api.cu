@@ -1276,6 +1276,8 @@ struct ptb_peer {
     uint8_t* root_image = nullptr;            // this process's mapping of rank 0's image
     std::vector<void*> opened;                // cudaIpcOpenMemHandle mappings to close
     const float** d_ptrs = nullptr;           // device copy of accum_of
+    unsigned* d_flags = nullptr;              // this rank's flag block (exported): 2 x world words + [2 world] CTA counter + [2 world + 1] error
+    PeerSync sync{};                          // flags_of[k]: mapping of rank k's flag block
     bool connected = false;
 };
 
@@ -1289,10 +1291,18 @@ int ptb_peer_create(ptb_ctx* c, int rank, int world, int32_t max_width, int32_t 
     auto* p = new ptb_peer();
     p->ctx = c; p->rank = rank; p->world = world;
     p->max_pix = ((size_t)max_width * max_height + 3) / 4 * 4;
-    cudaError_t e = cudaMalloc((void**)&p->d_accum, p->max_pix * 3 * sizeof(float));
+    cudaError_t e = cudaMalloc((void**)&p->d_accum, 2 * p->max_pix * 3 * sizeof(float));      // two buffers: frame parity
     if (e == cudaSuccess && rank == 0) e = cudaMalloc((void**)&p->d_image, p->max_pix * 4);
     if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_ptrs, sizeof(float*) * world);
-    if (e != cudaSuccess) { cudaFree(p->d_accum); cudaFree(p->d_image); cudaFree((void*)p->d_ptrs); delete p; return fail(c, PTB_ERR_CUDA, "ptb_peer_create: %s", cudaGetErrorString(e)); }
+    if (e == cudaSuccess) e = cudaMalloc((void**)&p->d_flags, sizeof(unsigned) * (2 * kMaxPeers + 8));
+    if (e == cudaSuccess) e = cudaMemset(p->d_flags, 0, sizeof(unsigned) * (2 * kMaxPeers + 8));
+    if (e != cudaSuccess || world > kMaxPeers) {
+        cudaFree(p->d_accum); cudaFree(p->d_image); cudaFree((void*)p->d_ptrs); cudaFree(p->d_flags); delete p;
+        return world > kMaxPeers ? fail(c, PTB_ERR_LIMIT, "at most %d ranks per peer group", kMaxPeers) : fail(c, PTB_ERR_CUDA, "ptb_peer_create: %s", cudaGetErrorString(e));
+    }
+    p->sync.rank = rank; p->sync.world = world; p->sync.seq = 0;
+    p->sync.flags_of[rank] = p->d_flags;
+    p->sync.block_counter = p->d_flags + 2 * kMaxPeers; p->sync.error = p->d_flags + 2 * kMaxPeers + 1;
     p->accum_of.assign(world, nullptr);
     p->accum_of[rank] = p->d_accum;
     if (rank == 0) p->root_image = p->d_image;
@@ -1309,12 +1319,13 @@ void ptb_peer_destroy(ptb_peer* p) {
     cudaSetDevice(p->ctx->device);
     cudaDeviceSynchronize();
     for (void* m : p->opened) cudaIpcCloseMemHandle(m);
-    cudaFree(p->d_accum); cudaFree(p->d_image); cudaFree((void*)p->d_ptrs);
+    cudaFree(p->d_accum); cudaFree(p->d_image); cudaFree((void*)p->d_ptrs); cudaFree(p->d_flags);
     delete p;
 }
 
-int ptb_peer_handles(ptb_peer* p, unsigned char accum_handle[PTB_IPC_HANDLE_BYTES], unsigned char image_handle[PTB_IPC_HANDLE_BYTES]) {
-    if (!p || !accum_handle || !image_handle) return PTB_ERR_INVALID;
+int ptb_peer_handles(ptb_peer* p, unsigned char accum_handle[PTB_IPC_HANDLE_BYTES], unsigned char image_handle[PTB_IPC_HANDLE_BYTES],
+                     unsigned char flags_handle[PTB_IPC_HANDLE_BYTES]) {
+    if (!p || !accum_handle || !image_handle || !flags_handle) return PTB_ERR_INVALID;
     static_assert(sizeof(cudaIpcMemHandle_t) == PTB_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t is 64 bytes");
     ptb_ctx* c = p->ctx;
     std::lock_guard<std::mutex> lk(c->mu);
@@ -1324,11 +1335,13 @@ int ptb_peer_handles(ptb_peer* p, unsigned char accum_handle[PTB_IPC_HANDLE_BYTE
     std::memcpy(accum_handle, &h, sizeof h);
     std::memset(image_handle, 0, PTB_IPC_HANDLE_BYTES);
     if (p->rank == 0) { CK(c, cudaIpcGetMemHandle(&h, p->d_image)); std::memcpy(image_handle, &h, sizeof h); }
+    CK(c, cudaIpcGetMemHandle(&h, p->d_flags));
+    std::memcpy(flags_handle, &h, sizeof h);
     return PTB_OK;
 }
 
-int ptb_peer_connect(ptb_peer* p, const unsigned char* accum_handles, const unsigned char* root_image_handle) {
-    if (!p || !accum_handles || !root_image_handle) return PTB_ERR_INVALID;
+int ptb_peer_connect(ptb_peer* p, const unsigned char* accum_handles, const unsigned char* root_image_handle, const unsigned char* flags_handles) {
+    if (!p || !accum_handles || !root_image_handle || !flags_handles) return PTB_ERR_INVALID;
     ptb_ctx* c = p->ctx;
     std::lock_guard<std::mutex> lk(c->mu);
     CK(c, cudaSetDevice(c->device));
@@ -1341,6 +1354,11 @@ int ptb_peer_connect(ptb_peer* p, const unsigned char* accum_handles, const unsi
         CK(c, cudaIpcOpenMemHandle(&m, h, cudaIpcMemLazyEnablePeerAccess));
         p->opened.push_back(m);
         p->accum_of[k] = (const float*)m;
+        std::memcpy(&h, flags_handles + (size_t)k * PTB_IPC_HANDLE_BYTES, sizeof h);
+        m = nullptr;
+        CK(c, cudaIpcOpenMemHandle(&m, h, cudaIpcMemLazyEnablePeerAccess));
+        p->opened.push_back(m);
+        p->sync.flags_of[k] = (unsigned*)m;
     }
     if (p->rank != 0) {
         cudaIpcMemHandle_t h;
@@ -1355,7 +1373,9 @@ int ptb_peer_connect(ptb_peer* p, const unsigned char* accum_handles, const unsi
     return PTB_OK;
 }
 
-void* ptb_peer_accum(ptb_peer* p) { return p ? p->d_accum : nullptr; }
+void* ptb_peer_accum(ptb_peer* p) {     // the buffer of the NEXT frame (frames alternate between the two halves of the allocation)
+    return p ? p->d_accum + (size_t)((p->sync.seq + 1u) & 1u) * p->max_pix * 3 : nullptr;
+}
 void* ptb_peer_image(ptb_peer* p) { return p ? p->d_image : nullptr; }
 
 int ptb_peer_slice(const ptb_peer* p, int32_t width, int32_t height, int64_t* begin, int64_t* end) {
@@ -1377,8 +1397,21 @@ int ptb_peer_reduce_finalize(ptb_peer* p, int32_t width, int32_t height, int32_t
     CK(c, cudaSetDevice(c->device));
     int64_t b = 0, e = 0;
     ptb_peer_slice(p, width, height, &b, &e);
-    int rc = launch_reduce_finalize_slice(p->d_ptrs, p->world, b, e, spp_total, p->root_image, stream);
+    p->sync.seq += 1;                      // every rank calls this once per frame, in the same order
+    const size_t buf_off = (size_t)(p->sync.seq & 1u) * p->max_pix * 3;
+    int rc = launch_reduce_finalize_slice(p->d_ptrs, buf_off, p->world, b, e, spp_total, p->root_image, p->sync, stream);
     if (rc) return fail(c, PTB_ERR_CUDA, "reduce_finalize_slice launch: %s", cudaGetErrorString((cudaError_t)rc));
+    return PTB_OK;
+}
+
+int ptb_peer_status(ptb_peer* p) {
+    if (!p) return PTB_ERR_INVALID;
+    ptb_ctx* c = p->ctx;
+    std::lock_guard<std::mutex> lk(c->mu);
+    CK(c, cudaSetDevice(c->device));
+    unsigned err = 0;
+    CK(c, cudaMemcpy(&err, p->sync.error, sizeof err, cudaMemcpyDeviceToHost));
+    if (err) return fail(c, PTB_ERR_CUDA, "peer exchange: a rank did not signal within the time-out");
     return PTB_OK;
 }
 

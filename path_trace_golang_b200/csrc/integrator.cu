@@ -644,33 +644,75 @@ __global__ void finalize_peers_kernel(const float* const* __restrict__ bufs, int
 // [p_begin, p_end) of all ranks' buffers — its own from HBM, the others through NVLink peer loads (CUDA IPC mappings) — and
 // stores the finalised RGBA8 pixels straight into rank 0's image, again over NVLink: reduce-scatter, epilogue and gather in
 // one kernel, every link of the switch carrying 1/N of the traffic instead of everything converging on rank 0.
+// The cross-rank ordering is part of the kernel as well (no collective library call per frame): PeerSync::flags_of[k] is rank
+// k's flag block (2 x world words, mapped on every rank); a rank announces "my sums of frame `seq` are complete" by storing seq
+// into word [rank] of every rank's block, waits for all world announcements in its OWN block, reduces, and — its last CTA —
+// stores seq into word [world + rank] of every block: "my slice of the image is written and I no longer read anybody's sums".
 // p_begin is a multiple of 4 (3 x 16-byte loads per 4 pixels and buffer).  Sum order: rank 0, 1, 2, ... on every rank.
-__global__ void reduce_finalize_slice_kernel(const float* const* __restrict__ bufs, int n_bufs, long long p_begin, long long p_end, double inv_spp,
-                                             uchar4* __restrict__ rgba_root) {
-    const long long p0 = p_begin + 4ll * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
-    if (p0 >= p_end) return;
-    if (p0 + 4 <= p_end) {
-        float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
-        for (int k = 0; k < n_bufs; ++k) {
-            const float4* src = reinterpret_cast<const float4*>(bufs[k] + 3 * p0);
-            const float4 x = src[0], y = src[1], z = src[2];
-            a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
-            b.x += y.x; b.y += y.y; b.z += y.z; b.w += y.w;
-            c.x += z.x; c.y += z.y; c.z += z.z; c.w += z.w;
+__device__ __forceinline__ bool peer_wait_all(const volatile unsigned* flags, int world, unsigned seq) {
+    const long long t0 = clock64();
+    for (int k = 0; k < world; ++k)
+        while ((int)(flags[k] - seq) < 0)                                  // (sequence numbers only grow)
+            if (clock64() - t0 > 8000000000ll) return false;                // ~4 s: a rank died; do not hang the device
+    return true;
+}
+
+__global__ void reduce_finalize_slice_kernel(const float* const* __restrict__ bufs, size_t buf_off, int n_bufs, long long p_begin, long long p_end, double inv_spp,
+                                             uchar4* __restrict__ rgba_root, PeerSync sync) {
+    if (sync.world > 1) {
+        if (blockIdx.x == 0 && (int)threadIdx.x < sync.world) {
+            __threadfence_system();                                         // (the integrator's sums: written by the previous kernel of this stream)
+            *(volatile unsigned*)(sync.flags_of[threadIdx.x] + sync.rank) = sync.seq;
         }
-        uint4 o;   // 4 pixels = one 16-byte store
-        o.x = (uint32_t)to_u8(a.x, inv_spp) | (uint32_t)to_u8(a.y, inv_spp) << 8 | (uint32_t)to_u8(a.z, inv_spp) << 16 | 0xFF000000u;
-        o.y = (uint32_t)to_u8(a.w, inv_spp) | (uint32_t)to_u8(b.x, inv_spp) << 8 | (uint32_t)to_u8(b.y, inv_spp) << 16 | 0xFF000000u;
-        o.z = (uint32_t)to_u8(b.z, inv_spp) | (uint32_t)to_u8(b.w, inv_spp) << 8 | (uint32_t)to_u8(c.x, inv_spp) << 16 | 0xFF000000u;
-        o.w = (uint32_t)to_u8(c.y, inv_spp) | (uint32_t)to_u8(c.z, inv_spp) << 8 | (uint32_t)to_u8(c.w, inv_spp) << 16 | 0xFF000000u;
-        *reinterpret_cast<uint4*>(rgba_root + p0) = o;
-    } else {
-        for (long long p = p0; p < p_end; ++p) {
-            float r = 0, g = 0, bb = 0;
-            for (int k = 0; k < n_bufs; ++k) { const float* s = bufs[k] + 3 * p; r += s[0]; g += s[1]; bb += s[2]; }
-            rgba_root[p] = make_uchar4(to_u8(r, inv_spp), to_u8(g, inv_spp), to_u8(bb, inv_spp), 255);
+        __shared__ int ok;
+        if (threadIdx.x == 0) ok = peer_wait_all(sync.flags_of[sync.rank], sync.world, sync.seq) ? 1 : 0;
+        __syncthreads();
+        if (!ok) { if (threadIdx.x == 0) *sync.error = 1u; return; }
+        __threadfence_system();
+    }
+    const long long p0 = p_begin + 4ll * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    if (p0 < p_end) {
+        if (p0 + 4 <= p_end) {
+            float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
+            for (int k = 0; k < n_bufs; ++k) {
+                const float4* src = reinterpret_cast<const float4*>(bufs[k] + buf_off + 3 * p0);
+                const float4 x = __ldcv(src), y = __ldcv(src + 1), z = __ldcv(src + 2);   // (peer memory: never from a stale cache line)
+                a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+                b.x += y.x; b.y += y.y; b.z += y.z; b.w += y.w;
+                c.x += z.x; c.y += z.y; c.z += z.z; c.w += z.w;
+            }
+            uint4 o;   // 4 pixels = one 16-byte store
+            o.x = (uint32_t)to_u8(a.x, inv_spp) | (uint32_t)to_u8(a.y, inv_spp) << 8 | (uint32_t)to_u8(a.z, inv_spp) << 16 | 0xFF000000u;
+            o.y = (uint32_t)to_u8(a.w, inv_spp) | (uint32_t)to_u8(b.x, inv_spp) << 8 | (uint32_t)to_u8(b.y, inv_spp) << 16 | 0xFF000000u;
+            o.z = (uint32_t)to_u8(b.z, inv_spp) | (uint32_t)to_u8(b.w, inv_spp) << 8 | (uint32_t)to_u8(c.x, inv_spp) << 16 | 0xFF000000u;
+            o.w = (uint32_t)to_u8(c.y, inv_spp) | (uint32_t)to_u8(c.z, inv_spp) << 8 | (uint32_t)to_u8(c.w, inv_spp) << 16 | 0xFF000000u;
+            *reinterpret_cast<uint4*>(rgba_root + p0) = o;
+        } else {
+            for (long long p = p0; p < p_end; ++p) {
+                float r = 0, g = 0, bb = 0;
+                for (int k = 0; k < n_bufs; ++k) { const float* s = bufs[k] + buf_off + 3 * p; r += __ldcv(s); g += __ldcv(s + 1); bb += __ldcv(s + 2); }
+                rgba_root[p] = make_uchar4(to_u8(r, inv_spp), to_u8(g, inv_spp), to_u8(bb, inv_spp), 255);
+            }
         }
     }
+    if (sync.world > 1) {                       // last CTA of the grid: this rank's slice is in rank 0's image
+        __threadfence_system();
+        __syncthreads();
+        __shared__ unsigned last;
+        if (threadIdx.x == 0) last = atomicAdd(sync.block_counter, 1u) == gridDim.x - 1 ? 1u : 0u;
+        __syncthreads();
+        if (last) {
+            if (threadIdx.x == 0) *sync.block_counter = 0u;
+            if ((int)threadIdx.x < sync.world) *(volatile unsigned*)(sync.flags_of[threadIdx.x] + sync.world + sync.rank) = sync.seq;
+        }
+    }
+}
+
+// Stream-ordered wait for "every rank has finished frame `seq`".  The sums are double-buffered by frame parity, so a rank only
+// has to know that frame seq - 1 is finished everywhere before it renders frame seq + 1 into the same buffer — the ranks may
+// drift apart by a frame instead of marching in lock-step — while rank 0 waits for frame seq itself before it reads the image.
+__global__ void peer_wait_done_kernel(PeerSync sync, unsigned seq) {
+    if (threadIdx.x == 0 && !peer_wait_all(sync.flags_of[sync.rank] + sync.world, sync.world, seq)) *sync.error = 1u;
 }
 
 // FP32 FMA throughput probe: 8 independent chains per thread, 2 flop per FMA.
@@ -865,12 +907,17 @@ int launch_finalize_peers(const float* const* d_bufs_on_dev0, int n_bufs, int wi
     return (int)cudaGetLastError();
 }
 
-int launch_reduce_finalize_slice(const float* const* d_bufs, int n_bufs, long long p_begin, long long p_end, int spp_total, uint8_t* rgba_root, void* stream) {
-    if (p_end <= p_begin) return 0;
-    const long long groups = (p_end - p_begin + 3) / 4;
+int launch_reduce_finalize_slice(const float* const* d_bufs, size_t buf_off, int n_bufs, long long p_begin, long long p_end, int spp_total, uint8_t* rgba_root,
+                                 const PeerSync& sync, void* stream) {
+    // (an empty slice still takes part in the flag protocol: one CTA)
+    const long long groups = p_end > p_begin ? (p_end - p_begin + 3) / 4 : 1;
     const int threads = 256;
-    reduce_finalize_slice_kernel<<<(unsigned)((groups + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(d_bufs, n_bufs, p_begin, p_end, 1.0 / (double)spp_total,
-                                                                                                                   reinterpret_cast<uchar4*>(rgba_root));
+    reduce_finalize_slice_kernel<<<(unsigned)((groups + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(d_bufs, buf_off, n_bufs, p_begin, p_end > p_begin ? p_end : p_begin,
+                                                                                                                   1.0 / (double)spp_total, reinterpret_cast<uchar4*>(rgba_root), sync);
+    if (sync.world > 1) {
+        const unsigned need = sync.rank == 0 ? sync.seq : sync.seq - 1u;        // (seq >= 1; "frame 0" is finished by definition)
+        peer_wait_done_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(sync, need);
+    }
     return (int)cudaGetLastError();
 }
 

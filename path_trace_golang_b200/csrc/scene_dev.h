@@ -185,7 +185,18 @@ int launch_finalize(const float* accum, int width, int height, int spp_total, ui
 int launch_primary_hits(const Obj64* d_world, int n_obj, const float4* bvh_nodes, const float4* bvh_tris, const Camera64& cam,
                         int width, int height, double xi_u, double xi_v, int32_t* d_ids, double* d_t, void* stream);
 int launch_finalize_peers(const float* const* d_bufs_on_dev0, int n_bufs, int width, int height, int spp_total, uint8_t* rgba, void* stream);
-int launch_reduce_finalize_slice(const float* const* d_bufs, int n_bufs, long long p_begin, long long p_end, int spp_total, uint8_t* rgba_root, void* stream);
+// Cross-rank flags of the multi-process exchange (ptb_peer_*): flags_of[k] = this process's mapping of rank k's flag block,
+// 2 x world words: [j] "rank j's sums of frame seq are complete", [world + j] "rank j has written its slice of frame seq".
+constexpr int kMaxPeers = 16;
+struct PeerSync {
+    unsigned* flags_of[kMaxPeers];
+    unsigned* block_counter;     // local: CTAs of the slice kernel that have finished
+    unsigned* error;             // local: set when a wait timed out
+    int rank, world;
+    unsigned seq;                // frame sequence number (1, 2, ...)
+};
+int launch_reduce_finalize_slice(const float* const* d_bufs, size_t buf_off, int n_bufs, long long p_begin, long long p_end, int spp_total, uint8_t* rgba_root,
+                                 const PeerSync& sync, void* stream);
 int launch_finalize_planes(const float* planes, int split_k, int width, int height, int spp_total, float* accum, int accum_resume, uint8_t* rgba, void* stream);
 int wf_split_factor(int sm_count, long long n_pix, int n_samples);   // split_k the wavefront launcher wants for this frame
 int launch_fma_peak(float* d_out, int blocks, int threads, int iters, void* stream);

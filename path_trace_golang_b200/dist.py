@@ -113,8 +113,8 @@ def render_rows_distributed(ctx, cfg_full, group=None, to_all: bool = False):
 
 
 # ---- the fused exchange (default on GPUs): ONE kernel per rank does reduce-scatter + pixel epilogue + gather over NVLink peer
-# memory (ptb_peer_*, include/ptb200.h).  torch.distributed is the plumbing only: it carries the 64-byte CUDA IPC handles once
-# and provides the stream-ordered barriers (4-byte all-reduces) around the kernel.
+# memory, cross-rank ordering included (flag words in peer memory; ptb_peer_*, include/ptb200.h).  torch.distributed is the
+# plumbing only: it carries the 64-byte CUDA IPC handles ONCE; no collective runs per frame.
 
 class _DevPtr:
     """A raw device pointer dressed up for torch.as_tensor (CUDA array interface)."""
@@ -138,17 +138,17 @@ class PeerGroup:
         ctx._check(self._L.ptb_peer_create(ctx._h, self.rank, self.world, self.max_width, self.max_height, C.byref(h)))
         self._h = h
         dev = torch.device("cuda", ctx.device)
-        self._token = torch.zeros(1, dtype=torch.int32, device=dev)
         if self.world > 1:
-            mine = (C.c_ubyte * 128)()
-            ctx._check(self._L.ptb_peer_handles(self._h, mine, C.byref(mine, 64)))
+            mine = (C.c_ubyte * 192)()
+            ctx._check(self._L.ptb_peer_handles(self._h, mine, C.byref(mine, 64), C.byref(mine, 128)))
             t = torch.tensor(list(mine), dtype=torch.uint8, device=dev)
-            allh = torch.empty(self.world * 128, dtype=torch.uint8, device=dev)
+            allh = torch.empty(self.world * 192, dtype=torch.uint8, device=dev)
             dist.all_gather_into_tensor(allh, t, group=group)
-            allh = allh.cpu().numpy().reshape(self.world, 128)
+            allh = allh.cpu().numpy().reshape(self.world, 192)
             accum = (C.c_ubyte * (64 * self.world))(*allh[:, :64].reshape(-1).tolist())
-            image = (C.c_ubyte * 64)(*allh[0, 64:].tolist())
-            ctx._check(self._L.ptb_peer_connect(self._h, accum, image))
+            image = (C.c_ubyte * 64)(*allh[0, 64:128].tolist())
+            flags = (C.c_ubyte * (64 * self.world))(*allh[:, 128:].reshape(-1).tolist())
+            ctx._check(self._L.ptb_peer_connect(self._h, accum, image, flags))
             dist.barrier(group=group)                      # nobody renders before every mapping exists
 
     def close(self):
@@ -173,15 +173,14 @@ class PeerGroup:
             return None
         return torch.as_tensor(_DevPtr(int(p), (height, width, 4), "|u1"), device=torch.device("cuda", self._ctx.device))
 
-    def _barrier(self):
-        if self.world > 1:
-            dist.all_reduce(self._token, group=self._group)   # stream-ordered: completes when every rank's stream got here
-
     def reduce_finalize(self, width: int, height: int, spp_total: int, stream: int = 0):
-        """Every rank's sums are complete on its stream -> barrier -> fused slice kernel -> barrier (rank 0 owns the image)."""
-        self._barrier()
+        """Stream-ordered behind this rank's render: announce it, wait for every rank's announcement, reduce + finalise + store this
+        rank's slice, wait until every rank has done so (all of it inside the library's kernels: flag words in peer memory)."""
         self._ctx._check(self._L.ptb_peer_reduce_finalize(self._h, int(width), int(height), int(spp_total), stream))
-        self._barrier()
+
+    def check(self):
+        """Raises if a wait of the exchange timed out (a rank never arrived)."""
+        self._ctx._check(self._L.ptb_peer_status(self._h))
 
 
 def render_distributed_peer(ctx, cfg_full, peers: PeerGroup):

@@ -236,6 +236,34 @@ def test_gpu_bvh_is_reused_for_identical_meshes(ctx):
     assert ctx.bvh_info()["n_triangles"] == 0
 
 
+@pytest.mark.gpu
+def test_gpu_mesh_generation_skips_the_triangles_and_pipeline_matches(ctx, monkeypatch):
+    """(1) ptb_scene.mesh_generation: the host mirror stamps every flattened scene with the identity of its mesh data, so the
+    second upload of an unchanged Scene reuses the BVH without hashing the triangles, and a scene whose triangles differ gets
+    another generation and another BVH.  (2) The mesh pipeline (wavefront across kernels, PTB_MESH_PIPELINE=1 — an alternative
+    to the in-kernel traversal kept for A/B) renders the same per-pixel sums bit for bit: same helpers, same
+    per-slot sample order."""
+    from path_trace_golang_b200 import scene
+    sc = scene.Parse(json.dumps(with_heightfield("test_comprehensive", 200, 150, pos=(0, 1.2, 2), size=(14, 2.5, 10))))
+    assert sc.flat().mesh_generation != 0 and sc.flat().mesh_generation == sc.flat().mesh_generation
+    other = scene.Parse(json.dumps(with_heightfield("test_comprehensive", 200, 150, pos=(0, 1.2, 2), size=(14, 2.5, 10), seed=5)))
+    assert other.flat().mesh_generation != sc.flat().mesh_generation
+    ctx.upload(sc)
+    first = ctx.bvh_info()
+    ctx.upload(sc)
+    assert ctx.bvh_info() == first
+    cfg = ctx.cfg(480, 270, 3, 10, seed=2)
+    a = ctx.render_accum(cfg)
+    assert ctx.last_kernel().startswith("integrate_wf_kernel<0, 1")
+    monkeypatch.setenv("PTB_MESH_PIPELINE", "1")
+    b = ctx.render_accum(cfg)
+    assert ctx.last_kernel().startswith("mp_shade_scan_kernel")
+    monkeypatch.delenv("PTB_MESH_PIPELINE")
+    assert (a == b).all()
+    ctx.render_accum(ctx.cfg(480, 270, 3, 10, seed=2, stats=True))
+    assert ctx.stats()["bvh_stack_overflows"] == 0 and ctx.stats()["bvh_nodes_visited"] > 0
+
+
 def test_bvh_builder_selfcheck_cpu():
     """Host-only: the emitted node array is sound — every child box (centre / half extent, binary32) contains all the
     triangles below it, every triangle is in exactly one leaf (ptb_bvh_selfcheck, no CUDA involved)."""

@@ -30,8 +30,8 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     ctx = engine.Context(local)
     out = {"world": world, "cases": []}
-    peers = pdist.PeerGroup(ctx, 1920, 1080)
-    for name, W, H, spp, depth in [("metal_glass_room", 1920, 1080, 32, 16), ("test_scene", 333, 211, 7, 10), ("example_simple", 64, 64, 1, 8)]:
+    peers = pdist.PeerGroup(ctx, 3840, 2160)
+    for name, W, H, spp, depth in [("metal_glass_room", 3840, 2160, 8, 16), ("metal_glass_room", 1920, 1080, 32, 16), ("test_scene", 333, 211, 7, 10), ("example_simple", 64, 64, 1, 8)]:
         sc = scene.Load(ROOT / "scenes" / f"{name}.json")
         ctx.upload(sc)
         cfg = ctx.cfg(W, H, spp, depth, seed=9)
@@ -49,14 +49,34 @@ def main():
             pdist.render_distributed_peer(ctx, cfg, peers)
         torch.cuda.synchronize()
         t_peer = (time.perf_counter() - t0) / 5
+        # the exchange alone (ranks aligned by a barrier first): fused peer kernel vs NCCL reduce + epilogue on rank 0
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        acc = torch.zeros((H, W, 3), dtype=torch.float32, device=dev)
+        rgba = torch.empty((H, W, 4), dtype=torch.uint8, device=dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        t_ex_peer = t_ex_reduce = 0.0
+        for _ in range(5):
+            torch.cuda.synchronize(); dist.barrier()
+            ev[0].record(); peers.reduce_finalize(W, H, spp, stream); ev[1].record()
+            torch.cuda.synchronize(); dist.barrier()
+            ev[2].record(); pdist.reduce_to_root(acc)
+            if rank == 0:
+                ctx.finalize_device(acc.data_ptr(), W, H, spp, rgba.data_ptr(), stream)
+            ev[3].record()
+            torch.cuda.synchronize()
+            t_ex_peer, t_ex_reduce = ev[0].elapsed_time(ev[1]), ev[2].elapsed_time(ev[3])
+        tt = torch.tensor([t_ex_peer, t_ex_reduce], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_ex_peer, t_ex_reduce = tt.tolist()
         if rank == 0:
             img_red = img_red.cpu().numpy()
             one = ctx.render(cfg)
             d = lambda a, b: int(np.abs(a.astype(np.int16) - b.astype(np.int16)).max())
             frac = lambda a, b: float((a != b).any(axis=2).mean())
             out["cases"].append({"scene": name, "size": [W, H, spp], "peer_vs_one_max": d(img_peer, one), "peer_vs_one_frac": frac(img_peer, one),
-                                 "peer_vs_scatter_max": d(img_peer, img_sc), "peer_vs_reduce_max": d(img_peer, img_red), "peer_ms": t_peer * 1e3,
+                                 "peer_vs_scatter_max": d(img_peer, img_sc), "peer_vs_reduce_max": d(img_peer, img_red), "peer_ms": t_peer * 1e3, "exchange_only_peer_ms": t_ex_peer, "exchange_only_nccl_reduce_ms": t_ex_reduce,
                                  "alpha_ok": bool((img_peer[..., 3] == 255).all())})
+    peers.check()
     peers.close()
     dist.barrier()
     if rank == 0 and torch.cuda.device_count() >= 2:
