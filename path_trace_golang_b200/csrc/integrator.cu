@@ -674,9 +674,12 @@ __global__ void reduce_finalize_slice_kernel(const float* const* __restrict__ bu
     if (p0 < p_end) {
         if (p0 + 4 <= p_end) {
             float4 a = make_float4(0, 0, 0, 0), b = a, c = a;
+            // (plain loads: this kernel has not touched the peers' sums before their "complete" flags arrived, and L1 does not
+            // outlive a kernel, so no stale line can be read; the loop is unrolled to keep many NVLink reads in flight per thread)
+#pragma unroll 4
             for (int k = 0; k < n_bufs; ++k) {
                 const float4* src = reinterpret_cast<const float4*>(bufs[k] + buf_off + 3 * p0);
-                const float4 x = __ldcv(src), y = __ldcv(src + 1), z = __ldcv(src + 2);   // (peer memory: never from a stale cache line)
+                const float4 x = src[0], y = src[1], z = src[2];
                 a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
                 b.x += y.x; b.y += y.y; b.z += y.z; b.w += y.w;
                 c.x += z.x; c.y += z.y; c.z += z.z; c.w += z.w;
@@ -690,7 +693,7 @@ __global__ void reduce_finalize_slice_kernel(const float* const* __restrict__ bu
         } else {
             for (long long p = p0; p < p_end; ++p) {
                 float r = 0, g = 0, bb = 0;
-                for (int k = 0; k < n_bufs; ++k) { const float* s = bufs[k] + buf_off + 3 * p; r += __ldcv(s); g += __ldcv(s + 1); bb += __ldcv(s + 2); }
+                for (int k = 0; k < n_bufs; ++k) { const float* s = bufs[k] + buf_off + 3 * p; r += s[0]; g += s[1]; bb += s[2]; }
                 rgba_root[p] = make_uchar4(to_u8(r, inv_spp), to_u8(g, inv_spp), to_u8(bb, inv_spp), 255);
             }
         }
