@@ -219,7 +219,9 @@ int ptb_host_buffer_unpin(ptb_ctx* ctx, void* p);
 int ptb_render_accum(ptb_ctx* ctx, const ptb_cfg* cfg, float* rgb_sum);
 /* ... or asynchronously into DEVICE memory on a caller-supplied CUDA stream (cudaStream_t passed as
  * void*, used exactly as given: NULL is the CUDA default stream, which is also PyTorch's default
- * stream).  This is what a multi-GPU caller reduces with NCCL. */
+ * stream).  This is what a multi-GPU caller hands to the exchange (ptb_peer_* below, or NCCL).  (With the environment
+ * variable PTB_MESH_PIPELINE set, scenes with meshes are rendered by a multi-kernel pipeline driven from the host: the call
+ * then returns when the frame is complete.) */
 int ptb_render_accum_device(ptb_ctx* ctx, const ptb_cfg* cfg, void* d_rgb_sum, void* stream);
 /* Checkpointable rendering (the reference persists only scenes and PNGs, util.go:45-55; a long render on a GPU backend
  * wants to survive a restart): renders samples [sample_begin, sample_begin + sample_count) of cfg CONTINUING the sums

@@ -61,7 +61,7 @@ struct ptb_ctx {
     BvhNode* d_bvh_nodes = nullptr;      // EXTENSION: mesh BVH
     BvhTri* d_bvh_tris = nullptr;
     float* d_planes = nullptr; size_t planes_cap = 0;   // partial-sum planes of split (small) frames
-    int* d_trav = nullptr; size_t trav_cap = 0;   // suspended-traversal scratch (persistent kernel with in-kernel traversal: PTB_MESH_PERSISTENT)
+    int* d_trav = nullptr; size_t trav_cap = 0;   // suspended-traversal scratch of the in-kernel traversal (the default for mesh scenes)
     MeshPipe mesh_pipe;                           // mesh scenes: global path state + ray queue of the wavefront across kernels
     BvhNode* d_bvh_nodes_keep = nullptr; // last built BVH, reused when the same triangles are uploaded again
     BvhTri* d_bvh_tris_keep = nullptr;
