@@ -231,7 +231,7 @@ int plan_bound(const SplitPlan& p, int g) { return p.full_begin + (int)((unsigne
 // partition and a progressive render group every pixel's samples exactly like one launch does
 SplitPlan make_plan(ptb_ctx* c, const ptb_cfg* cfg, int s0, int s1) {
     SplitPlan p;
-    int k = std::getenv("PTB_NO_SPLIT") ? 1 : wf_split_factor(c->prop.multiProcessorCount, (long long)cfg->width * cfg->height, s1 - s0);
+    int k = std::getenv("PTB_NO_SPLIT") ? 1 : wf_split_factor(c->prop.multiProcessorCount, (long long)cfg->width * rows_of(cfg), s1 - s0);
     if (const char* force = std::getenv("PTB_SPLIT")) { k = std::atoi(force); if (k < 1) k = 1; if (k > s1 - s0) k = s1 - s0; if (k > 64) k = 64; }   // tuning
     if ((cfg->flags & PTB_FLAG_MEGAKERNEL) || cfg->max_depth <= 0) k = 1;
     p.total = k; p.base = 0; p.count = k; p.full_begin = s0; p.full_end = s1;
@@ -304,7 +304,10 @@ int render_launch(ptb_ctx* c, const ptb_cfg* cfg, const SplitPlan& plan, float* 
             if (rc) return rc;
             fp.split_k = k; fp.planes = c->d_planes;
         }
-        c->last_kernel = std::string("integrate_wf_kernel<") + (stats ? "1, " : "0, ") + (c->d_bvh_nodes ? "1, " : "0, ") + (hs.big ? "1>" : "0>");
+        // sphere-rich scenes: the packed two-ray sphere test (PTB_PACKED=0/1 forces the choice: tests, tuning)
+        bool packed = hs.hdr.n_sphere_run >= kPackedSphereMin;
+        if (const char* force = std::getenv("PTB_PACKED")) packed = std::atoi(force) != 0;
+        c->last_kernel = std::string("integrate_wf_kernel<") + (stats ? "1, " : "0, ") + (c->d_bvh_nodes ? "1, " : "0, ") + (hs.big ? "1, " : "0, ") + (packed ? "1>" : "0>");
         if (mesh_pipeline) {
             MeshPipe& mp = c->mesh_pipe;
             const int n_slots = mesh_pool_slots(c->prop.multiProcessorCount, (long long)W * R * k);
@@ -324,7 +327,7 @@ int render_launch(ptb_ctx* c, const ptb_cfg* cfg, const SplitPlan& plan, float* 
             CK(c, cudaStreamWaitEvent(c->stream, c->ev_batch[0], 0));
             e = launch_mesh_pipeline(ka, stats, hs.big, c->prop.multiProcessorCount, &c->launch_cache, mp, c->stream);
         } else
-        e = launch_integrator_wf(ka, stats, hs.big, c->prop.multiProcessorCount, &c->launch_cache, stream);
+        e = launch_integrator_wf(ka, stats, hs.big, packed, c->prop.multiProcessorCount, &c->launch_cache, stream);
         if (!e && plan.total > 1) e = launch_finalize_planes(c->d_planes, k, W, R, cfg->samples_per_px, d_accum, resume ? 1 : 0, d_rgba, stream);
     }
     if (e) return fail(c, PTB_ERR_CUDA, "integrator launch: %s", cudaGetErrorString((cudaError_t)e));

@@ -229,6 +229,59 @@ __device__ __forceinline__ bool hit_plane(float4 lo, const RayK& r, float tmin, 
     t_out = t;
     return !(fabsf(r.d.y) < 1e-6f) && !(t < tmin || t > tmax);
 }
+// ---- two rays per instruction: sm_100a's packed binary32 arithmetic (PTX fma/add/mul.rn.f32x2 -> SASS FFMA2 / FADD2 / FMUL2 on
+// 64-bit register pairs).  The wavefront scan tests the TWO rays of a thread against every record, and the kernel is bound by
+// instruction issue (profiles/r02z: issue slots 80.7 % busy, FMA pipe 30 %): with half 0 of a pair = ray 0 and half 1 = ray 1 the
+// arithmetic of both rays issues once.  A record field is a scalar from the constant bank; `dup2` makes the pair (x, x), which
+// ptxas folds into the instruction as a broadcast uniform operand (URn.F32, negation included) — no extra moves.  Same roundings
+// as the scalar forms (each half is an ordinary round-to-nearest FFMA/FADD/FMUL).
+// A packed instruction runs at HALF the scalar rate (tools/probes/ffma2_probe.cu), so it frees issue slots, not FMA-pipe time.
+// Measured (profiles/r02t_packed.log, r02u_packed.log):
+//   * the sphere test (3-register FFMA/FADD/FMUL, then two square roots and the root selection): 141 instead of 192 instructions
+//     per 4 spheres x 2 rays; C5 (17 spheres) +5.3 %, C2 (11) +2.4 %, C4 +1.4 % — but C3 (2 spheres) -2.9 %: building the pairs
+//     costs more than two sphere tests save.  Hence a kernel instantiation of its own (PK), chosen per scene (kPackedSphereMin);
+//   * the slab test, whose scalar FFMAs take a uniform operand and already overlap with its min/max chain, loses when packed
+//     (116 instead of 149 instructions per 4 boxes x 2 rays, yet C3 -3 %): boxes stay scalar.
+typedef unsigned long long P2;
+__device__ __forceinline__ P2 pk2(float a, float b) { P2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ P2 dup2(float a) { return pk2(a, a); }
+__device__ __forceinline__ float lo2(P2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi2(P2 v) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ P2 fma2(P2 a, P2 b, P2 c) { P2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ P2 mul2(P2 a, P2 b) { P2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ P2 add2(P2 a, P2 b) { P2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ P2 sub2(P2 a, P2 b) { P2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// The per-ray constants the sphere test consumes, for a pair of rays: -o, d, -a, 1/a.
+struct RayP { P2 no[3], d[3], na, inv_a; };
+__device__ __forceinline__ RayP pair_rays(const RayK& r0, const RayK& r1) {
+    RayP p;
+    // Origin and direction arrive as scalars (one LDS.128 per ray).  Passing the pairs through one packed instruction (x + -0:
+    // exact) makes the PAIR the value ptxas keeps; otherwise it re-packs them from the scalars inside the sphere loop
+    // (two moves per operand per trip).
+    const P2 z = dup2(-0.0f);
+    p.no[0] = add2(pk2(-r0.o.x, -r1.o.x), z); p.no[1] = add2(pk2(-r0.o.y, -r1.o.y), z); p.no[2] = add2(pk2(-r0.o.z, -r1.o.z), z);
+    p.d[0] = add2(pk2(r0.d.x, r1.d.x), z); p.d[1] = add2(pk2(r0.d.y, r1.d.y), z); p.d[2] = add2(pk2(r0.d.z, r1.d.z), z);
+    p.na = pk2(-r0.a, -r1.a); p.inv_a = pk2(r0.inv_a, r1.inv_a);
+    return p;
+}
+// hit_sphere4 for two rays.  Works with c - o and -(o - c).d (exact negations of the scalar form's oc and hb, so the roots are
+// the same binary32 values): 13 packed instructions instead of 30 scalar ones; the two square roots and the root selection
+// stay per ray.
+__device__ __forceinline__ void hit_sphere_pair(float cx, float cy, float cz, float r2, const RayP& r, float tmin, const float (&tmax)[2],
+                                                float (&t_out)[2], bool (&hit)[2]) {
+    const P2 ox = add2(dup2(cx), r.no[0]), oy = add2(dup2(cy), r.no[1]), oz = add2(dup2(cz), r.no[2]);     // c - o
+    const P2 nhb = fma2(oz, r.d[2], fma2(oy, r.d[1], mul2(ox, r.d[0])));                                    // -hb
+    const P2 c = fma2(oz, oz, fma2(oy, oy, fma2(ox, ox, dup2(-r2))));
+    const P2 disc = fma2(nhb, nhb, mul2(r.na, c));
+    const P2 sq = pk2(sqrt_(lo2(disc)), sqrt_(hi2(disc)));
+    const P2 q1 = mul2(sub2(nhb, sq), r.inv_a), q2 = mul2(add2(nhb, sq), r.inv_a);
+    const float a0 = lo2(q1), a1 = hi2(q1);
+    const float root0 = (a0 >= tmin) ? a0 : lo2(q2), root1 = (a1 >= tmin) ? a1 : hi2(q2);
+    t_out[0] = root0; t_out[1] = root1;
+    hit[0] = root0 >= tmin && root0 <= tmax[0]; hit[1] = root1 >= tmin && root1 <= tmax[1];
+}
+
 // Object record as two 16-byte vectors: lo = (a.xyz, meta), hi = (b.xyz, world_idx).
 __device__ __forceinline__ float4 obj_lo(const DevObj* objs, int i) { return reinterpret_cast<const float4*>(objs + i)[0]; }
 __device__ __forceinline__ float4 obj_hi(const DevObj* objs, int i) { return reinterpret_cast<const float4*>(objs + i)[1]; }
@@ -753,17 +806,17 @@ size_t wf_trav_scratch_bytes(int sm_count) { return (size_t)sm_count * kMeshBloc
 // The opt-in to more than 48 KB of dynamic shared memory is a per-DEVICE attribute of the kernel and the occupancy depends on
 // the shared-memory size of the scene at hand, so both are remembered per context (= per device) and per size: a small
 // scene rendered first, a large one later, or several devices in one process all get the right attribute and grid.
-template <bool STATS, bool MESH, bool BIG>
+template <bool STATS, bool MESH, bool BIG, bool PK>
 static int launch_wf_variant(const KernelArgs& ka, size_t smem, int sm_count, LaunchCache::Entry& lc, cudaStream_t stream) {
     const FrameParams& fp = ka.fp;
     if (smem > 48 * 1024 && smem > lc.smem_optin) {
-        cudaError_t e = cudaFuncSetAttribute(integrate_wf_kernel<STATS, MESH, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(integrate_wf_kernel<STATS, MESH, BIG, PK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
         lc.smem_optin = smem;
     }
     if (lc.smem_occ != smem) {
         int nb = 0;
-        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, integrate_wf_kernel<STATS, MESH, BIG>, WF_THREADS, smem);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, integrate_wf_kernel<STATS, MESH, BIG, PK>, WF_THREADS, smem);
         if (e != cudaSuccess) return (int)e;
         lc.blocks_per_sm = nb > 0 ? nb : 1;
         lc.smem_occ = smem;
@@ -772,17 +825,18 @@ static int launch_wf_variant(const KernelArgs& ka, size_t smem, int sm_count, La
     long long grid = (long long)sm_count * (MESH && lc.blocks_per_sm > kMeshBlocksPerSm ? kMeshBlocksPerSm : lc.blocks_per_sm);   // trav_scratch is sized for kMeshBlocksPerSm
     const long long need = (n_pix * (fp.split_k > 1 ? fp.split_k : 1) + WF_SLOTS - 1) / WF_SLOTS;
     if (grid > need) grid = need;
-    integrate_wf_kernel<STATS, MESH, BIG><<<(unsigned)grid, WF_THREADS, smem, stream>>>(ka);
+    integrate_wf_kernel<STATS, MESH, BIG, PK><<<(unsigned)grid, WF_THREADS, smem, stream>>>(ka);
     return (int)cudaGetLastError();
 }
 
-int launch_integrator_wf(const KernelArgs& ka, bool stats, bool big, int sm_count, LaunchCache* cache, void* stream) {
+int launch_integrator_wf(const KernelArgs& ka, bool stats, bool big, bool packed, int sm_count, LaunchCache* cache, void* stream) {
     // BIG worlds read the object / material records in place (global memory): no shared-memory copy
     const size_t smem = ((sizeof(WfState) + 15) / 16 + (big ? 0 : (size_t)(ka.sc.n_obj * 2 + ka.sc.n_mat * 3))) * sizeof(uint4);
     cudaStream_t st = (cudaStream_t)stream;
     const bool mesh = ka.fp.bvh_nodes != nullptr;      // the mesh-free instantiation carries no traversal code (it costs ~10 %)
-    LaunchCache::Entry& lc = cache->wf[(stats ? 4 : 0) | (mesh ? 2 : 0) | (big ? 1 : 0)];
-#define PTB_WF_CASE(S, M, B) if (stats == S && mesh == M && big == B) return launch_wf_variant<S, M, B>(ka, smem, sm_count, lc, st);
+    LaunchCache::Entry& lc = cache->wf[(packed ? 8 : 0) | (stats ? 4 : 0) | (mesh ? 2 : 0) | (big ? 1 : 0)];
+#define PTB_WF_CASE(S, M, B) if (stats == S && mesh == M && big == B) \
+        return packed ? launch_wf_variant<S, M, B, true>(ka, smem, sm_count, lc, st) : launch_wf_variant<S, M, B, false>(ka, smem, sm_count, lc, st);
     PTB_WF_CASE(false, false, false) PTB_WF_CASE(false, false, true) PTB_WF_CASE(false, true, false) PTB_WF_CASE(false, true, true)
     PTB_WF_CASE(true, false, false) PTB_WF_CASE(true, false, true) PTB_WF_CASE(true, true, false) PTB_WF_CASE(true, true, true)
 #undef PTB_WF_CASE
@@ -892,14 +946,20 @@ int launch_finalize_planes(const float* planes, int split_k, int width, int heig
     return (int)cudaGetLastError();
 }
 
-// Whole pixels as work items leave most path slots idle on small frames (and the last wave of a mid-size frame runs almost
-// empty): aim for at least 4 items per resident slot, items of at least one sample, at most 64 planes.
+// Whole pixels as work items leave path slots idle on small frames, and on mid-size frames the kernel ends on a long tail: the
+// slots finish their last items at different times while every CTA still pays for full-width scans.  The tail lasts about one
+// item, so it costs ~1 / (items per slot); pixels of very different cost (sky next to glass) make it worse.  Measured on a B200
+// (profiles/r02s_split.log): C2 (1920x1080, 64 spp, 6.8 pixels per slot) 22.6 ms as whole pixels, 20.7 ms in 8 planes; C3 (4K, 27
+// pixels per slot) gains nothing from planes and C5 (8K, 109 per slot) loses 1 % to the plane traffic.  Policy: about 40 work
+// items per resident slot (rounded to the nearest plane count), items of at least one sample, at most 64 planes — so the plane
+// buffer never exceeds 40 x slots x 12 bytes = 146 MB.
 int wf_split_factor(int sm_count, long long n_pix, int n_samples) {
     const long long slots = (long long)sm_count * PTB_WF_MIN_BLOCKS * WF_SLOTS;
-    if (n_pix >= 4 * slots || n_samples < 2) return 1;
-    long long k = (4 * slots + n_pix - 1) / n_pix;
+    if (n_samples < 2 || n_pix < 1) return 1;
+    long long k = (40 * slots + n_pix / 2) / n_pix;
     if (k > n_samples) k = n_samples;
     if (k > 64) k = 64;
+    if (k < 1) k = 1;
     return (int)k;
 }
 

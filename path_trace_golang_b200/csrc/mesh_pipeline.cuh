@@ -181,7 +181,7 @@ mp_shade_scan_kernel(const __grid_constant__ KernelArgs ka, const __grid_constan
             live[k] = d2 != 0u && d2 != kDepDead;
             alive |= d2 != kDepDead;
         }
-        scan_analytic<BIG>(c_scene, sk, s_obj, ray, best, bid);
+        scan_analytic<BIG, false>(c_scene, sk, s_obj, ray, best, bid);
 #pragma unroll
         for (int k = 0; k < WF_SG; ++k) {
             const int j = tid + k * WF_THREADS;

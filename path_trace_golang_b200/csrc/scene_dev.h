@@ -55,6 +55,9 @@ constexpr int kBoxGroup = PTB_BOX_GROUP;
 #endif
 constexpr int kSphereGroup = PTB_SPHERE_GROUP;
 constexpr int kMaxExitTyped = 64;
+// Scenes with at least this many spheres in the typed sphere run get the kernel instantiation that tests a thread's two rays
+// against a sphere in packed arithmetic (integrator.cu "two rays per instruction"): below it, building the pairs costs more than it saves.
+constexpr int kPackedSphereMin = 6;
 
 // Scan tables that fit travel as kernel parameters; larger worlds use the BIG instantiation (tables in global memory).
 constexpr int kTabFloats = 1920;                 // 7.5 KB: e.g. 256 boxes + 64 spheres + the typed exit-search copies
@@ -169,13 +172,13 @@ enum StatWord {
 // it has opted into and the resident CTAs per SM for the last shared-memory size asked for.
 struct LaunchCache {
     struct Entry { size_t smem_optin = 0, smem_occ = ~(size_t)0; int blocks_per_sm = 0; };
-    Entry wf[8];                 // integrate_wf_kernel<STATS, MESH, BIG>
+    Entry wf[16];                // integrate_wf_kernel<STATS, MESH, BIG, PK>
     Entry mp[4];                 // mp_shade_scan_kernel<STATS, BIG>
 };
 
 // launchers (integrator.cu / primary_fp64.cu)
 int launch_integrator(const KernelArgs& ka, bool stats, void* stream);          // pixel-per-lane megakernel (small worlds only)
-int launch_integrator_wf(const KernelArgs& ka, bool stats, bool big, int sm_count, LaunchCache* cache, void* stream);
+int launch_integrator_wf(const KernelArgs& ka, bool stats, bool big, bool packed, int sm_count, LaunchCache* cache, void* stream);
 // mesh scenes: the wavefront across kernels.  Launches iteration after iteration on `stream` and WAITS for completion in
 // steps (the host reads an "alive" flag a few iterations behind): returns when the frame is complete.
 int launch_mesh_pipeline(const KernelArgs& ka, bool stats, bool big, int sm_count, LaunchCache* cache, MeshPipe& mp, void* stream);

@@ -379,7 +379,7 @@ struct ScanK {
 
 // Closest hit of WF_SG rays over the analytic world (renderer.go:292-302): every record of the per-type scan tables is tested
 // against all the rays as it is loaded (warp-uniform loops; operands from the constant bank via LDCU unless BIG).
-template <bool BIG>
+template <bool BIG, bool PK>
 __device__ __forceinline__ void scan_analytic(const SceneK& sc, const ScanK& k_, const DevObj* __restrict__ s_obj, const RayK (&ray)[WF_SG],
                                               float (&best)[WF_SG], int (&bid)[WF_SG]) {
     for (int gi = 0; gi < k_.n_box_groups; ++gi) {              // kBoxGroup boxes per trip, 6 floats each (scene_dev.h)
@@ -406,14 +406,29 @@ __device__ __forceinline__ void scan_analytic(const SceneK& sc, const ScanK& k_,
             if (hit_plane1(py, ray[k], 0.001f, best[k], t)) { best[k] = t; bid[k] = k_.n_box + i; }
         }
     }
-    for (int gi = 0; gi < k_.n_sphere_groups; ++gi) {
+    if constexpr (PK) {                                         // the two rays of the thread per instruction (integrator.cu "two rays per instruction")
+        static_assert(WF_SG == 2, "the packed sphere test pairs the two rays of a thread");
+        const RayP rp = pair_rays(ray[0], ray[1]);
+        for (int gi = 0; gi < k_.n_sphere_groups; ++gi) {
 #pragma unroll
-        for (int u = 0; u < kSphereGroup; ++u) {
-            const float4 sp = tab_ld4<BIG>(sc, k_.sphere_off4 + gi * kSphereGroup + u);
+            for (int u = 0; u < kSphereGroup; ++u) {
+                const float4 sp = tab_ld4<BIG>(sc, k_.sphere_off4 + gi * kSphereGroup + u);
+                float t[2]; bool h[2];
+                hit_sphere_pair(sp.x, sp.y, sp.z, sp.w, rp, 0.001f, best, t, h);
 #pragma unroll
-            for (int k = 0; k < WF_SG; ++k) {
-                float t;
-                if (hit_sphere4(sp.x, sp.y, sp.z, sp.w, ray[k], 0.001f, best[k], t)) { best[k] = t; bid[k] = k_.sphere_base + gi * kSphereGroup + u; }
+                for (int k = 0; k < 2; ++k) if (h[k]) { best[k] = t[k]; bid[k] = k_.sphere_base + gi * kSphereGroup + u; }
+            }
+        }
+    } else {
+        for (int gi = 0; gi < k_.n_sphere_groups; ++gi) {
+#pragma unroll
+            for (int u = 0; u < kSphereGroup; ++u) {
+                const float4 sp = tab_ld4<BIG>(sc, k_.sphere_off4 + gi * kSphereGroup + u);
+#pragma unroll
+                for (int k = 0; k < WF_SG; ++k) {
+                    float t;
+                    if (hit_sphere4(sp.x, sp.y, sp.z, sp.w, ray[k], 0.001f, best[k], t)) { best[k] = t; bid[k] = k_.sphere_base + gi * kSphereGroup + u; }
+                }
             }
         }
     }
@@ -429,7 +444,7 @@ __device__ __forceinline__ void scan_analytic(const SceneK& sc, const ScanK& k_,
     }
 }
 
-template <bool STATS, bool MESH, bool BIG>
+template <bool STATS, bool MESH, bool BIG, bool PK>
 __global__ void __launch_bounds__(WF_THREADS, PTB_WF_MIN_BLOCKS)
 integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
     const FrameParams& fp = ka.fp;
@@ -489,7 +504,7 @@ integrate_wf_kernel(const __grid_constant__ KernelArgs ka) {
                 ray[k] = make_ray(f3(ov.x, ov.y, ov.z), f3(dv.x, dv.y, dv.z));
                 best[k] = FLT_MAX; bid[k] = -1;
             }
-            scan_analytic<BIG>(c_scene, sk, s_obj, ray, best, bid);
+            scan_analytic<BIG, PK>(c_scene, sk, s_obj, ray, best, bid);
             if (MESH) {
                 // EXTENSION: triangle meshes, tested after the analytic objects (bvh.cuh).  Only rays that reach the meshes'
                 // bounds before their analytic hit (or whose traversal was suspended) are traversed, and they are compacted

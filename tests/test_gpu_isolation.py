@@ -66,8 +66,11 @@ def test_large_world_matches_oracle(n, box_every, ctx, oracle_mod):
     # thousands of pixel-sized spheres: far more silhouette pixels than in the shipped scenes, where binary32 with approximate
     # reciprocals and the binary32 oracle may decide hit / miss differently (measured 0.990 with 2 000 spheres; shipped scenes 0.998+)
     assert ok >= 0.98
+    # counters: 1 % of the oracle's, plus an allowance for the paths that diverged (each changes a counter by a few units; rare
+    # events such as exit scans — ~450 in this frame — would otherwise be held to +-10 while ~370 paths differ)
+    n_div = (1.0 - ok) * W * H
     for k in ["segments", "exit_scans", "scatters", "end_sky", "end_emissive"]:
-        assert abs(st[k] - ost[k]) <= 0.01 * max(ost[k], 1000), (k, st[k], ost[k])
+        assert abs(st[k] - ost[k]) <= 0.01 * ost[k] + 0.05 * n_div + 5, (k, st[k], ost[k])
 
 
 def test_parameter_table_boundary_matches_global_tables(ctx, oracle_mod, monkeypatch):
@@ -88,6 +91,29 @@ def test_parameter_table_boundary_matches_global_tables(ctx, oracle_mod, monkeyp
     ora = oracle_mod.OracleScene(doc)
     ref, _ = ora.render_sum(320, 180, 4, 6, seed=8, precision=32)
     assert (np.abs(small - ref) <= 4e-3 * np.maximum(1.0, np.abs(ref))).all(axis=2).mean() >= 0.99
+
+
+def test_packed_sphere_instantiation_matches_scalar(ctx, host_scenes, monkeypatch):
+    """Sphere-rich scenes run the instantiation that tests a thread's two rays against a sphere in packed binary32 arithmetic
+    (integrator.cu "two rays per instruction"; chosen by kPackedSphereMin, forced here with PTB_PACKED).  Each packed half is the
+    same round-to-nearest operation as the scalar form, so the sums must agree; the selection itself is checked by kernel name."""
+    cfg = ctx.cfg(480, 270, 8, 10, seed=21)
+    ctx.upload(host_scenes["metal_glass_room"])                    # 2 spheres: scalar
+    ctx.render_accum(cfg)
+    assert ctx.last_kernel() == "integrate_wf_kernel<0, 0, 0, 0>"
+    ctx.upload(host_scenes["test_scene"])                          # 11 spheres: packed
+    auto = ctx.render_accum(cfg)
+    assert ctx.last_kernel() == "integrate_wf_kernel<0, 0, 0, 1>"
+    monkeypatch.setenv("PTB_PACKED", "0")
+    scalar = ctx.render_accum(cfg)
+    assert ctx.last_kernel() == "integrate_wf_kernel<0, 0, 0, 0>"
+    monkeypatch.setenv("PTB_PACKED", "1")
+    packed = ctx.render_accum(cfg)
+    monkeypatch.delenv("PTB_PACKED")
+    assert (packed == auto).all()
+    same = (packed == scalar).all(axis=2).mean()
+    print(f"packed vs scalar sphere test: {same:.6f} of the pixels bit-identical")
+    assert same == 1.0
 
 
 def test_small_scene_then_large_scene_same_process(host_scenes):
