@@ -441,8 +441,13 @@ def main():
         flat = sc.flat()
         h2d = 8 * (flat.n_obj * 8 + flat.n_mat * 12) + 512          # flattened SoA + camera/sky structs (bytes, approx. exact)
         tr = traffic_record(args.workload)
-        split_k = 1                                                 # (frames of >= 1.2 M pixels are not split: 1 launch per frame)
-        per_rank_launches = 1 if (world == 1 or args.partition == "rows") else 2
+        # kernels of libptb200.so per rank and step: the integrator (+ finalize_planes_kernel when the frame is rendered as
+        # (pixel, sample sub-range) work items), then the exchange: peer = reduce_finalize_slice_kernel +
+        # peer_wait_done_kernel; scatter / reduce = NCCL + finalize_kernel
+        frame_kernels = kernel_name.split(" + ")
+        exchange_kernels = [] if (world == 1 or args.partition == "rows") else (
+            ["reduce_finalize_slice_kernel", "peer_wait_done_kernel"] if args.exchange == "peer" else ["finalize_kernel"])
+        per_rank_launches = len(frame_kernels) + len(exchange_kernels)
         out = {
             "metric": "Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -455,7 +460,7 @@ def main():
                                           f"{tr['source']} ({tr['what']}; that launch traced {tr.get('spp_captured')} spp — the scene is on chip, so the bytes do not grow with "
                                           f"spp); read from profiles/traffic.json at run time") if tr else
                                          "no ncu capture recorded in profiles/traffic.json",
-                         "kernel": kernel_name, "kernel_ms": kernel_ms,
+                         "kernel": frame_kernels[0], "kernel_ms": kernel_ms,
                          "flops_per_sample": fps, "simt_lane_utilisation": simt_util,
                          "peak_source": "measured here: ptb_measure_fp32_peak (FFMA microbenchmark, 2 flop/FMA); "
                                         "MEASURED_PEAKS.json has no fp32 entry; nominal 148x128x2x1.965 GHz = 74.5",
@@ -466,10 +471,9 @@ def main():
                     "d2h_bytes_per_step": W * H * 4, "ms_per_step": e2e_s / args.steps * 1e3,
                     "api": "engine.RenderInto(scene, cfg, host image)" if world == 1 else
                            "scene upload + dist.render_partition + NCCL reduce + epilogue + D2H on rank 0"},
-            "gpu_launches": args.steps * per_rank_launches * world * split_k,
-            "gpu_launches_note": f"{per_rank_launches} kernel(s) of libptb200.so per rank and step in timed region 1 ({kernel_name}"
-                                 + (" + reduce_finalize_slice_kernel" if per_rank_launches == 2 and args.exchange == "peer" else
-                                    " + finalize_kernel" if per_rank_launches == 2 else "") + f") x {world} rank(s); the L2 flush is a torch memset",
+            "gpu_launches": args.steps * per_rank_launches * world,
+            "gpu_launches_note": f"{per_rank_launches} kernel(s) of libptb200.so per rank and step in timed region 1 ("
+                                 + " + ".join(frame_kernels + exchange_kernels) + f") x {world} rank(s); the L2 flush is a torch memset",
             "clocks": clocks,
         }
         if bvh["n_triangles"]:
@@ -486,7 +490,7 @@ def main():
             out["roofline"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak or 6650.0, "unit": "GB/s",
                                "frac": ach / (hbm_peak or 6650.0),
                                "traffic": (tr["dram_bytes_read"] + tr["dram_bytes_write"]) if tr else None,
-                               "kernel": kernel_name,
+                               "kernel": frame_kernels[0],
                                "kernel_ms": kernel_ms, "bytes_per_sample": bytes_per_sample,
                                "nodes_per_ray": st["bvh_nodes_visited"] / st["segments"], "tris_per_ray": st["bvh_tris_tested"] / st["segments"],
                                "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if hbm_peak else "fallback 6.65 TB/s (of fallback)",

@@ -250,8 +250,10 @@ int ptb_primary_hits(ptb_ctx* ctx, const ptb_cfg* cfg, double xi_u, double xi_v,
 /* Counters of the last render that ran with PTB_FLAG_STATS (last_render_ms is always valid). */
 int ptb_get_stats(ptb_ctx* ctx, ptb_stats* out);
 int ptb_get_bvh_info(ptb_ctx* ctx, ptb_bvh_info* out);
-/* Symbol of the integrator kernel the last render of ctx launched, as ncu prints it (e.g. "integrate_wf_kernel<0, 0, 0>":
- * counting build?, mesh traversal?, global-memory tables?).  Valid until the next render on ctx. */
+/* Symbols of the kernels the last render of ctx launched for the frame, as ncu prints them, joined by " + ": the integrator
+ * (e.g. "integrate_wf_kernel<0, 0, 0, 1>": counting build?, mesh traversal?, global-memory tables?, packed two-ray sphere
+ * test?) and, when the frame was rendered as (pixel, sample sub-range) work items, "finalize_planes_kernel".  Valid until the
+ * next render on ctx. */
 const char* ptb_last_kernel(ptb_ctx* ctx);
 
 /* ---- single-process multi-GPU (what a Go host that owns every GPU of the box calls; one process per GPU + NCCL is the

@@ -328,6 +328,7 @@ int render_launch(ptb_ctx* c, const ptb_cfg* cfg, const SplitPlan& plan, float* 
             e = launch_mesh_pipeline(ka, stats, hs.big, c->prop.multiProcessorCount, &c->launch_cache, mp, c->stream);
         } else
         e = launch_integrator_wf(ka, stats, hs.big, packed, c->prop.multiProcessorCount, &c->launch_cache, stream);
+        if (plan.total > 1) c->last_kernel += " + finalize_planes_kernel";
         if (!e && plan.total > 1) e = launch_finalize_planes(c->d_planes, k, W, R, cfg->samples_per_px, d_accum, resume ? 1 : 0, d_rgba, stream);
     }
     if (e) return fail(c, PTB_ERR_CUDA, "integrator launch: %s", cudaGetErrorString((cudaError_t)e));
