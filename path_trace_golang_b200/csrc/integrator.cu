@@ -271,7 +271,8 @@ __device__ __forceinline__ RayP pair_rays(const RayK& r0, const RayK& r1) {
 __device__ __forceinline__ void hit_sphere_pair(float cx, float cy, float cz, float r2, const RayP& r, float tmin, const float (&tmax)[2],
                                                 float (&t_out)[2], bool (&hit)[2]) {
     const P2 ox = add2(dup2(cx), r.no[0]), oy = add2(dup2(cy), r.no[1]), oz = add2(dup2(cz), r.no[2]);     // c - o
-    const P2 nhb = fma2(oz, r.d[2], fma2(oy, r.d[1], mul2(ox, r.d[0])));                                    // -hb
+    // -hb, contracted as nvcc contracts the scalar `ocx * dx + ocy * dy + ocz * dz`: fma(z, fma(x, (y product)))
+    const P2 nhb = fma2(oz, r.d[2], fma2(ox, r.d[0], mul2(oy, r.d[1])));
     const P2 c = fma2(oz, oz, fma2(oy, oy, fma2(ox, ox, dup2(-r2))));
     const P2 disc = fma2(nhb, nhb, mul2(r.na, c));
     const P2 sq = pk2(sqrt_(lo2(disc)), sqrt_(hi2(disc)));
