@@ -307,6 +307,13 @@ int ptb_peer_reduce_finalize(ptb_peer* p, int32_t width, int32_t height, int32_t
  * or a negative PTB_ERR_* (message: ptb_last_error(NULL)). */
 int ptb_scene_device_order(const ptb_scene* scene, int32_t* order, int32_t cap, int32_t counts[6]);
 
+/* Test hook, host only (no CUDA call): the launch plan the wavefront integrator would use on a device with sm_count SMs.
+ * Returns k = the number of sample planes a frame of n_pixels pixels and n_samples samples per pixel is rendered in (work items
+ * are (pixel, 1/k of its sample range); 1 = whole pixels), chosen for about 40 work items per resident path slot; if packed is
+ * not NULL, *packed = 1 when a scene with n_spheres spheres in its typed sphere run gets the kernel instantiation with the packed
+ * two-ray sphere test, else 0.  Negative PTB_ERR_* on bad arguments. */
+int ptb_launch_plan(int32_t sm_count, int64_t n_pixels, int32_t n_samples, int32_t n_spheres, int32_t* packed);
+
 /* Test hook, host only (no CUDA call): builds the BVH over n_tri world-space triangles (9 floats each) exactly as
  * ptb_scene_upload does and checks the emitted node array: every child box (centre/half extent in binary32) contains all
  * the triangles below it, every triangle sits in exactly one leaf, links and counts are consistent.

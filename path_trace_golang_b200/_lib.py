@@ -111,6 +111,7 @@ SYMBOLS = {
     "ptb_get_bvh_info": (C.c_int, [C.c_void_p, C.POINTER(PtbBvhInfo)]),
     "ptb_measure_fp32_peak": (C.c_int, [C.c_void_p, _dp]),
     "ptb_scene_device_order": (C.c_int, [C.POINTER(PtbScene), C.POINTER(C.c_int32), C.c_int32, C.POINTER(C.c_int32)]),
+    "ptb_launch_plan": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "ptb_bvh_selfcheck": (C.c_int64, [C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "ptb_bvh_build": (C.c_int, [C.POINTER(C.c_float), C.c_int64, C.POINTER(PtbBvh)]),
     "ptb_bvh_free": (None, [C.POINTER(PtbBvh)]),

@@ -1438,6 +1438,12 @@ int ptb_scene_device_order(const ptb_scene* s, int32_t* order, int32_t cap, int3
     return hs.n_obj;
 }
 
+int ptb_launch_plan(int32_t sm_count, int64_t n_pixels, int32_t n_samples, int32_t n_spheres, int32_t* packed) {
+    if (sm_count < 1 || n_pixels < 1 || n_samples < 1 || n_spheres < 0) return fail(nullptr, PTB_ERR_INVALID, "bad argument");
+    if (packed) *packed = n_spheres >= kPackedSphereMin ? 1 : 0;
+    return wf_split_factor(sm_count, (long long)n_pixels, n_samples);
+}
+
 int64_t ptb_bvh_selfcheck(const float* tri_vertices, int64_t n_tri, int64_t* n_nodes, int32_t* max_depth) {
     if (!tri_vertices || n_tri < 1) return PTB_ERR_INVALID;
     std::vector<int32_t> zeros((size_t)n_tri, 0);

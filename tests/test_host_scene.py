@@ -194,3 +194,44 @@ def test_device_order_keeps_the_tie_rules():
         n_diel = sum(1 for o in doc["objects"] if o["type"] in ("sphere", "sphere_light", "plane", "box")
                      and any(m.get("id") == o.get("material_id") and m.get("type") == "dielectric" for m in doc["materials"]))
         assert n_dbox + n_dsph in (0, n_diel)
+
+
+def test_launch_plan_policy():
+    """Host-only hook ptb_launch_plan: the work-item size (sample planes per pixel, about 40 items per resident path slot of a
+    148-SM device: 148 x 4 CTAs x 512 slots) and the per-scene choice of the packed-sphere instantiation, on the BASELINE
+    configs and the reference's UI sizes (DESIGN 3.1 "Work-item size", 3.2 "Two rays per instruction")."""
+    import ctypes as C
+    import json
+    from path_trace_golang_b200 import _lib, scene
+    L = _lib.lib()
+
+    def plan(w, h, spp, spheres=0, sm=148):
+        packed = C.c_int32(-1)
+        k = L.ptb_launch_plan(sm, w * h, spp, spheres, C.byref(packed))
+        assert k >= 1, L.ptb_last_error(None)
+        return k, packed.value
+
+    assert plan(3840, 2160, 256)[0] == 1                  # C3: 27 whole pixels per slot already
+    assert plan(7680, 4320, 1024)[0] == 1                 # C5
+    assert plan(1920, 1080, 64)[0] == 6                   # C2: 6.8 pixels per slot -> 6 planes (measured 22.6 -> 20.8 ms)
+    assert plan(640, 360, 16)[0] == 16                    # C1: capped by the samples
+    assert plan(400, 225, 20)[0] == 20 and plan(800, 450, 50)[0] == 34      # the reference's preview / final sizes (util.go:25-39)
+    assert plan(1920, 1080, 8)[0] == 6 and plan(1920, 1080, 4)[0] == 4      # a sample-range partition of C2 over 8 / 16 GPUs
+    assert plan(64, 64, 1000)[0] == 64                    # never more than 64 planes
+    assert plan(3840, 2160, 1)[0] == 1
+    # the plane buffer stays bounded: k x pixels x 12 bytes <= 40 x slots x 12 bytes (+ rounding)
+    for (w, h) in [(1280, 720), (1920, 1080), (2560, 1440), (3840, 2160), (5120, 2880)]:
+        k, _ = plan(w, h, 4096)
+        assert k * w * h <= 41 * 148 * 4 * 512 + w * h // 2
+    # instantiation by sphere count of the typed sphere run (the five shipped scenes: 8 / 11 / 2 / 24 / 17 spheres)
+    counts = {}
+    for name in ("example_simple", "test_scene", "metal_glass_room", "test_comprehensive", "gpu_showcase"):
+        sc = scene.Parse(open(scene_path(name)).read())                  # (kept alive: the flat view points into it)
+        flat = sc.flat()
+        buf, c6 = (C.c_int32 * 600)(), (C.c_int32 * 6)()
+        assert L.ptb_scene_device_order(C.byref(flat), buf, 600, c6) >= 0
+        counts[name] = c6[2]
+        assert plan(1920, 1080, 64, c6[2])[1] == (1 if c6[2] >= 6 else 0)
+    assert counts["metal_glass_room"] == 2 and plan(3840, 2160, 256, counts["metal_glass_room"])[1] == 0      # C3: scalar kernel
+    assert counts == {"example_simple": 8, "test_scene": 11, "metal_glass_room": 2, "test_comprehensive": 24, "gpu_showcase": 17}
+    assert L.ptb_launch_plan(0, 100, 1, 0, None) < 0 and L.ptb_launch_plan(148, 0, 1, 0, None) < 0
