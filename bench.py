@@ -147,8 +147,9 @@ def parity_block(ctx, workload, W, H, depth):
     """The run's own parity evidence (outside every timed region; the oracle is the checker, never the thing measured):
     primary-hit ids/t of the workload's frame, bit-exact, and the converged block-mean comparison of tests/test_gpu_converged.py."""
     import numpy as np
-    out = {"oracle": "oracle/ (C++ restatement of the Go CPU path; pinned by hand-derived KATs only: the Go toolchain is absent, "
-                     "the reference ships no golden vectors — go/tools/gen_golden.go produces them on a box with Go)"}
+    out = {"oracle": "oracle/ (C++ restatement of the Go CPU path; pinned by hand-derived KATs and by bit-for-bit agreement with an "
+                     "independent Python restatement, oracle/goref.py; the Go toolchain is absent and the reference ships no golden "
+                     "vectors — go/cmd/gengolden produces them on a box with Go)"}
     ora = load_oracle(workload)
     ids, t = ctx.primary_hits(W, H, 0.5, 0.5)
     oids, ot = ora.primary_hits(W, H, 0.5, 0.5)

@@ -9,8 +9,13 @@
  *
  * PARITY UNPINNED: the reference ships no tests, no golden vectors and no
  * stored renders, and its Go toolchain is absent here, so this restatement
- * cannot be pinned against reference outputs.  It is pinned only against
- * hand-derived known-answer vectors (tests/golden/, tests/test_oracle_kat.py).
+ * cannot be pinned against reference outputs.  It is pinned against
+ * hand-derived known-answer vectors (tests/golden/, tests/test_oracle_kat.py)
+ * and against a second, independent restatement of the same Go sources in
+ * plain Python (oracle/goref.py): tests/test_oracle_crosscheck.py demands
+ * bit-for-bit agreement of worlds, cameras, primary hits, per-pixel radiance
+ * sums and event counters on the five shipped scenes and on random scenes.
+ * go/cmd/gengolden produces the reference-side vectors on a box with Go.
  */
 #ifndef PTB_ORACLE_H
 #define PTB_ORACLE_H

@@ -2,7 +2,8 @@
 
 TEST INFRASTRUCTURE ONLY — see oracle/oracle.h.  Import from tests/, from
 __graft_entry__.smoke() and from bench.py's cpu_baseline / --impl reference legs,
-never from the product package.  PARITY UNPINNED (no reference golden vectors).
+never from the product package.  PARITY UNPINNED (no reference golden vectors); cross-checked bit for bit
+against the independent Python restatement oracle/goref.py (tests/test_oracle_crosscheck.py).
 """
 from __future__ import annotations
 
